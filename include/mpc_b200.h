@@ -1,0 +1,188 @@
+/*
+ * mpc_b200.h -- C ABI of libmpc_b200.so: the B200 (sm_100a) point-set hot path of
+ * ssr0512/Markov-Process-Analysis-on-Point-Cloud.
+ *
+ * The reference has no FFI: its seam is the set of Python free functions and nn.Modules in
+ * R/modules/pointnet2_utils.py and R/modules/repsurface_utils.py (R = Markov_Process_Analysis_on_Point_Cloud/).
+ * Each entry point below names the reference function whose arithmetic it replaces (file:line).  The
+ * Python host side (markov-process-analysis-on-point-cloud_b200/pointnet2_utils.py) mirrors the reference
+ * signatures on top of this ABI; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions (every function):
+ *   - all pointers are DEVICE pointers on the current device; tensors are dense row-major ("contiguous");
+ *   - float data is IEEE binary32, indices are int64 (the reference's API dtype);
+ *   - the caller owns every buffer (outputs and scratch included); nothing is allocated, nothing
+ *     synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - re-entrant, no global state: safe for one process per GPU under torchrun, and capturable into a
+ *     CUDA graph;
+ *   - returns 0 on success, a positive cudaError_t if a launch failed, or a negative MPC_ERR_* code if
+ *     the arguments are rejected (nothing is launched in that case).
+ *   - indices that are out of range are never dereferenced: gather-type kernels clamp them into range
+ *     (the reference would raise from ATen; the Python wrappers can validate with MPC_CHECK_INDEX=1).
+ */
+#ifndef MPC_B200_H_
+#define MPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_OK 0
+#define MPC_ERR_INVALID (-1)     /* bad sizes / null pointers */
+#define MPC_ERR_UNSUPPORTED (-2) /* shape outside what the kernels cover (documented per function) */
+
+typedef void* mpc_stream_t; /* cudaStream_t */
+
+/* Library / build identification.  mpc_version() = 10000*major + 100*minor + patch. */
+int mpc_version(void);
+/* Compute capability the kernels were compiled for (1000 = sm_100a). */
+int mpc_compiled_arch(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Farthest point sampling.  Replaces farthest_point_sample, R/modules/pointnet2_utils.py:84-109
+ * (== R/modules/repsurface_utils.py:150-172).
+ *   xyz [B,N,C] f32, start [B] i64 (the reference draws it with torch.randint on the CPU generator, :96;
+ *   the host passes it in), out [B,npoint] i64.
+ * Bit-exact contract: running min distance starts at 1e10; dist = ((dx*dx + dy*dy) + dz*dz) with
+ * separately rounded mul/add (no fma); update on strict <; next = argmax, lowest index on ties.
+ * C == 3: one persistent CTA per cloud for N <= 8192, one thread-block cluster (<= 16 CTAs, DSMEM argmax
+ * exchange) per cloud for N <= 262144.  C != 3 (feature-space FPS): N * 4 bytes of shared memory, N <= 50000.
+ * Otherwise MPC_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, int64_t B, int64_t N, int64_t C,
+                int64_t npoint, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * k nearest neighbours.  Replaces square_distance + knn_point, R/modules/pointnet2_utils.py:190-222, and
+ * (with K = 3) the three_nn of PointNetFeaturePropagation, :899-901.
+ *   ref [B,N,C] f32 (the reference's `xyz`), qry [B,S,C] f32 (`new_xyz`),
+ *   dist_out [B,S,K] f32 ascending (may be NULL), idx_out [B,S,K] i64.
+ * Bit-exact contract: d = ((-2*dot) + |q|^2) + |r|^2, dot = fma chain over c = 0..C-1 from 0, norms
+ * sequential non-fused; ascending (d, index) order -- equal distances resolve to the lower index (torch.topk
+ * leaves that order undefined).  1 <= K <= 32, K <= N, C <= 1024; else MPC_ERR_INVALID / UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_knn_f32(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, int64_t B,
+                int64_t N, int64_t S, int64_t C, int64_t K, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Ball query.  Replaces query_ball_point, R/modules/pointnet2_utils.py:112-134.
+ *   xyz [B,N,C], new_xyz [B,S,C], idx_out [B,S,nsample] i64; r2 = radius^2 rounded to f32.
+ * First `nsample` indices n (ascending) with NOT(d > r2), d as in mpc_knn_f32; padded with the first hit;
+ * a query without any hit yields N in every slot (reference quirk, preserved).
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_ball_query_f32(const float* xyz, const float* new_xyz, int64_t* idx_out, float r2, int64_t B,
+                       int64_t N, int64_t S, int64_t C, int64_t nsample, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Gather / group.  Replaces index_points, R/modules/pointnet2_utils.py:64-81 (idx rank 2 "gathering" or
+ * rank 3 "grouping": pass M = S or M = S*K).
+ *   points [B,N,C] f32, idx [B,M] i64, out [B,M,C] f32:  out[b,m,:] = points[b, idx[b,m], :].
+ * mpc_gather_bwd_f32 is what autograd derives (index_put_ accumulate): it zero-fills grad_points [B,N,C]
+ * and adds grad_out rows into it with red.global (run-to-run fp32 summation order is not fixed).
+ * mpc_gather_i64 is the same gather for an int64 payload with C = 1 (the composed FPS index chains of
+ * Fuse.forward, :617-628).
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_gather_f32(const float* points, const int64_t* idx, float* out, int64_t B, int64_t N, int64_t M,
+                   int64_t C, mpc_stream_t stream);
+int mpc_gather_bwd_f32(const float* grad_out, const int64_t* idx, float* grad_points, int64_t B, int64_t N,
+                       int64_t M, int64_t C, mpc_stream_t stream);
+int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* out, int64_t B, int64_t N, int64_t M,
+                   mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Markov state transition.  Replaces upsample, R/modules/pointnet2_utils.py:13-50 (dense [B,S,N,C]
+ * scatter + sum + count_nonzero) with its sparse form D^-1 A^T X:
+ *   out[b,n,:] = (sum over s with n in idx[b,s,:] of points[b,s,:]) / cnt[b,n]
+ *   cnt[b,n]   = #{s : n in idx[b,s,:] and points[b,s,0] != 0}, 0 -> 1;  a repeated n inside one row counts once.
+ *   points [B,S,C], idx [B,S,K] i64 (values in [0,N)), out [B,N,C], cnt [B,N] f32 (kept for backward).
+ * Backward (cnt is a constant of the graph): grad_points[b,s,:] = sum_k grad_out[b,idx[b,s,k],:] / cnt[b,idx[b,s,k]].
+ * K <= 32.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_transition_fwd_f32(const float* points, const int64_t* idx, float* out, float* cnt, int64_t B,
+                           int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
+int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, const float* cnt, float* grad_points,
+                           int64_t B, int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * three_interpolate.  Replaces R/modules/pointnet2_utils.py:903-906.
+ *   dist [B,N,3] f32 and idx [B,N,3] i64 from mpc_knn_f32(K=3); points2 [B,S,C];
+ *   weight_out [B,N,3] = (1/(d+1e-8)) / sum_i (1/(d_i+1e-8)); out [B,N,C] = sum_i w_i * points2[b,idx_i,:].
+ * Backward: grad_points2 [B,S,C] zero-filled, += w_i * grad_out[b,n,:] at row idx_i.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_three_interpolate_fwd_f32(const float* points2, const float* dist, const int64_t* idx,
+                                  float* weight_out, float* out, int64_t B, int64_t N, int64_t S, int64_t C,
+                                  mpc_stream_t stream);
+int mpc_three_interpolate_bwd_f32(const float* grad_out, const float* weight, const int64_t* idx,
+                                  float* grad_points2, int64_t B, int64_t N, int64_t S, int64_t C,
+                                  mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Difference-wise attention core, feature branch.  Replaces the materialised [B,S,K,C] chain of
+ * LocalTrans.forward with xyz=False, R/modules/pointnet2_utils.py:553-569 (gather k, gather v, q - k,
+ * per-channel softmax over K of energy/sqrt(C), minus its own sum over K, times v, max over K).
+ *   q   [B,S,C] rows with stride ldq floats; kf, vf [B,N,C] rows with stride ldkv floats (so q/k/v may be
+ *   column slices of one fused projection buffer); idx [B,S,K] i64; ctx_out [B,S,C] dense.
+ * Backward recomputes the softmax: given grad_ctx [B,S,C] it writes grad_q [B,S,C] (stride ldgq) and
+ * ACCUMULATES (red.global) into grad_kf / grad_vf [B,N,C] (stride ldgkv), which the caller zero-fills.
+ * C % 4 == 0, C <= 1024, K <= 32 (K = 8 is the specialised fast path).
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, const float* vf, int64_t ldkv,
+                          const int64_t* idx, float* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K,
+                          int64_t C, mpc_stream_t stream);
+int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t ldq, const float* kf,
+                          const float* vf, int64_t ldkv, const int64_t* idx, float* grad_q, int64_t ldgq,
+                          float* grad_kf, float* grad_vf, int64_t ldgkv, int64_t B, int64_t S, int64_t N,
+                          int64_t K, int64_t C, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Difference-wise attention core, coordinate branch.  Replaces LocalTrans.forward with xyz=True,
+ * R/modules/pointnet2_utils.py:520-544: k, v = W (neighbour - centre) + b computed on the fly from the
+ * Cin-channel differences (Cin = 3 in every live model, Cin <= 16 supported), q = Wq centre + bq, then the
+ * same core as above.  Nothing of size [B,S,K,C] is ever written.
+ *   feat [B,N,Cin]; center_idx [B,S] i64 or NULL (then S == N and centre s is point s); idx [B,S,K] i64;
+ *   wq,wk,wv [C,Cin] (nn.Linear layout), bq,bk,bv [C]; ctx_out [B,S,C].
+ * Backward: grad_w* [C,Cin] and grad_b* [C] are ACCUMULATED (caller zero-fills); grad_feat [B,N,Cin] may
+ * be NULL (coordinates are data in the reference's training scripts) else it is ACCUMULATED too.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_attn_xyz_fwd_f32(const float* feat, const int64_t* center_idx, const int64_t* idx, const float* wq,
+                         const float* bq, const float* wk, const float* bk, const float* wv, const float* bv,
+                         float* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
+                         mpc_stream_t stream);
+int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t* center_idx,
+                         const int64_t* idx, const float* wq, const float* bq, const float* wk,
+                         const float* bk, const float* wv, const float* bv, float* grad_wq, float* grad_bq,
+                         float* grad_wk, float* grad_bk, float* grad_wv, float* grad_bv, float* grad_feat,
+                         int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
+                         mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Shared-MLP block tail.  Replaces the BatchNorm1d-over-channels + LeakyReLU(0.2) of `Linear.forward`,
+ * R/modules/pointnet2_utils.py:413-425, on the [M,C] view (M = all leading axes), without the two
+ * permute().contiguous() copies of :420.
+ *   mpc_bn_stats_f32: stats[0:C] = mean, stats[C:2C] = biased variance of y over M rows (fp64 accumulation
+ *     in `scratch`, 2*C doubles, zero-filled by the call).  If non-NULL, running_mean / running_var [C] get
+ *     nn.BatchNorm1d's update (x = (1-momentum)*x + momentum*stat, unbiased variance) and
+ *     *num_batches_tracked (device int64) is incremented.
+ *   mpc_bn_act_fwd_f32: out = lrelu(gamma * (y - mean) * rsqrt(var + eps) + beta, slope); slope = 1 => no act.
+ *   mpc_bn_act_bwd_f32: given grad_out and the saved pre-norm y, writes grad_y [M,C] and grad_gamma/beta [C]
+ *     (train = 1: batch statistics take part in the gradient; train = 0: running statistics are constants).
+ *     scratch: 2*C doubles.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* running_var,
+                     int64_t* num_batches_tracked, float momentum, double* scratch, int64_t M, int64_t C,
+                     mpc_stream_t stream);
+int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, const float* gamma,
+                       const float* beta, float eps, float slope, float* out, int64_t M, int64_t C,
+                       mpc_stream_t stream);
+int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean, const float* var,
+                       const float* gamma, const float* beta, float eps, float slope, int train,
+                       float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, int64_t M,
+                       int64_t C, mpc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H_ */

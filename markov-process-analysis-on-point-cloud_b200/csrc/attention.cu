@@ -1,0 +1,469 @@
+// Difference-wise attention core of LocalTrans for sm_100a.  See include/mpc_b200.h (mpc_attn_*) for the
+// contract and the reference lines replaced (pointnet2_utils.py:518-569).
+//
+// The reference materialises ~9 tensors of shape [B,S,K,C] per call (gathered k, gathered v, energy, scaled
+// energy, softmax, row-sum, shifted attention, product, max).  Here one thread owns 4 channels (feature
+// branch) or 1 channel (coordinate branch) of one centre point, keeps the K neighbour values in registers and
+// writes only the [B,S,C] context; the backward recomputes the softmax instead of saving it.  Both are
+// gather-bound: per centre point they read K rows of k and v (L2-resident at the live sizes) with 128-bit
+// loads, so the roofline that applies is HBM/L2 bandwidth, not the tensor pipe.
+#include "common.cuh"
+
+namespace mpc {
+
+constexpr int AT = 256;
+constexpr int KMAX = 32;
+
+static inline unsigned attn_grid(int64_t work_items, int threads) {
+    int64_t g = ceil_div(work_items, threads);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// One channel of the core.  e[j] holds q - k_j on entry.  Returns ctx; fills a[j] (softmax) and O = sum a.
+template <int K>
+__device__ __forceinline__ float attn_channel(const float (&e)[K], const float (&v)[K], float sqrtc,
+                                              float (&a)[K], float& O, int& jstar) {
+    float s[K];
+    float m = -__int_as_float(0x7f800000);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        s[j] = __fdiv_rn(e[j], sqrtc);
+        m = fmaxf(m, s[j]);
+    }
+    float Z = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        a[j] = expf(s[j] - m);
+        Z += a[j];
+    }
+    O = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        a[j] = __fdiv_rn(a[j], Z);
+        O += a[j];
+    }
+    float best = -__int_as_float(0x7f800000);
+    jstar = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const float c = (a[j] - O) * v[j];
+        if (c > best) {  // first maximum, like torch.max(dim)
+            best = c;
+            jstar = j;
+        }
+    }
+    return best;
+}
+
+// Backward of one channel: given g = dL/dctx, the recomputed a, O, jstar: returns de[j] (w.r.t. energy q-k_j)
+// and dv (for v_{jstar}).  ctx = (a_{j*} - sum_i a_i) * v_{j*}.
+template <int K>
+__device__ __forceinline__ void attn_channel_bwd(float g, const float (&a)[K], float O, int jstar,
+                                                 const float (&v)[K], float sqrtc, float (&de)[K], float& dv) {
+    float vstar = 0.f, astar = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (j == jstar) {
+            vstar = v[j];
+            astar = a[j];
+        }
+    dv = g * (astar - O);
+    const float gv = g * vstar;
+    // dL/da_i = gv * (delta(i,j*) - 1);  softmax backward: ds_i = a_i * (da_i - sum_m a_m da_m)
+    const float dot = gv * astar - gv * O;  // sum_m a_m da_m
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const float da = (j == jstar ? gv : 0.f) - gv;
+        de[j] = __fdiv_rn(a[j] * (da - dot), sqrtc);
+    }
+}
+
+// ---- feature branch ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(AT)
+attn_feat_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ kf,
+                     const float* __restrict__ vf, int64_t ldkv, const int64_t* __restrict__ idx,
+                     float* __restrict__ ctx, int S, int N, int CV, float sqrtc, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * AT + threadIdx.x; t < total; t += (int64_t)gridDim.x * AT) {
+        const int64_t row = t / CV;
+        const int c4 = (int)(t - row * CV) * 4;
+        const int64_t b = row / S;
+        const int64_t* irow = idx + row * K;
+        float4 kk[K], vv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const size_t src = ((size_t)b * N + clamp_index(__ldg(irow + j), N)) * ldkv + c4;
+            kk[j] = __ldg(reinterpret_cast<const float4*>(kf + src));
+            vv[j] = __ldg(reinterpret_cast<const float4*>(vf + src));
+        }
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(q + row * ldq + c4));
+        float4 out;
+        float e[K], v[K], a[K], O;
+        int js;
+#define MPC_CH(comp)                                              \
+    _Pragma("unroll") for (int j = 0; j < K; ++j) {               \
+        e[j] = qq.comp - kk[j].comp;                              \
+        v[j] = vv[j].comp;                                        \
+    }                                                             \
+    out.comp = attn_channel<K>(e, v, sqrtc, a, O, js);
+        MPC_CH(x) MPC_CH(y) MPC_CH(z) MPC_CH(w)
+#undef MPC_CH
+        *reinterpret_cast<float4*>(ctx + row * (int64_t)CV * 4 + c4) = out;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(AT)
+attn_feat_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ q, int64_t ldq,
+                     const float* __restrict__ kf, const float* __restrict__ vf, int64_t ldkv,
+                     const int64_t* __restrict__ idx, float* __restrict__ gq, int64_t ldgq,
+                     float* __restrict__ gkf, float* __restrict__ gvf, int64_t ldgkv, int S, int N, int CV,
+                     float sqrtc, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * AT + threadIdx.x; t < total; t += (int64_t)gridDim.x * AT) {
+        const int64_t row = t / CV;
+        const int c4 = (int)(t - row * CV) * 4;
+        const int64_t b = row / S;
+        const int64_t* irow = idx + row * K;
+        int nb[K];
+        float4 kk[K], vv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            nb[j] = clamp_index(__ldg(irow + j), N);
+            const size_t src = ((size_t)b * N + nb[j]) * ldkv + c4;
+            kk[j] = __ldg(reinterpret_cast<const float4*>(kf + src));
+            vv[j] = __ldg(reinterpret_cast<const float4*>(vf + src));
+        }
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(q + row * ldq + c4));
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(gctx + row * (int64_t)CV * 4 + c4));
+        float4 dk[K];
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+        float e[K], v[K], a[K], de[K], O, dv;
+        int js;
+#define MPC_CH(comp, ci)                                                                   \
+    _Pragma("unroll") for (int j = 0; j < K; ++j) {                                        \
+        e[j] = qq.comp - kk[j].comp;                                                       \
+        v[j] = vv[j].comp;                                                                 \
+    }                                                                                      \
+    attn_channel<K>(e, v, sqrtc, a, O, js);                                                \
+    attn_channel_bwd<K>(gg.comp, a, O, js, v, sqrtc, de, dv);                              \
+    _Pragma("unroll") for (int j = 0; j < K; ++j) {                                        \
+        dq.comp += de[j];                                                                  \
+        dk[j].comp = -de[j];                                                               \
+    }                                                                                      \
+    {                                                                                      \
+        int n = nb[0];                                                                     \
+        _Pragma("unroll") for (int j = 1; j < K; ++j) n = (j == js) ? nb[j] : n;           \
+        red_add_f32(gvf + ((size_t)b * N + n) * ldgkv + c4 + ci, dv);      \
+    }
+        MPC_CH(x, 0) MPC_CH(y, 1) MPC_CH(z, 2) MPC_CH(w, 3)
+#undef MPC_CH
+        *reinterpret_cast<float4*>(gq + row * ldgq + c4) = dq;
+#pragma unroll
+        for (int j = 0; j < K; ++j) red_add_f32x4(gkf + ((size_t)b * N + nb[j]) * ldgkv + c4, dk[j]);
+    }
+}
+
+// ---- coordinate branch --------------------------------------------------------------------------------------------
+// thread = (centre row, channel c); blockDim.x is a multiple of C so a thread's channel (and its 3*CIN weights)
+// never changes across its grid-stride rows.
+template <int K, int CIN>
+__global__ void __launch_bounds__(256)
+attn_xyz_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ cidx,
+                    const int64_t* __restrict__ idx, const float* __restrict__ wq, const float* __restrict__ bq,
+                    const float* __restrict__ wk, const float* __restrict__ bk, const float* __restrict__ wv,
+                    const float* __restrict__ bv, float* __restrict__ ctx, int64_t rows, int S, int N, int C,
+                    int cin_rt, float sqrtc) {
+    const int cin = CIN > 0 ? CIN : cin_rt;
+    constexpr int CM = CIN > 0 ? CIN : 16;
+    const int Cb = C < 256 ? C : 256;  // channels per CTA; C > 256 is split along gridDim.y (C % 256 == 0)
+    const int c = blockIdx.y * Cb + threadIdx.x % Cb;
+    const int rpb = blockDim.x / Cb;
+    float Wq[CM], Wk[CM], Wv[CM];
+#pragma unroll
+    for (int i = 0; i < CM; ++i)
+        if (i < cin) {
+            Wq[i] = wq[c * cin + i];
+            Wk[i] = wk[c * cin + i];
+            Wv[i] = wv[c * cin + i];
+        }
+    const float Bq = bq[c], Bk = bk[c], Bv = bv[c];
+    for (int64_t row = (int64_t)blockIdx.x * rpb + threadIdx.x / Cb; row < rows; row += (int64_t)gridDim.x * rpb) {
+        const int64_t b = row / S;
+        const int cn = cidx ? clamp_index(__ldg(cidx + row), N) : (int)(row - b * S);
+        const float* cp = feat + ((size_t)b * N + cn) * cin;
+        float cen[CM];
+#pragma unroll
+        for (int i = 0; i < CM; ++i)
+            if (i < cin) cen[i] = __ldg(cp + i);
+        float qv = 0.f;
+#pragma unroll
+        for (int i = 0; i < CM; ++i)
+            if (i < cin) qv = fmaf(cen[i], Wq[i], qv);
+        qv += Bq;
+        float e[K], v[K], a[K], O;
+        int js;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float* np = feat + ((size_t)b * N + clamp_index(__ldg(idx + row * K + j), N)) * cin;
+            float kv = 0.f, vv = 0.f;
+#pragma unroll
+            for (int i = 0; i < CM; ++i)
+                if (i < cin) {
+                    const float d = __ldg(np + i) - cen[i];
+                    kv = fmaf(d, Wk[i], kv);
+                    vv = fmaf(d, Wv[i], vv);
+                }
+            e[j] = qv - (kv + Bk);
+            v[j] = vv + Bv;
+        }
+        ctx[row * C + c] = attn_channel<K>(e, v, sqrtc, a, O, js);
+    }
+}
+
+template <int K, int CIN>
+__global__ void __launch_bounds__(256)
+attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ feat,
+                    const int64_t* __restrict__ cidx, const int64_t* __restrict__ idx,
+                    const float* __restrict__ wq, const float* __restrict__ bq, const float* __restrict__ wk,
+                    const float* __restrict__ bk, const float* __restrict__ wv, const float* __restrict__ bv,
+                    float* __restrict__ gwq, float* __restrict__ gbq, float* __restrict__ gwk,
+                    float* __restrict__ gbk, float* __restrict__ gwv, float* __restrict__ gbv,
+                    float* __restrict__ gfeat, int64_t rows, int S, int N, int C, int cin_rt, float sqrtc) {
+    const int cin = CIN > 0 ? CIN : cin_rt;
+    constexpr int CM = CIN > 0 ? CIN : 16;
+    const int Cb = C < 256 ? C : 256;
+    const int c = blockIdx.y * Cb + threadIdx.x % Cb;
+    const int rpb = blockDim.x / Cb;
+    const bool warp_uniform_row = (C % 32) == 0;  // all 32 lanes of a warp work on the same centre row
+    float Wq[CM], Wk[CM], Wv[CM], GWq[CM], GWk[CM], GWv[CM];
+#pragma unroll
+    for (int i = 0; i < CM; ++i) {
+        GWq[i] = GWk[i] = GWv[i] = 0.f;
+        if (i < cin) {
+            Wq[i] = wq[c * cin + i];
+            Wk[i] = wk[c * cin + i];
+            Wv[i] = wv[c * cin + i];
+        }
+    }
+    const float Bq = bq[c], Bk = bk[c], Bv = bv[c];
+    float GBq = 0.f, GBk = 0.f, GBv = 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * rpb + threadIdx.x / Cb; row < rows; row += (int64_t)gridDim.x * rpb) {
+        const int64_t b = row / S;
+        const int cn = cidx ? clamp_index(__ldg(cidx + row), N) : (int)(row - b * S);
+        const float* cp = feat + ((size_t)b * N + cn) * cin;
+        float cen[CM];
+#pragma unroll
+        for (int i = 0; i < CM; ++i)
+            if (i < cin) cen[i] = __ldg(cp + i);
+        float qv = 0.f;
+#pragma unroll
+        for (int i = 0; i < CM; ++i)
+            if (i < cin) qv = fmaf(cen[i], Wq[i], qv);
+        qv += Bq;
+        float e[K], v[K], a[K], de[K], O, dv;
+        int js, nb[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            nb[j] = clamp_index(__ldg(idx + row * K + j), N);
+            const float* np = feat + ((size_t)b * N + nb[j]) * cin;
+            float kv = 0.f, vv = 0.f;
+#pragma unroll
+            for (int i = 0; i < CM; ++i)
+                if (i < cin) {
+                    const float d = __ldg(np + i) - cen[i];
+                    kv = fmaf(d, Wk[i], kv);
+                    vv = fmaf(d, Wv[i], vv);
+                }
+            e[j] = qv - (kv + Bk);
+            v[j] = vv + Bv;
+        }
+        attn_channel<K>(e, v, sqrtc, a, O, js);
+        attn_channel_bwd<K>(__ldg(gctx + row * C + c), a, O, js, v, sqrtc, de, dv);
+        // q = Wq cen + bq ; k_j = Wk (x_j - cen) + bk ; v_j = Wv (x_j - cen) + bv ; e_j = q - k_j
+        float dq = 0.f;
+        float gcen[CM];
+#pragma unroll
+        for (int i = 0; i < CM; ++i) gcen[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            dq += de[j];
+            const float dkj = -de[j];
+            const float dvj = (j == js) ? dv : 0.f;
+            GBk += dkj;
+            GBv += dvj;
+            const float* np = feat + ((size_t)b * N + nb[j]) * cin;
+#pragma unroll
+            for (int i = 0; i < CM; ++i)
+                if (i < cin) {
+                    const float d = __ldg(np + i) - cen[i];
+                    GWk[i] = fmaf(dkj, d, GWk[i]);
+                    GWv[i] = fmaf(dvj, d, GWv[i]);
+                    if (gfeat) {
+                        float gd = dkj * Wk[i] + dvj * Wv[i];  // dL/d(x_j - cen)_i from this channel
+                        gcen[i] -= gd;
+                        if (warp_uniform_row) {
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) gd += __shfl_xor_sync(0xffffffffu, gd, o);
+                            if ((threadIdx.x & 31) == 0) red_add_f32(gfeat + ((size_t)b * N + nb[j]) * cin + i, gd);
+                        } else {
+                            red_add_f32(gfeat + ((size_t)b * N + nb[j]) * cin + i, gd);
+                        }
+                    }
+                }
+        }
+        GBq += dq;
+#pragma unroll
+        for (int i = 0; i < CM; ++i)
+            if (i < cin) {
+                GWq[i] = fmaf(dq, cen[i], GWq[i]);
+                if (gfeat) {
+                    float gd = gcen[i] + dq * Wq[i];
+                    if (warp_uniform_row) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) gd += __shfl_xor_sync(0xffffffffu, gd, o);
+                        if ((threadIdx.x & 31) == 0) red_add_f32(gfeat + ((size_t)b * N + cn) * cin + i, gd);
+                    } else {
+                        red_add_f32(gfeat + ((size_t)b * N + cn) * cin + i, gd);
+                    }
+                }
+            }
+    }
+    // one reduction per thread into the [C,cin] / [C] accumulators
+#pragma unroll
+    for (int i = 0; i < CM; ++i)
+        if (i < cin) {
+            red_add_f32(gwq + c * cin + i, GWq[i]);
+            red_add_f32(gwk + c * cin + i, GWk[i]);
+            red_add_f32(gwv + c * cin + i, GWv[i]);
+        }
+    red_add_f32(gbq + c, GBq);
+    red_add_f32(gbk + c, GBk);
+    red_add_f32(gbv + c, GBv);
+}
+
+static inline int xyz_threads(int C) {  // C <= 256: several rows per CTA; else 256 channels per CTA
+    if (C >= 256) return 256;
+    return C * (256 / C);
+}
+
+}  // namespace mpc
+
+using namespace mpc;
+
+#define MPC_DISPATCH_K(K, CALL)            \
+    switch (K) {                           \
+        case 3: { constexpr int KK = 3; CALL; } break;   \
+        case 4: { constexpr int KK = 4; CALL; } break;   \
+        case 8: { constexpr int KK = 8; CALL; } break;   \
+        case 9: { constexpr int KK = 9; CALL; } break;   \
+        case 16: { constexpr int KK = 16; CALL; } break; \
+        case 32: { constexpr int KK = 32; CALL; } break; \
+        default: return MPC_ERR_UNSUPPORTED;             \
+    }
+
+MPC_API int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, const float* vf, int64_t ldkv,
+                                  const int64_t* idx, float* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K,
+                                  int64_t C, mpc_stream_t stream) {
+    if (!q || !kf || !vf || !idx || !ctx_out || B < 0 || S < 0 || N <= 0 || K <= 0 || C <= 0) return MPC_ERR_INVALID;
+    if (C % 4 || ldq % 4 || ldkv % 4 || ldq < C || ldkv < C || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (((uintptr_t)q | (uintptr_t)kf | (uintptr_t)vf | (uintptr_t)ctx_out) & 15u) return MPC_ERR_INVALID;
+    if (K > KMAX || C > 1024) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    const int CV = (int)(C / 4);
+    const int64_t total = B * S * CV;
+    const float sqrtc = sqrtf((float)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_DISPATCH_K(K, (attn_feat_fwd_kernel<KK><<<attn_grid(total, AT), AT, 0, st>>>(
+                          q, ldq, kf, vf, ldkv, idx, ctx_out, (int)S, (int)N, CV, sqrtc, total)));
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t ldq, const float* kf,
+                                  const float* vf, int64_t ldkv, const int64_t* idx, float* grad_q, int64_t ldgq,
+                                  float* grad_kf, float* grad_vf, int64_t ldgkv, int64_t B, int64_t S, int64_t N,
+                                  int64_t K, int64_t C, mpc_stream_t stream) {
+    if (!grad_ctx || !q || !kf || !vf || !idx || !grad_q || !grad_kf || !grad_vf) return MPC_ERR_INVALID;
+    if (B < 0 || S < 0 || N <= 0 || K <= 0 || C <= 0 || C % 4 || ldq % 4 || ldkv % 4 || ldgq % 4 || ldgkv % 4)
+        return MPC_ERR_INVALID;
+    if (ldq < C || ldkv < C || ldgq < C || ldgkv < C || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (((uintptr_t)grad_ctx | (uintptr_t)q | (uintptr_t)kf | (uintptr_t)vf | (uintptr_t)grad_q |
+         (uintptr_t)grad_kf | (uintptr_t)grad_vf) & 15u)
+        return MPC_ERR_INVALID;
+    if (K > KMAX || C > 1024) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    const int CV = (int)(C / 4);
+    const int64_t total = B * S * CV;
+    const float sqrtc = sqrtf((float)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_DISPATCH_K(K, (attn_feat_bwd_kernel<KK><<<attn_grid(total, AT), AT, 0, st>>>(
+                          grad_ctx, q, ldq, kf, vf, ldkv, idx, grad_q, ldgq, grad_kf, grad_vf, ldgkv, (int)S, (int)N,
+                          CV, sqrtc, total)));
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_attn_xyz_fwd_f32(const float* feat, const int64_t* center_idx, const int64_t* idx, const float* wq,
+                                 const float* bq, const float* wk, const float* bk, const float* wv, const float* bv,
+                                 float* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
+                                 mpc_stream_t stream) {
+    if (!feat || !idx || !wq || !bq || !wk || !bk || !wv || !bv || !ctx_out) return MPC_ERR_INVALID;
+    if (B < 0 || S < 0 || N <= 0 || K <= 0 || Cin <= 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (!center_idx && S != N) return MPC_ERR_INVALID;
+    if (K > KMAX || C > 1024 || Cin > 16) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    if (C > 256 && C % 256) return MPC_ERR_UNSUPPORTED;
+    const int threads = xyz_threads((int)C);
+    const int rpb = C >= 256 ? 1 : threads / (int)C;
+    const int64_t rows = B * S;
+    const dim3 grid(attn_grid(ceil_div(rows, rpb) * threads, threads), C > 256 ? (unsigned)(C / 256) : 1u);
+    const float sqrtc = sqrtf((float)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 3) {
+        MPC_DISPATCH_K(K, (attn_xyz_fwd_kernel<KK, 3><<<grid, threads, 0, st>>>(
+                              feat, center_idx, idx, wq, bq, wk, bk, wv, bv, ctx_out, rows, (int)S, (int)N, (int)C, 3,
+                              sqrtc)));
+    } else {
+        MPC_DISPATCH_K(K, (attn_xyz_fwd_kernel<KK, 0><<<grid, threads, 0, st>>>(
+                              feat, center_idx, idx, wq, bq, wk, bk, wv, bv, ctx_out, rows, (int)S, (int)N, (int)C,
+                              (int)Cin, sqrtc)));
+    }
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t* center_idx,
+                                 const int64_t* idx, const float* wq, const float* bq, const float* wk,
+                                 const float* bk, const float* wv, const float* bv, float* grad_wq, float* grad_bq,
+                                 float* grad_wk, float* grad_bk, float* grad_wv, float* grad_bv, float* grad_feat,
+                                 int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
+                                 mpc_stream_t stream) {
+    if (!grad_ctx || !feat || !idx || !wq || !bq || !wk || !bk || !wv || !bv) return MPC_ERR_INVALID;
+    if (!grad_wq || !grad_bq || !grad_wk || !grad_bk || !grad_wv || !grad_bv) return MPC_ERR_INVALID;
+    if (B < 0 || S < 0 || N <= 0 || K <= 0 || Cin <= 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (!center_idx && S != N) return MPC_ERR_INVALID;
+    if (K > KMAX || C > 1024 || Cin > 16) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    if (C > 256 && C % 256) return MPC_ERR_UNSUPPORTED;
+    const int threads = xyz_threads((int)C);
+    const int rpb = C >= 256 ? 1 : threads / (int)C;
+    const int64_t rows = B * S;
+    // fewer, longer-lived CTAs: every thread ends with 3*Cin+3 reductions into shared accumulators
+    int64_t g = ceil_div(rows, rpb);
+    const int64_t cap = (int64_t)kNumSMs * 4;
+    const dim3 grid((unsigned)(g > cap ? cap : g), C > 256 ? (unsigned)(C / 256) : 1u);
+    const float sqrtc = sqrtf((float)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 3) {
+        MPC_DISPATCH_K(K, (attn_xyz_bwd_kernel<KK, 3><<<grid, threads, 0, st>>>(
+                              grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, grad_wq, grad_bq, grad_wk,
+                              grad_bk, grad_wv, grad_bv, grad_feat, rows, (int)S, (int)N, (int)C, 3, sqrtc)));
+    } else {
+        MPC_DISPATCH_K(K, (attn_xyz_bwd_kernel<KK, 0><<<grid, threads, 0, st>>>(
+                              grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, grad_wq, grad_bq, grad_wk,
+                              grad_bk, grad_wv, grad_bv, grad_feat, rows, (int)S, (int)N, (int)C, (int)Cin, sqrtc)));
+    }
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}

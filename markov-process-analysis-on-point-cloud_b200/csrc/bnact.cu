@@ -1,0 +1,306 @@
+// Tail of the shared-MLP block (`Linear`: nn.Linear -> BatchNorm1d over channels -> LeakyReLU(0.2)) for
+// sm_100a.  See include/mpc_b200.h (mpc_bn_*) and pointnet2_utils.py:413-425.
+//
+// Works on the [M,C] view (M = every leading axis), so the two permute().contiguous() copies the reference
+// makes around BatchNorm1d (:420) disappear.  All three kernels are pure HBM streams: 128-bit accesses, one
+// warp per 128 consecutive channels of a row, per-channel partial sums in registers -> shared -> one fp64
+// atomic per (CTA, channel).
+#include "common.cuh"
+
+namespace mpc {
+
+constexpr int BN_TX = 32;  // lanes along channels (float4 each => 128 channels per CTA column)
+constexpr int BN_TY = 8;   // row slots per CTA
+
+struct Dims {
+    dim3 grid, block;
+};
+static inline Dims bn_dims(int64_t M, int CV) {
+    Dims d;
+    d.block = dim3(BN_TX, BN_TY);
+    unsigned gx = (unsigned)ceil_div(CV, BN_TX);
+    int64_t want = ((int64_t)kNumSMs * 8) / gx;  // ~8 CTAs per SM overall
+    int64_t gy = ceil_div(M, BN_TY * 4);         // at least 4 rows per thread
+    if (gy > want) gy = want;
+    if (gy < 1) gy = 1;
+    d.grid = dim3(gx, (unsigned)gy);
+    return d;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p, bool vec) {
+    if (vec) return __ldg(reinterpret_cast<const float4*>(p));
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Reduce 4 channel partials (a: 4 values, b: 4 values) over the BN_TY row slots and add to the fp64 scratch.
+__device__ __forceinline__ void block_reduce_to_scratch(float4 a, float4 b, double* __restrict__ sa,
+                                                        double* __restrict__ sb, int cbase, int C) {
+    __shared__ float4 ra[BN_TY][BN_TX], rb[BN_TY][BN_TX];
+    ra[threadIdx.y][threadIdx.x] = a;
+    rb[threadIdx.y][threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        double A[4] = {0, 0, 0, 0}, Bv[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int y = 0; y < BN_TY; ++y) {
+            float4 u = ra[y][threadIdx.x], w = rb[y][threadIdx.x];
+            A[0] += u.x; A[1] += u.y; A[2] += u.z; A[3] += u.w;
+            Bv[0] += w.x; Bv[1] += w.y; Bv[2] += w.z; Bv[3] += w.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (cbase + i < C) {
+                atomicAdd(sa + cbase + i, A[i]);
+                atomicAdd(sb + cbase + i, Bv[i]);
+            }
+    }
+}
+
+// per-channel sum and sum of squares (C % 4 == 0 path: float4; else scalar path with 1 channel per lane)
+template <bool VEC4>
+__global__ void __launch_bounds__(BN_TX* BN_TY)
+bn_sums_kernel(const float* __restrict__ y, double* __restrict__ s1, double* __restrict__ s2, int64_t M, int C) {
+    const int cw = VEC4 ? 4 : 1;
+    const int cbase = (blockIdx.x * BN_TX + threadIdx.x) * cw;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (cbase < C) {
+        for (int64_t r = (int64_t)blockIdx.y * BN_TY + threadIdx.y; r < M; r += (int64_t)gridDim.y * BN_TY) {
+            if (VEC4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + cbase));
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y);
+                b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
+            } else {
+                const float v = __ldg(y + r * C + cbase);
+                a.x += v;
+                b.x = fmaf(v, v, b.x);
+            }
+        }
+    }
+    block_reduce_to_scratch(a, b, s1, s2, cbase, VEC4 ? C : min(C, cbase + 1));
+}
+
+// mean / biased variance, plus nn.BatchNorm1d's running-statistics update (unbiased variance, momentum)
+__global__ void bn_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2,
+                                   float* __restrict__ stats, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked,
+                                   float momentum, int64_t M, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    if (c >= C) return;
+    const double mean = s1[c] / (double)M;
+    double var = s2[c] / (double)M - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    stats[c] = (float)mean;
+    stats[C + c] = (float)var;
+    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) {
+        const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ var,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
+                  float* __restrict__ out, int C, int64_t total) {
+    const int cw = VEC4 ? 4 : 1;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int c = (int)((t * cw) % C);
+        if (VEC4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(y) + t);
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+            const float4 vr = __ldg(reinterpret_cast<const float4*>(var + c));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 o;
+#define MPC_BN(comp)                                                        \
+    {                                                                       \
+        const float sc = g.comp * (1.0f / sqrtf(vr.comp + eps));            \
+        const float z = fmaf(v.comp - mu.comp, sc, be.comp);                \
+        o.comp = z > 0.f ? z : z * slope;                                   \
+    }
+            MPC_BN(x) MPC_BN(y) MPC_BN(z) MPC_BN(w)
+#undef MPC_BN
+            reinterpret_cast<float4*>(out)[t] = o;
+        } else {
+            const float sc = gamma[c] * (1.0f / sqrtf(var[c] + eps));
+            const float z = fmaf(y[t] - mean[c], sc, beta[c]);
+            out[t] = z > 0.f ? z : z * slope;
+        }
+    }
+}
+
+// backward pass A: per channel sum(dz) and sum(dz * xhat)
+template <bool VEC4>
+__global__ void __launch_bounds__(BN_TX* BN_TY)
+bn_bwd_sums_kernel(const float* __restrict__ gout, const float* __restrict__ y, const float* __restrict__ mean,
+                   const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, float slope, double* __restrict__ s1, double* __restrict__ s2, int64_t M, int C) {
+    const int cw = VEC4 ? 4 : 1;
+    const int cbase = (blockIdx.x * BN_TX + threadIdx.x) * cw;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (cbase < C) {
+        float mu[4], is[4], g[4], be[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < cw) {
+                mu[i] = mean[cbase + i];
+                is[i] = 1.0f / sqrtf(var[cbase + i] + eps);
+                g[i] = gamma[cbase + i];
+                be[i] = beta[cbase + i];
+            }
+        for (int64_t r = (int64_t)blockIdx.y * BN_TY + threadIdx.y; r < M; r += (int64_t)gridDim.y * BN_TY) {
+            float yv[4], gv[4];
+            if (VEC4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + cbase));
+                const float4 go = __ldg(reinterpret_cast<const float4*>(gout + r * C + cbase));
+                yv[0] = v.x; yv[1] = v.y; yv[2] = v.z; yv[3] = v.w;
+                gv[0] = go.x; gv[1] = go.y; gv[2] = go.z; gv[3] = go.w;
+            } else {
+                yv[0] = __ldg(y + r * C + cbase);
+                gv[0] = __ldg(gout + r * C + cbase);
+            }
+            float da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < cw) {
+                    const float xh = (yv[i] - mu[i]) * is[i];
+                    const float z = fmaf(xh, g[i], be[i]);
+                    const float dz = z > 0.f ? gv[i] : gv[i] * slope;
+                    da[i] = dz;
+                    db[i] = dz * xh;
+                }
+            a.x += da[0]; a.y += da[1]; a.z += da[2]; a.w += da[3];
+            b.x += db[0]; b.y += db[1]; b.z += db[2]; b.w += db[3];
+        }
+    }
+    block_reduce_to_scratch(a, b, s1, s2, cbase, VEC4 ? C : min(C, cbase + 1));
+}
+
+// backward pass B: grad_y; also publishes grad_beta = s1, grad_gamma = s2 (CTA 0)
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ y, const float* __restrict__ mean,
+                    const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float eps, float slope, int train, const double* __restrict__ s1, const double* __restrict__ s2,
+                    float* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta, int64_t M, int C,
+                    int64_t total) {
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += 256) {
+            gbeta[c] = (float)s1[c];
+            ggamma[c] = (float)s2[c];
+        }
+    const int cw = VEC4 ? 4 : 1;
+    const float invM = train ? (float)(1.0 / (double)M) : 0.f;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int c0 = (int)((t * cw) % C);
+        float yv[4], gv[4], o[4];
+        if (VEC4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(y) + t);
+            const float4 go = __ldg(reinterpret_cast<const float4*>(gout) + t);
+            yv[0] = v.x; yv[1] = v.y; yv[2] = v.z; yv[3] = v.w;
+            gv[0] = go.x; gv[1] = go.y; gv[2] = go.z; gv[3] = go.w;
+        } else {
+            yv[0] = y[t];
+            gv[0] = gout[t];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < cw) {
+                const int c = c0 + i;
+                const float is = 1.0f / sqrtf(var[c] + eps);
+                const float g = gamma[c];
+                const float xh = (yv[i] - mean[c]) * is;
+                const float z = fmaf(xh, g, beta[c]);
+                const float dz = z > 0.f ? gv[i] : gv[i] * slope;
+                const float db = (float)s1[c], dg = (float)s2[c];
+                o[i] = g * is * (dz - invM * (db + xh * dg));
+            }
+        if (VEC4)
+            reinterpret_cast<float4*>(gy)[t] = make_float4(o[0], o[1], o[2], o[3]);
+        else
+            gy[t] = o[0];
+    }
+}
+
+static inline unsigned ew_grid(int64_t total) {
+    int64_t g = ceil_div(total, 256);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace mpc
+
+using namespace mpc;
+
+MPC_API int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* running_var,
+                             int64_t* num_batches_tracked, float momentum, double* scratch, int64_t M, int64_t C,
+                             mpc_stream_t stream) {
+    if (!y || !stats || !scratch || M <= 0 || C <= 0 || C > INT32_MAX / 4) return MPC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)C, st));
+    const bool v4 = C % 4 == 0 && al16(y);
+    const Dims d = bn_dims(M, (int)(v4 ? C / 4 : C));
+    if (v4)
+        bn_sums_kernel<true><<<d.grid, d.block, 0, st>>>(y, scratch, scratch + C, M, (int)C);
+    else
+        bn_sums_kernel<false><<<d.grid, d.block, 0, st>>>(y, scratch, scratch + C, M, (int)C);
+    MPC_LAUNCH_CHECK();
+    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(scratch, scratch + C, stats, running_mean, running_var,
+                                                                   num_batches_tracked, momentum, M, (int)C);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, const float* gamma,
+                               const float* beta, float eps, float slope, float* out, int64_t M, int64_t C,
+                               mpc_stream_t stream) {
+    if (!y || !mean || !var || !gamma || !beta || !out || M < 0 || C <= 0) return MPC_ERR_INVALID;
+    if (M == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v4 = C % 4 == 0 && al16(y) && al16(out) && al16(mean) && al16(var) && al16(gamma) && al16(beta);
+    const int64_t total = M * (v4 ? C / 4 : C);
+    if (v4)
+        bn_act_fwd_kernel<true><<<ew_grid(total), 256, 0, st>>>(y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
+    else
+        bn_act_fwd_kernel<false><<<ew_grid(total), 256, 0, st>>>(y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean, const float* var,
+                               const float* gamma, const float* beta, float eps, float slope, int train,
+                               float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, int64_t M,
+                               int64_t C, mpc_stream_t stream) {
+    if (!grad_out || !y || !mean || !var || !gamma || !beta || !grad_y || !grad_gamma || !grad_beta || !scratch)
+        return MPC_ERR_INVALID;
+    if (M <= 0 || C <= 0) return MPC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)C, st));
+    const bool v4 = C % 4 == 0 && al16(y) && al16(grad_out) && al16(grad_y);
+    const Dims d = bn_dims(M, (int)(v4 ? C / 4 : C));
+    const int64_t total = M * (v4 ? C / 4 : C);
+    if (v4) {
+        bn_bwd_sums_kernel<true><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, scratch,
+                                                            scratch + C, M, (int)C);
+        MPC_LAUNCH_CHECK();
+        bn_bwd_apply_kernel<true><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, train,
+                                                                 scratch, scratch + C, grad_y, grad_gamma, grad_beta, M,
+                                                                 (int)C, total);
+    } else {
+        bn_bwd_sums_kernel<false><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, scratch,
+                                                             scratch + C, M, (int)C);
+        MPC_LAUNCH_CHECK();
+        bn_bwd_apply_kernel<false><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
+                                                                  train, scratch, scratch + C, grad_y, grad_gamma,
+                                                                  grad_beta, M, (int)C, total);
+    }
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_version(void) { return 100; }  /* 0.1.0 */
+MPC_API int mpc_compiled_arch(void) { return 1000; }

@@ -1,0 +1,384 @@
+// Row gather / scatter family for sm_100a: index_points forward/backward, the sparse Markov transition
+// (`upsample`) forward/backward and three_interpolate forward/backward.  See include/mpc_b200.h for the
+// contracts and the reference lines replaced (pointnet2_utils.py:13-50, 64-81, 903-906).
+//
+// All of these are HBM/L2-bound row movers: rows are moved with 128-bit accesses (one float4 lane per 4
+// channels, consecutive lanes on consecutive 16-byte pieces of a row), reductions into rows use
+// red.global.add.v4.f32, and grids are sized from the element count so every SM has several CTAs in flight.
+#include "common.cuh"
+
+namespace mpc {
+
+constexpr int GT = 256;  // threads per CTA for the row movers
+
+static inline unsigned grid_for(int64_t work_items) {
+    int64_t g = ceil_div(work_items, GT);
+    const int64_t cap = (int64_t)kNumSMs * 32;  // grid-stride beyond 32 CTAs per SM
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ---- index_points forward ---------------------------------------------------------------------------------
+template <typename VEC>
+__global__ void __launch_bounds__(GT)
+gather_kernel(const VEC* __restrict__ points, const int64_t* __restrict__ idx, VEC* __restrict__ out,
+              int N, int64_t M, int CV, int64_t total) {
+    // total = B*M*CV vector elements; CV = vectors per row
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / CV;
+        const int v = (int)(t - row * CV);
+        const int64_t b = row / M;
+        const int n = clamp_index(__ldg(idx + row), N);
+        out[t] = __ldg(points + ((size_t)b * N + n) * CV + v);
+    }
+}
+
+// ---- index_points backward: grad_points[b, idx[b,m], :] += grad_out[b,m,:] ----------------------------------
+__global__ void __launch_bounds__(GT)
+scatter_add_v4_kernel(const float4* __restrict__ grad_out, const int64_t* __restrict__ idx,
+                      float* __restrict__ grad_points, int N, int64_t M, int CV, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / CV;
+        const int v = (int)(t - row * CV);
+        const int64_t b = row / M;
+        const int n = clamp_index(__ldg(idx + row), N);
+        red_add_f32x4(grad_points + (((size_t)b * N + n) * CV + v) * 4, __ldg(grad_out + t));
+    }
+}
+__global__ void __launch_bounds__(GT)
+scatter_add_s_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
+                     float* __restrict__ grad_points, int N, int64_t M, int C, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / C;
+        const int c = (int)(t - row * C);
+        const int64_t b = row / M;
+        const int n = clamp_index(__ldg(idx + row), N);
+        red_add_f32(grad_points + ((size_t)b * N + n) * C + c, __ldg(grad_out + t));
+    }
+}
+
+// ---- Markov transition ---------------------------------------------------------------------------------------
+// scatter phase: one work item = (row (b,s), k, vector v).  A neighbour index repeated at an earlier k of the
+// same row is skipped (the reference's scatter_ overwrites, it does not accumulate).
+template <bool VEC4>
+__global__ void __launch_bounds__(GT)
+transition_scatter_kernel(const float* __restrict__ points, const int64_t* __restrict__ idx,
+                          float* __restrict__ out, float* __restrict__ cnt, int S, int K, int C, int N,
+                          int64_t total) {
+    const int CV = VEC4 ? C / 4 : C;
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t rk = t / CV;  // (row, k)
+        const int v = (int)(t - rk * CV);
+        const int64_t row = rk / K;
+        const int k = (int)(rk - row * K);
+        const int64_t b = row / S;
+        const int64_t* irow = idx + row * K;
+        const int64_t raw = __ldg(irow + k);
+        if (raw < 0 || raw >= N) continue;  // validated on the host; never touch memory out of range
+        bool dup = false;
+        for (int j = 0; j < k; ++j) dup |= (__ldg(irow + j) == raw);
+        if (dup) continue;
+        const size_t dst = ((size_t)b * N + (size_t)raw);
+        if (VEC4) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(points) + row * CV + v);
+            red_add_f32x4(out + (dst * CV + v) * 4, p);
+            if (v == 0 && p.x != 0.0f) red_add_f32(cnt + dst, 1.0f);
+        } else {
+            const float p = __ldg(points + row * C + v);
+            red_add_f32(out + dst * C + v, p);
+            if (v == 0 && p != 0.0f) red_add_f32(cnt + dst, 1.0f);
+        }
+    }
+}
+
+// normalise phase: out[b,n,:] /= (cnt == 0 ? 1 : cnt); cnt is rewritten with the divisor actually used.
+template <bool VEC4>
+__global__ void __launch_bounds__(GT)
+transition_normalise_kernel(float* __restrict__ out, float* __restrict__ cnt, int C, int64_t total) {
+    const int CV = VEC4 ? C / 4 : C;
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / CV;
+        const int v = (int)(t - row * CV);
+        float d = cnt[row];
+        d = d == 0.0f ? 1.0f : d;
+        if (VEC4) {
+            float4* o = reinterpret_cast<float4*>(out) + t;
+            float4 x = *o;
+            x.x = __fdiv_rn(x.x, d);
+            x.y = __fdiv_rn(x.y, d);
+            x.z = __fdiv_rn(x.z, d);
+            x.w = __fdiv_rn(x.w, d);
+            *o = x;
+        } else {
+            out[t] = __fdiv_rn(out[t], d);
+        }
+        (void)v;
+    }
+}
+__global__ void __launch_bounds__(GT) transition_fix_cnt_kernel(float* __restrict__ cnt, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT)
+        if (cnt[t] == 0.0f) cnt[t] = 1.0f;
+}
+
+// backward: a pure gather (no atomics): grad_points[row,:] = sum_k grad_out[b, idx[row,k], :] / cnt[b, idx[row,k]]
+template <bool VEC4>
+__global__ void __launch_bounds__(GT)
+transition_bwd_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
+                      const float* __restrict__ cnt, float* __restrict__ grad_points, int S, int K, int C,
+                      int N, int64_t total) {
+    const int CV = VEC4 ? C / 4 : C;
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / CV;
+        const int v = (int)(t - row * CV);
+        const int64_t b = row / S;
+        const int64_t* irow = idx + row * K;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < K; ++k) {
+            const int64_t raw = __ldg(irow + k);
+            if (raw < 0 || raw >= N) continue;
+            bool dup = false;
+            for (int j = 0; j < k; ++j) dup |= (__ldg(irow + j) == raw);
+            if (dup) continue;
+            const size_t src = (size_t)b * N + (size_t)raw;
+            const float d = __ldg(cnt + src);
+            if (VEC4) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(grad_out) + src * CV + v);
+                acc.x += __fdiv_rn(g.x, d);
+                acc.y += __fdiv_rn(g.y, d);
+                acc.z += __fdiv_rn(g.z, d);
+                acc.w += __fdiv_rn(g.w, d);
+            } else {
+                acc.x += __fdiv_rn(__ldg(grad_out + src * C + v), d);
+            }
+        }
+        if (VEC4)
+            reinterpret_cast<float4*>(grad_points)[t] = acc;
+        else
+            grad_points[t] = acc.x;
+    }
+}
+
+// ---- three_interpolate ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT)
+three_weights_kernel(const float* __restrict__ dist, float* __restrict__ weight, int64_t rows) {
+    for (int64_t r = (int64_t)blockIdx.x * GT + threadIdx.x; r < rows; r += (int64_t)gridDim.x * GT) {
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(dist[r * 3 + 0], 1e-8f));
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(dist[r * 3 + 1], 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(dist[r * 3 + 2], 1e-8f));
+        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        weight[r * 3 + 0] = __fdiv_rn(r0, norm);
+        weight[r * 3 + 1] = __fdiv_rn(r1, norm);
+        weight[r * 3 + 2] = __fdiv_rn(r2, norm);
+    }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(GT)
+three_interp_fwd_kernel(const float* __restrict__ points2, const float* __restrict__ weight,
+                        const int64_t* __restrict__ idx, float* __restrict__ out, int N, int S, int C,
+                        int64_t total) {
+    const int CV = VEC4 ? C / 4 : C;
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / CV;
+        const int v = (int)(t - row * CV);
+        const int64_t b = row / N;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int s = clamp_index(__ldg(idx + row * 3 + i), S);
+            const float w = __ldg(weight + row * 3 + i);
+            if (VEC4) {
+                const float4 p = __ldg(reinterpret_cast<const float4*>(points2) + ((size_t)b * S + s) * CV + v);
+                // products rounded separately, summed left to right (torch.sum over the 3-axis)
+                acc.x = i == 0 ? __fmul_rn(w, p.x) : __fadd_rn(acc.x, __fmul_rn(w, p.x));
+                acc.y = i == 0 ? __fmul_rn(w, p.y) : __fadd_rn(acc.y, __fmul_rn(w, p.y));
+                acc.z = i == 0 ? __fmul_rn(w, p.z) : __fadd_rn(acc.z, __fmul_rn(w, p.z));
+                acc.w = i == 0 ? __fmul_rn(w, p.w) : __fadd_rn(acc.w, __fmul_rn(w, p.w));
+            } else {
+                const float p = __ldg(points2 + ((size_t)b * S + s) * C + v);
+                acc.x = i == 0 ? __fmul_rn(w, p) : __fadd_rn(acc.x, __fmul_rn(w, p));
+            }
+        }
+        if (VEC4)
+            reinterpret_cast<float4*>(out)[t] = acc;
+        else
+            out[t] = acc.x;
+    }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(GT)
+three_interp_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ weight,
+                        const int64_t* __restrict__ idx, float* __restrict__ grad_points2, int N, int S, int C,
+                        int64_t total) {
+    const int CV = VEC4 ? C / 4 : C;
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / CV;
+        const int v = (int)(t - row * CV);
+        const int64_t b = row / N;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (VEC4)
+            g = __ldg(reinterpret_cast<const float4*>(grad_out) + t);
+        else
+            g.x = __ldg(grad_out + t);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int s = clamp_index(__ldg(idx + row * 3 + i), S);
+            const float w = __ldg(weight + row * 3 + i);
+            if (VEC4)
+                red_add_f32x4(grad_points2 + (((size_t)b * S + s) * CV + v) * 4,
+                              make_float4(w * g.x, w * g.y, w * g.z, w * g.w));
+            else
+                red_add_f32(grad_points2 + ((size_t)b * S + s) * C + v, w * g.x);
+        }
+    }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace mpc
+
+using namespace mpc;
+
+MPC_API int mpc_gather_f32(const float* points, const int64_t* idx, float* out, int64_t B, int64_t N, int64_t M,
+                           int64_t C, mpc_stream_t stream) {
+    if (!points || !idx || !out || B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (B == 0 || M == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
+        const int CV = (int)(C / 4);
+        const int64_t total = B * M * CV;
+        gather_kernel<float4><<<grid_for(total), GT, 0, st>>>(reinterpret_cast<const float4*>(points), idx,
+                                                             reinterpret_cast<float4*>(out), (int)N, M, CV, total);
+    } else {
+        const int64_t total = B * M * C;
+        gather_kernel<float><<<grid_for(total), GT, 0, st>>>(points, idx, out, (int)N, M, (int)C, total);
+    }
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* out, int64_t B, int64_t N,
+                           int64_t M, mpc_stream_t stream) {
+    if (!values || !idx || !out || B < 0 || N <= 0 || M < 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (B == 0 || M == 0) return MPC_OK;
+    const int64_t total = B * M;
+    gather_kernel<long long><<<grid_for(total), GT, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long*>(values), idx, reinterpret_cast<long long*>(out), (int)N, M, 1, total);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_gather_bwd_f32(const float* grad_out, const int64_t* idx, float* grad_points, int64_t B,
+                               int64_t N, int64_t M, int64_t C, mpc_stream_t stream) {
+    if (!grad_out || !idx || !grad_points || B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (B == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * N * C * sizeof(float), st));
+    if (M == 0) return MPC_OK;
+    if (C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points)) {
+        const int CV = (int)(C / 4);
+        const int64_t total = B * M * CV;
+        scatter_add_v4_kernel<<<grid_for(total), GT, 0, st>>>(reinterpret_cast<const float4*>(grad_out), idx,
+                                                              grad_points, (int)N, M, CV, total);
+    } else {
+        const int64_t total = B * M * C;
+        scatter_add_s_kernel<<<grid_for(total), GT, 0, st>>>(grad_out, idx, grad_points, (int)N, M, (int)C, total);
+    }
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_transition_fwd_f32(const float* points, const int64_t* idx, float* out, float* cnt, int64_t B,
+                                   int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream) {
+    if (!points || !idx || !out || !cnt || B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX)
+        return MPC_ERR_INVALID;
+    if (K > 32) return MPC_ERR_UNSUPPORTED;
+    if (B == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA(cudaMemsetAsync(out, 0, (size_t)B * N * C * sizeof(float), st));
+    MPC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)B * N * sizeof(float), st));
+    const bool v4 = C % 4 == 0 && aligned16(points) && aligned16(out);
+    const int CV = (int)(v4 ? C / 4 : C);
+    if (S > 0) {
+        const int64_t total = B * S * K * CV;
+        if (v4)
+            transition_scatter_kernel<true><<<grid_for(total), GT, 0, st>>>(points, idx, out, cnt, (int)S, (int)K,
+                                                                           (int)C, (int)N, total);
+        else
+            transition_scatter_kernel<false><<<grid_for(total), GT, 0, st>>>(points, idx, out, cnt, (int)S, (int)K,
+                                                                            (int)C, (int)N, total);
+        MPC_LAUNCH_CHECK();
+    }
+    const int64_t total = B * N * CV;
+    if (v4)
+        transition_normalise_kernel<true><<<grid_for(total), GT, 0, st>>>(out, cnt, (int)C, total);
+    else
+        transition_normalise_kernel<false><<<grid_for(total), GT, 0, st>>>(out, cnt, (int)C, total);
+    MPC_LAUNCH_CHECK();
+    transition_fix_cnt_kernel<<<grid_for(B * N), GT, 0, st>>>(cnt, B * N);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, const float* cnt,
+                                   float* grad_points, int64_t B, int64_t S, int64_t K, int64_t C, int64_t N,
+                                   mpc_stream_t stream) {
+    if (!grad_out || !idx || !cnt || !grad_points || B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX)
+        return MPC_ERR_INVALID;
+    if (K > 32) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v4 = C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points);
+    const int CV = (int)(v4 ? C / 4 : C);
+    const int64_t total = B * S * CV;
+    if (v4)
+        transition_bwd_kernel<true><<<grid_for(total), GT, 0, st>>>(grad_out, idx, cnt, grad_points, (int)S, (int)K,
+                                                                   (int)C, (int)N, total);
+    else
+        transition_bwd_kernel<false><<<grid_for(total), GT, 0, st>>>(grad_out, idx, cnt, grad_points, (int)S, (int)K,
+                                                                    (int)C, (int)N, total);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_three_interpolate_fwd_f32(const float* points2, const float* dist, const int64_t* idx,
+                                          float* weight_out, float* out, int64_t B, int64_t N, int64_t S,
+                                          int64_t C, mpc_stream_t stream) {
+    if (!points2 || !dist || !idx || !weight_out || !out || B < 0 || N < 0 || S <= 0 || C <= 0 || S > INT32_MAX)
+        return MPC_ERR_INVALID;
+    if (B == 0 || N == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    three_weights_kernel<<<grid_for(B * N), GT, 0, st>>>(dist, weight_out, B * N);
+    MPC_LAUNCH_CHECK();
+    const bool v4 = C % 4 == 0 && aligned16(points2) && aligned16(out);
+    const int64_t total = B * N * (v4 ? C / 4 : C);
+    if (v4)
+        three_interp_fwd_kernel<true><<<grid_for(total), GT, 0, st>>>(points2, weight_out, idx, out, (int)N, (int)S,
+                                                                     (int)C, total);
+    else
+        three_interp_fwd_kernel<false><<<grid_for(total), GT, 0, st>>>(points2, weight_out, idx, out, (int)N, (int)S,
+                                                                      (int)C, total);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_three_interpolate_bwd_f32(const float* grad_out, const float* weight, const int64_t* idx,
+                                          float* grad_points2, int64_t B, int64_t N, int64_t S, int64_t C,
+                                          mpc_stream_t stream) {
+    if (!grad_out || !weight || !idx || !grad_points2 || B < 0 || N < 0 || S <= 0 || C <= 0 || S > INT32_MAX)
+        return MPC_ERR_INVALID;
+    if (B == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA(cudaMemsetAsync(grad_points2, 0, (size_t)B * S * C * sizeof(float), st));
+    if (N == 0) return MPC_OK;
+    const bool v4 = C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points2);
+    const int64_t total = B * N * (v4 ? C / 4 : C);
+    if (v4)
+        three_interp_bwd_kernel<true><<<grid_for(total), GT, 0, st>>>(grad_out, weight, idx, grad_points2, (int)N,
+                                                                     (int)S, (int)C, total);
+    else
+        three_interp_bwd_kernel<false><<<grid_for(total), GT, 0, st>>>(grad_out, weight, idx, grad_points2, (int)N,
+                                                                      (int)S, (int)C, total);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}

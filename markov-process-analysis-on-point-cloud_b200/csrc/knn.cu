@@ -1,0 +1,324 @@
+// Brute-force k nearest neighbours and ball query for sm_100a.  See include/mpc_b200.h (mpc_knn_f32,
+// mpc_ball_query_f32) for the contract and the reference lines replaced (pointnet2_utils.py:112-134,190-222).
+//
+// The reference materialises the [B,S,N] distance matrix (537 MB per call at 32x2048x2048) and runs a full
+// topk over it.  Here a thread owns one query and a sorted K-list in registers; reference points stream
+// through shared memory in tiles, so HBM sees each coordinate once per CTA and the distance matrix never
+// exists.  Arithmetic must stay fp32 FFMA in the oracle's order (indices have to be bit-exact), so the
+// tensor cores are deliberately not used.
+#include "common.cuh"
+
+namespace mpc {
+
+// Sorted insertion of (d, n) into an ascending K-list held in registers.  Strict < keeps equal distances
+// in ascending index order (candidates arrive in ascending n).
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bi)[K], float d, int n) {
+    bd[K - 1] = d;
+    bi[K - 1] = n;
+#pragma unroll
+    for (int p = K - 1; p > 0; --p) {
+        if (bd[p] < bd[p - 1]) {
+            float td = bd[p];
+            bd[p] = bd[p - 1];
+            bd[p - 1] = td;
+            int ti = bi[p];
+            bi[p] = bi[p - 1];
+            bi[p - 1] = ti;
+        }
+    }
+}
+
+// ---- C == 3 ------------------------------------------------------------------------------------------------
+constexpr int KNN3_THREADS = 128;
+constexpr int KNN3_TILE = 2048;  // reference points per shared-memory tile (float4 x,y,z,|r|^2 = 32 KB)
+
+template <int K>
+__global__ void __launch_bounds__(KNN3_THREADS)
+knn3_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
+            int64_t* __restrict__ idx_out, int N, int S) {
+    __shared__ float4 tile[KNN3_TILE];
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * KNN3_THREADS + threadIdx.x;
+    const bool active = s < S;
+    const float* rb = ref + (size_t)b * N * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        const float* q = qry + ((size_t)b * S + s) * 3;
+        qx = q[0];
+        qy = q[1];
+        qz = q[2];
+    }
+    const float qn = sqnorm3(qx, qy, qz);
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        bd[k] = __int_as_float(0x7f800000);  // +inf
+        bi[k] = 0;
+    }
+    for (int t0 = 0; t0 < N; t0 += KNN3_TILE) {
+        const int tn = min(KNN3_TILE, N - t0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < tn; j += KNN3_THREADS) {
+            const float* r = rb + (size_t)(t0 + j) * 3;
+            float x = r[0], y = r[1], z = r[2];
+            tile[j] = make_float4(x, y, z, sqnorm3(x, y, z));
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int j = 0; j < tn; ++j) {
+                const float4 r = tile[j];  // broadcast read
+                float dot = __fmul_rn(qx, r.x);
+                dot = __fmaf_rn(qy, r.y, dot);
+                dot = __fmaf_rn(qz, r.z, dot);
+                const float d = sqdist_from_dot(dot, qn, r.w);
+                if (d < bd[K - 1]) topk_insert<K>(bd, bi, d, t0 + j);
+            }
+        }
+    }
+    if (active) {
+        const size_t o = ((size_t)b * S + s) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (dist_out) dist_out[o + k] = bd[k];
+            idx_out[o + k] = bi[k];
+        }
+    }
+}
+
+// ---- generic C (feature-space kNN, C = 64..256 in the live models) ---------------------------------------
+// CTA = 128 queries.  Queries live in shared memory [q][C+1]; reference tiles of 32 points are stored
+// transposed [c][32+4] so that one broadcast LDS.128 feeds 4 reference points; a thread advances 8 reference
+// points at once (8 independent fma chains, each sequential in c as the oracle prescribes).
+constexpr int KNNG_THREADS = 128;
+constexpr int KNNG_TR = 32;           // reference points per tile
+constexpr int KNNG_LD = KNNG_TR + 4;  // padded row (floats), keeps 16-byte alignment
+
+template <int K>
+__global__ void __launch_bounds__(KNNG_THREADS)
+knng_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
+            int64_t* __restrict__ idx_out, int N, int S, int C) {
+    extern __shared__ __align__(16) float smem[];
+    float* qs = smem;                                // [128][C+1]
+    float* rt = qs + KNNG_THREADS * (C + 1);         // [C][KNNG_LD]   (offset is a multiple of 4 floats, see launch)
+    float* rn = rt + (size_t)C * KNNG_LD;            // [KNNG_TR]
+    const int b = blockIdx.y;
+    const int s0 = blockIdx.x * KNNG_THREADS;
+    const int tid = threadIdx.x;
+    const int s = s0 + tid;
+    const bool active = s < S;
+    const float* rb = ref + (size_t)b * N * C;
+    const float* qb = qry + ((size_t)b * S + s0) * C;
+    const int nq = min(KNNG_THREADS, S - s0);
+    for (int i = tid; i < nq * C; i += KNNG_THREADS) {
+        int q = i / C, c = i - q * C;
+        qs[q * (C + 1) + c] = qb[i];
+    }
+    __syncthreads();
+    const float* myq = qs + tid * (C + 1);
+    float qn = 0.f;
+    if (active) {
+        qn = __fmul_rn(myq[0], myq[0]);
+        for (int c = 1; c < C; ++c) qn = __fadd_rn(qn, __fmul_rn(myq[c], myq[c]));
+    }
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        bd[k] = __int_as_float(0x7f800000);
+        bi[k] = 0;
+    }
+    for (int t0 = 0; t0 < N; t0 += KNNG_TR) {
+        const int tn = min(KNNG_TR, N - t0);
+        __syncthreads();
+        for (int i = tid; i < KNNG_TR * C; i += KNNG_THREADS) {
+            int j = i / C, c = i - j * C;
+            rt[c * KNNG_LD + j] = j < tn ? rb[(size_t)(t0 + j) * C + c] : 0.f;
+        }
+        __syncthreads();
+        if (tid < KNNG_TR) {
+            float a = __fmul_rn(rt[tid], rt[tid]);
+            for (int c = 1; c < C; ++c) {
+                float v = rt[c * KNNG_LD + tid];
+                a = __fadd_rn(a, __fmul_rn(v, v));
+            }
+            rn[tid] = a;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 1
+            for (int j0 = 0; j0 < KNNG_TR; j0 += 8) {
+                float acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) {
+                    const float qv = myq[c];
+                    const float4 r0 = *reinterpret_cast<const float4*>(rt + c * KNNG_LD + j0);
+                    const float4 r1 = *reinterpret_cast<const float4*>(rt + c * KNNG_LD + j0 + 4);
+                    acc[0] = __fmaf_rn(qv, r0.x, acc[0]);
+                    acc[1] = __fmaf_rn(qv, r0.y, acc[1]);
+                    acc[2] = __fmaf_rn(qv, r0.z, acc[2]);
+                    acc[3] = __fmaf_rn(qv, r0.w, acc[3]);
+                    acc[4] = __fmaf_rn(qv, r1.x, acc[4]);
+                    acc[5] = __fmaf_rn(qv, r1.y, acc[5]);
+                    acc[6] = __fmaf_rn(qv, r1.z, acc[6]);
+                    acc[7] = __fmaf_rn(qv, r1.w, acc[7]);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j0 + u;
+                    const float d = sqdist_from_dot(acc[u], qn, rn[j]);
+                    if (j < tn && d < bd[K - 1]) topk_insert<K>(bd, bi, d, t0 + j);
+                }
+            }
+        }
+    }
+    if (active) {
+        const size_t o = ((size_t)b * S + s) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (dist_out) dist_out[o + k] = bd[k];
+            idx_out[o + k] = bi[k];
+        }
+    }
+}
+
+template <int K>
+static int launch_knn(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, int B, int N,
+                      int S, int C, cudaStream_t st) {
+    if (C == 3) {
+        dim3 grid((unsigned)ceil_div(S, KNN3_THREADS), (unsigned)B);
+        knn3_kernel<K><<<grid, KNN3_THREADS, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+        MPC_LAUNCH_CHECK();
+        return MPC_OK;
+    }
+    // qs occupies 128*(C+1) floats; round the rt offset up to a multiple of 4 floats by padding C+1 -> handled
+    // here by requiring 128*(C+1) % 4 == 0, which holds for every C (128 is a multiple of 4).
+    size_t smem = ((size_t)KNNG_THREADS * (C + 1) + (size_t)C * KNNG_LD + KNNG_TR) * sizeof(float);
+    if (smem > 220 * 1024) return MPC_ERR_UNSUPPORTED;
+    auto kern = knng_kernel<K>;
+    if (smem > 48 * 1024) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(S, KNNG_THREADS), (unsigned)B);
+    kern<<<grid, KNNG_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+// ---- ball query ---------------------------------------------------------------------------------------------
+constexpr int BQ_THREADS = 128;
+constexpr int BQ_TILE = 1024;
+
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query3_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                   int64_t* __restrict__ idx_out, float r2, int N, int S, int nsample) {
+    __shared__ float4 tile[BQ_TILE];
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * BQ_THREADS + threadIdx.x;
+    const bool active = s < S;
+    const float* rb = xyz + (size_t)b * N * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        const float* q = new_xyz + ((size_t)b * S + s) * 3;
+        qx = q[0];
+        qy = q[1];
+        qz = q[2];
+    }
+    const float qn = sqnorm3(qx, qy, qz);
+    int64_t* o = idx_out + ((size_t)b * S + (active ? s : 0)) * nsample;
+    int cnt = 0;
+    int64_t first = N;
+    for (int t0 = 0; t0 < N; t0 += BQ_TILE) {
+        const int tn = min(BQ_TILE, N - t0);
+        const bool need = active && cnt < nsample;
+        if (!__syncthreads_or(need)) break;  // every query of the CTA is full
+        for (int j = threadIdx.x; j < tn; j += BQ_THREADS) {
+            const float* r = rb + (size_t)(t0 + j) * 3;
+            float x = r[0], y = r[1], z = r[2];
+            tile[j] = make_float4(x, y, z, sqnorm3(x, y, z));
+        }
+        __syncthreads();
+        if (need) {
+            for (int j = 0; j < tn && cnt < nsample; ++j) {
+                const float4 r = tile[j];
+                float dot = __fmul_rn(qx, r.x);
+                dot = __fmaf_rn(qy, r.y, dot);
+                dot = __fmaf_rn(qz, r.z, dot);
+                const float d = sqdist_from_dot(dot, qn, r.w);
+                if (!(d > r2)) {
+                    if (cnt == 0) first = t0 + j;
+                    o[cnt++] = t0 + j;
+                }
+            }
+        }
+    }
+    if (active)
+        for (int k = cnt; k < nsample; ++k) o[k] = first;
+}
+
+// generic C: one thread per query straight from global memory (not on any live model path)
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query_generic_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                          int64_t* __restrict__ idx_out, float r2, int N, int S, int C, int nsample) {
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * BQ_THREADS + threadIdx.x;
+    if (s >= S) return;
+    const float* q = new_xyz + ((size_t)b * S + s) * C;
+    float qn = __fmul_rn(q[0], q[0]);
+    for (int c = 1; c < C; ++c) qn = __fadd_rn(qn, __fmul_rn(q[c], q[c]));
+    int64_t* o = idx_out + ((size_t)b * S + s) * nsample;
+    int cnt = 0;
+    int64_t first = N;
+    for (int n = 0; n < N && cnt < nsample; ++n) {
+        const float* r = xyz + ((size_t)b * N + n) * C;
+        float dot = 0.f, rn = __fmul_rn(r[0], r[0]);
+        for (int c = 0; c < C; ++c) dot = __fmaf_rn(q[c], r[c], dot);
+        for (int c = 1; c < C; ++c) rn = __fadd_rn(rn, __fmul_rn(r[c], r[c]));
+        const float d = sqdist_from_dot(dot, qn, rn);
+        if (!(d > r2)) {
+            if (cnt == 0) first = n;
+            o[cnt++] = n;
+        }
+    }
+    for (int k = cnt; k < nsample; ++k) o[k] = first;
+}
+
+}  // namespace mpc
+
+MPC_API int mpc_knn_f32(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, int64_t B,
+                        int64_t N, int64_t S, int64_t C, int64_t K, mpc_stream_t stream) {
+    using namespace mpc;
+    if (!ref || !qry || !idx_out || B < 0 || N <= 0 || S < 0 || C <= 0 || K <= 0 || K > N) return MPC_ERR_INVALID;
+    if (K > 32 || C > 1024 || N > INT32_MAX || S > INT32_MAX || B > 65535) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int b = (int)B, n = (int)N, s = (int)S, c = (int)C;
+    if (K <= 3) {
+        if (K == 3) return launch_knn<3>(ref, qry, dist_out, idx_out, b, n, s, c, st);
+        if (K == 1) return launch_knn<1>(ref, qry, dist_out, idx_out, b, n, s, c, st);
+    }
+    if (K == 8) return launch_knn<8>(ref, qry, dist_out, idx_out, b, n, s, c, st);
+    if (K == 9) return launch_knn<9>(ref, qry, dist_out, idx_out, b, n, s, c, st);
+    if (K == 16) return launch_knn<16>(ref, qry, dist_out, idx_out, b, n, s, c, st);
+    if (K == 32) return launch_knn<32>(ref, qry, dist_out, idx_out, b, n, s, c, st);
+    return MPC_ERR_UNSUPPORTED;  // the host wrapper rounds K up to a supported list length and slices
+}
+
+MPC_API int mpc_ball_query_f32(const float* xyz, const float* new_xyz, int64_t* idx_out, float r2, int64_t B,
+                               int64_t N, int64_t S, int64_t C, int64_t nsample, mpc_stream_t stream) {
+    using namespace mpc;
+    if (!xyz || !new_xyz || !idx_out || B < 0 || N <= 0 || S < 0 || C <= 0 || nsample <= 0) return MPC_ERR_INVALID;
+    if (N > INT32_MAX || S > INT32_MAX || B > 65535 || nsample > INT32_MAX) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ceil_div(S, BQ_THREADS), (unsigned)B);
+    if (C == 3)
+        ball_query3_kernel<<<grid, BQ_THREADS, 0, st>>>(xyz, new_xyz, idx_out, r2, (int)N, (int)S, (int)nsample);
+    else
+        ball_query_generic_kernel<<<grid, BQ_THREADS, 0, st>>>(xyz, new_xyz, idx_out, r2, (int)N, (int)S, (int)C,
+                                                               (int)nsample);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}

@@ -1,0 +1,434 @@
+"""Point-set ops of the Markov encoder/decoder on B200: the reference's free functions, same names and
+argument order, backed by the hand-written sm_100a kernels in csrc/ through the C ABI (include/mpc_b200.h).
+
+R = Markov_Process_Analysis_on_Point_Cloud/ in the reference tree.  Mirrors R/modules/pointnet2_utils.py:13-222
+(and the byte-identical copies in R/modules/repsurface_utils.py:129-204).  The upstream `cuda=` / `is_group=`
+keyword arguments that reference call sites still pass are accepted and ignored.
+
+Every op runs on the caller's current CUDA stream, allocates only its outputs through torch, never
+synchronises, and raises if given CPU tensors: there is no CPU fallback.
+"""
+import contextlib
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, require_cuda
+
+_i64 = ctypes.c_int64
+_CHECK_INDEX = os.environ.get("MPC_CHECK_INDEX", "0") == "1"
+_KNN_LIST_LENGTHS = (1, 3, 8, 9, 16, 32)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("mpc_b200 kernels compute in float32, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _i64c(t):
+    return t.to(torch.int64).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# index injection / recording (test and debugging aid: feed another implementation's FPS / kNN indices
+# into this path so that float outputs can be compared without neighbour flips -- SURVEY.md 4 / H1)
+# ------------------------------------------------------------------------------------------------------
+class _IndexTape:
+    def __init__(self):
+        self.inject = None  # list of index tensors consumed in call order
+        self.record = None  # list that receives (kind, idx) in call order
+        self.fps_starts = None  # list of [B] int64 start tensors consumed in call order
+
+
+_tape = _IndexTape()
+
+
+@contextlib.contextmanager
+def index_tape(inject=None, record=None, fps_starts=None):
+    """inject: iterable of index tensors returned (in call order) by farthest_point_sample / knn_point
+    instead of computing them; record: list receiving ("fps"|"knn", idx); fps_starts: iterable of [B] start
+    indices used instead of drawing them from the CPU generator."""
+    old = (_tape.inject, _tape.record, _tape.fps_starts)
+    _tape.inject = list(inject) if inject is not None else None
+    _tape.record = record
+    _tape.fps_starts = list(fps_starts) if fps_starts is not None else None
+    try:
+        yield
+    finally:
+        _tape.inject, _tape.record, _tape.fps_starts = old
+
+
+def _taped(kind, device):
+    if _tape.inject is not None:
+        idx = _tape.inject.pop(0)
+        return idx.to(device=device, dtype=torch.int64).contiguous()
+    return None
+
+
+def _record(kind, idx):
+    if _tape.record is not None:
+        _tape.record.append((kind, idx))
+
+
+# ------------------------------------------------------------------------------------------------------
+# sampling / neighbour search (integer outputs, no gradient)
+# ------------------------------------------------------------------------------------------------------
+def draw_fps_start(B, N, device):
+    """The reference draws the start index on the CPU default generator and moves it to the device
+    (R/modules/pointnet2_utils.py:96); consuming the generator identically keeps runs comparable."""
+    if _tape.fps_starts is not None:
+        return _tape.fps_starts.pop(0).to(device=device, dtype=torch.int64)
+    return torch.randint(0, N, (B,), dtype=torch.long).to(device)
+
+
+@torch.no_grad()
+def farthest_point_sample(xyz, npoint, cuda=False, start=None):
+    """R/modules/pointnet2_utils.py:84-109.  xyz [B,N,C] -> int64 [B,npoint]; bit-exact with the reference
+    for C = 3 (same start index, same arithmetic order, lowest index on ties)."""
+    require_cuda(xyz)
+    B, N, C = xyz.shape
+    if start is None:
+        start = draw_fps_start(B, N, xyz.device)  # drawn even when injecting: RNG consumption stays identical
+    taped = _taped("fps", xyz.device)
+    if taped is not None:
+        _record("fps", taped)
+        return taped
+    xyz = _f32c(xyz.detach())
+    start = _i64c(start.to(xyz.device))
+    out = torch.empty(B, npoint, dtype=torch.int64, device=xyz.device)
+    call("mpc_fps_f32", ptr(xyz), ptr(start), ptr(out), _i64(B), _i64(N), _i64(C), _i64(npoint))
+    _record("fps", out)
+    return out
+
+
+def _list_length(k):
+    for L in _KNN_LIST_LENGTHS:
+        if k <= L:
+            return L
+    raise ValueError("knn_point supports nsample <= %d, got %d" % (_KNN_LIST_LENGTHS[-1], k))
+
+
+@torch.no_grad()
+def knn_point(nsample, xyz, new_xyz):
+    """R/modules/pointnet2_utils.py:211-222.  NOTE the reference's argument order: (k, reference set
+    [B,N,C], queries [B,S,C]) -> (dist [B,S,k] ascending, idx int64 [B,S,k]).  Equal distances resolve to
+    the lower index (torch.topk leaves it undefined)."""
+    require_cuda(xyz, new_xyz)
+    B, N, C = xyz.shape
+    S = new_xyz.shape[1]
+    if nsample > N:
+        raise RuntimeError("selected index k out of range")  # what torch.topk raises in the reference
+    taped = _taped("knn", xyz.device)
+    xyz, new_xyz = _f32c(xyz.detach()), _f32c(new_xyz.detach())
+    L = _list_length(nsample)  # the kernels keep sorted lists of these lengths; a longer list is sliced
+    if L > N:
+        raise ValueError("knn_point: k=%d with only N=%d reference points is not supported" % (nsample, N))
+    dist = torch.empty(B, S, L, dtype=torch.float32, device=xyz.device)
+    idx = torch.empty(B, S, L, dtype=torch.int64, device=xyz.device)
+    call("mpc_knn_f32", ptr(xyz), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N), _i64(S), _i64(C), _i64(L))
+    if L != nsample:
+        dist, idx = dist[:, :, :nsample].contiguous(), idx[:, :, :nsample].contiguous()
+    if taped is not None:
+        idx = taped
+    _record("knn", idx)
+    return dist, idx
+
+
+def query_knn_point(k, xyz, new_xyz, cuda=False):
+    """Upstream RepSurf name still used by reference call sites (R/modules/repsurface_utils.py:111,
+    R/modules/recons_utils.py:19): indices only."""
+    return knn_point(k, xyz, new_xyz)[1]
+
+
+def square_distance(src, dst):
+    """R/modules/pointnet2_utils.py:190-209: dense [B,N,M] expanded-form distances.  Provided for API
+    completeness (the kernels never materialise this matrix); computed as a full-length sorted neighbour
+    list scattered back would be wasteful, so this is the one function kept as a plain ATen expression."""
+    require_cuda(src, dst)
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    dist += torch.sum(src ** 2, -1).view(B, N, 1)
+    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
+    return dist
+
+
+@torch.no_grad()
+def query_ball_point(radius, nsample, xyz, new_xyz, cuda=False):
+    """R/modules/pointnet2_utils.py:112-134 -> int64 [B,S,nsample] (ascending index order, padded with the
+    first hit, N where a query has no hit)."""
+    require_cuda(xyz, new_xyz)
+    B, N, C = xyz.shape
+    S = new_xyz.shape[1]
+    xyz, new_xyz = _f32c(xyz.detach()), _f32c(new_xyz.detach())
+    out = torch.empty(B, S, nsample, dtype=torch.int64, device=xyz.device)
+    r2 = ctypes.c_float(float(np.float32(radius ** 2)))
+    call("mpc_ball_query_f32", ptr(xyz), ptr(new_xyz), ptr(out), r2, _i64(B), _i64(N), _i64(S), _i64(C),
+         _i64(nsample))
+    return out
+
+
+def _check_index(idx, n, what):
+    if _CHECK_INDEX and idx.numel():
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0 or hi >= n:
+            raise RuntimeError("%s: index out of range [0, %d): min %d max %d" % (what, n, lo, hi))
+
+
+# ------------------------------------------------------------------------------------------------------
+# gather / group
+# ------------------------------------------------------------------------------------------------------
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        B, N, C = points.shape
+        M = idx.numel() // B if B else 0
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
+        call("mpc_gather_f32", ptr(points), ptr(idx), ptr(out), _i64(B), _i64(N), _i64(M), _i64(C))
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, N, M, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, N, M, C = ctx.dims
+        grad_out = _f32c(grad_out)
+        grad_points = torch.empty(B, N, C, dtype=torch.float32, device=grad_out.device)
+        call("mpc_gather_bwd_f32", ptr(grad_out), ptr(idx), ptr(grad_points), _i64(B), _i64(N), _i64(M), _i64(C))
+        return grad_points, None
+
+
+def index_points(points, idx, cuda=False, is_group=False):
+    """R/modules/pointnet2_utils.py:64-81.  points [B,N,C], idx [B,S] or [B,S,K] (int64) ->
+    [B,S,C] / [B,S,K,C].  float32 payloads are differentiable (backward = scatter-add); int64 payloads
+    (the composed FPS index chains of Fuse.forward) are moved bit-for-bit."""
+    require_cuda(points, idx)
+    idx = _i64c(idx)
+    B, N, C = points.shape
+    _check_index(idx, N, "index_points")
+    if points.dtype == torch.float32:
+        return _Gather.apply(_f32c(points), idx)
+    if points.dtype == torch.int64:
+        points = points.contiguous()
+        M = idx.numel() // B if B else 0
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.int64, device=points.device)
+        if C == 1:
+            call("mpc_gather_i64", ptr(points), ptr(idx), ptr(out), _i64(B), _i64(N), _i64(M))
+        else:  # an int64 row of C values is a float32 row of 2C values as far as a byte mover cares
+            call("mpc_gather_f32", ptr(points), ptr(idx), ptr(out), _i64(B), _i64(N), _i64(M), _i64(2 * C))
+        return out
+    raise TypeError("index_points supports float32 and int64 payloads, got %s" % points.dtype)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Markov state transition
+# ------------------------------------------------------------------------------------------------------
+class _Transition(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx, n_out):
+        B, S, C = points.shape
+        K = idx.shape[2]
+        out = torch.empty(B, n_out, C, dtype=torch.float32, device=points.device)
+        cnt = torch.empty(B, n_out, dtype=torch.float32, device=points.device)
+        call("mpc_transition_fwd_f32", ptr(points), ptr(idx), ptr(out), ptr(cnt), _i64(B), _i64(S), _i64(K),
+             _i64(C), _i64(n_out))
+        ctx.save_for_backward(idx, cnt)
+        ctx.dims = (B, S, K, C, n_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, cnt = ctx.saved_tensors
+        B, S, K, C, n_out = ctx.dims
+        grad_out = _f32c(grad_out)
+        g = torch.empty(B, S, C, dtype=torch.float32, device=grad_out.device)
+        call("mpc_transition_bwd_f32", ptr(grad_out), ptr(idx), ptr(cnt), ptr(g), _i64(B), _i64(S), _i64(K),
+             _i64(C), _i64(n_out))
+        return g, None, None
+
+
+def upsample(points, knn_idx, scale_ratio=2, dist=None, n_out=None):
+    """The Markov state transition, R/modules/pointnet2_utils.py:13-50: out = D^-1 A^T points with A the
+    S x N kNN incidence (K ones per row) and D the count-normalisation of :44-48.  points [B,S,C], knn_idx
+    [B,S,K] with values < S*scale_ratio -> [B, S*scale_ratio, C].  `dist` is accepted and ignored, as in the
+    reference (:30-34).  n_out overrides S*scale_ratio (sizes that are not an integer multiple)."""
+    require_cuda(points, knn_idx)
+    S = points.shape[1]
+    if n_out is None:
+        n_out = S * scale_ratio
+    knn_idx = _i64c(knn_idx)
+    _check_index(knn_idx, n_out, "upsample")
+    return _Transition.apply(_f32c(points), knn_idx, int(n_out))
+
+
+# ------------------------------------------------------------------------------------------------------
+# three_nn / three_interpolate
+# ------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def three_nn(xyz1, xyz2):
+    """R/modules/pointnet2_utils.py:899-901: for every xyz1 point the 3 nearest xyz2 points (expanded-form
+    distances, ascending) -> (dist [B,N,3], idx int64 [B,N,3])."""
+    return knn_point(3, xyz2, xyz1)
+
+
+class ThreeInterpolate(torch.autograd.Function):
+    """R/modules/pointnet2_utils.py:903-906 as an autograd Function: inverse-distance weights
+    1/(d+1e-8) normalised over the 3 neighbours, weighted sum of the gathered rows."""
+
+    @staticmethod
+    def forward(ctx, points2, dist, idx):
+        B, S, C = points2.shape
+        N = idx.shape[1]
+        weight = torch.empty(B, N, 3, dtype=torch.float32, device=points2.device)
+        out = torch.empty(B, N, C, dtype=torch.float32, device=points2.device)
+        call("mpc_three_interpolate_fwd_f32", ptr(points2), ptr(dist), ptr(idx), ptr(weight), ptr(out), _i64(B),
+             _i64(N), _i64(S), _i64(C))
+        ctx.save_for_backward(idx, weight)
+        ctx.dims = (B, N, S, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        B, N, S, C = ctx.dims
+        grad_out = _f32c(grad_out)
+        g = torch.empty(B, S, C, dtype=torch.float32, device=grad_out.device)
+        call("mpc_three_interpolate_bwd_f32", ptr(grad_out), ptr(weight), ptr(idx), ptr(g), _i64(B), _i64(N),
+             _i64(S), _i64(C))
+        return g, None, None
+
+
+def three_interpolate(points2, dist, idx):
+    require_cuda(points2, dist, idx)
+    return ThreeInterpolate.apply(_f32c(points2), _f32c(dist.detach()), _i64c(idx))
+
+
+# ------------------------------------------------------------------------------------------------------
+# difference-wise attention core
+# ------------------------------------------------------------------------------------------------------
+class AttnFeat(torch.autograd.Function):
+    """LocalTrans core, feature branch (R/modules/pointnet2_utils.py:553-569).  q [B,S,C]; kv [B,N,2C] holds
+    the projected keys in columns [0,C) and values in [C,2C) (one fused projection); idx [B,S,K]."""
+
+    @staticmethod
+    def forward(ctx, q, kv, idx):
+        B, S, C = q.shape
+        N = kv.shape[1]
+        K = idx.shape[2]
+        out = torch.empty(B, S, C, dtype=torch.float32, device=q.device)
+        call("mpc_attn_feat_fwd_f32", ptr(q), _i64(C), ptr(kv), ctypes.c_void_p(kv.data_ptr() + 4 * C),
+             _i64(2 * C), ptr(idx), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C))
+        ctx.save_for_backward(q, kv, idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_ctx):
+        q, kv, idx = ctx.saved_tensors
+        B, S, C = q.shape
+        N = kv.shape[1]
+        K = idx.shape[2]
+        grad_ctx = _f32c(grad_ctx)
+        gq = torch.empty_like(q)
+        gkv = torch.zeros_like(kv)
+        call("mpc_attn_feat_bwd_f32", ptr(grad_ctx), ptr(q), _i64(C), ptr(kv),
+             ctypes.c_void_p(kv.data_ptr() + 4 * C), _i64(2 * C), ptr(idx), ptr(gq), _i64(C), ptr(gkv),
+             ctypes.c_void_p(gkv.data_ptr() + 4 * C), _i64(2 * C), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C))
+        return gq, gkv, None
+
+
+class AttnXyz(torch.autograd.Function):
+    """LocalTrans core, coordinate branch (R/modules/pointnet2_utils.py:520-544) with the q/k/v projections
+    of the Cin-channel differences computed inside the kernel."""
+
+    @staticmethod
+    def forward(ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv):
+        B, N, Cin = feat.shape
+        S, K = idx.shape[1], idx.shape[2]
+        C = wq.shape[0]
+        out = torch.empty(B, S, C, dtype=torch.float32, device=feat.device)
+        call("mpc_attn_xyz_fwd_f32", ptr(feat), ptr(center_idx), ptr(idx), ptr(wq), ptr(bq), ptr(wk), ptr(bk),
+             ptr(wv), ptr(bv), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C))
+        ctx.save_for_backward(feat, idx, wq, bq, wk, bk, wv, bv)
+        ctx.center_idx = center_idx
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_ctx):
+        feat, idx, wq, bq, wk, bk, wv, bv = ctx.saved_tensors
+        center_idx = ctx.center_idx
+        B, N, Cin = feat.shape
+        S, K = idx.shape[1], idx.shape[2]
+        C = wq.shape[0]
+        grad_ctx = _f32c(grad_ctx)
+        gw = torch.zeros(3, C, Cin, dtype=torch.float32, device=feat.device)
+        gb = torch.zeros(3, C, dtype=torch.float32, device=feat.device)
+        gfeat = torch.zeros_like(feat) if ctx.needs_input_grad[0] else None
+        call("mpc_attn_xyz_bwd_f32", ptr(grad_ctx), ptr(feat), ptr(center_idx), ptr(idx), ptr(wq), ptr(bq), ptr(wk),
+             ptr(bk), ptr(wv), ptr(bv), ptr(gw[0]), ptr(gb[0]), ptr(gw[1]), ptr(gb[1]), ptr(gw[2]), ptr(gb[2]),
+             ptr(gfeat), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C))
+        return gfeat, None, None, gw[0], gb[0], gw[1], gb[1], gw[2], gb[2]
+
+
+# ------------------------------------------------------------------------------------------------------
+# BatchNorm1d-over-channels + LeakyReLU on the [M,C] view
+# ------------------------------------------------------------------------------------------------------
+class BNAct(torch.autograd.Function):
+    """Tail of the reference's `Linear` block (R/modules/pointnet2_utils.py:417-423) with bn=False (=> BatchNorm1d)
+    on the [M,C] view.  Running statistics are updated in place exactly like nn.BatchNorm1d (momentum 0.1,
+    unbiased variance into running_var)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, num_batches_tracked, training, momentum, eps,
+                slope):
+        M, C = y.shape
+        dev = y.device
+        if training:
+            if M <= 1:
+                raise ValueError("Expected more than 1 value per channel when training, got input size %s"
+                                 % (tuple(y.shape),))
+            scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            stats = torch.empty(2 * C, dtype=torch.float32, device=dev)
+            call("mpc_bn_stats_f32", ptr(y), ptr(stats), ptr(running_mean), ptr(running_var),
+                 ptr(num_batches_tracked), ctypes.c_float(momentum), ptr(scratch), _i64(M), _i64(C))
+            mean, var = stats[:C], stats[C:]
+        else:
+            mean, var = running_mean, running_var
+        out = torch.empty_like(y)
+        call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
+             ctypes.c_float(slope), ptr(out), _i64(M), _i64(C))
+        ctx.save_for_backward(y, mean, var, gamma, beta)
+        ctx.cfg = (training, eps, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        y, mean, var, gamma, beta = ctx.saved_tensors
+        training, eps, slope = ctx.cfg
+        M, C = y.shape
+        grad_out = _f32c(grad_out)
+        gy = torch.empty_like(y)
+        gg = torch.empty(C, dtype=torch.float32, device=y.device)
+        gb = torch.empty(C, dtype=torch.float32, device=y.device)
+        scratch = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+        call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
+             ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
+             ptr(gb), ptr(scratch), _i64(M), _i64(C))
+        return gy, gg, gb, None, None, None, None, None, None, None
+
+
+def bn_act(y2d, gamma, beta, running_mean, running_var, num_batches_tracked, training, momentum=0.1, eps=1e-5,
+           slope=0.2):
+    """slope = 1.0 means no activation (Linear(..., act=False))."""
+    require_cuda(y2d)
+    return BNAct.apply(_f32c(y2d), gamma, beta, running_mean, running_var, num_batches_tracked, bool(training),
+                       float(momentum), float(eps), float(slope))
+
+
+def launches():
+    """C-ABI calls issued so far in this process (each enqueues one or more of our kernels)."""
+    return _lib.launch_count

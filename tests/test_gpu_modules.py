@@ -1,0 +1,257 @@
+"""nn.Module level parity on the GPU: the drop-in modules (same state_dict) vs the golden fixtures produced by
+the real reference, and vs the CPU oracle at other sizes.  Float tolerances are written per test; where the
+comparison would otherwise hinge on an arbitrary choice among exactly tied neighbours (feature-space kNN after a
+transition), the reference's / oracle's indices are injected through ops.index_tape."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import tape_of
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def synth(orc, specs, name):
+    return orc.synthetic_state_dict([tuple(e) for e in specs[name]])
+
+
+def close_grad(ours, theirs, key):
+    scale = float(np.abs(theirs).max())
+    if scale < 1e-3:  # true-zero gradients (bias in front of a train-mode BatchNorm): rounding noise both sides
+        assert float(np.abs(ours).max()) < 2e-3, key
+    else:
+        np.testing.assert_allclose(ours, theirs, rtol=2e-3, atol=2e-4 + 2e-3 * scale, err_msg=key)
+
+
+def test_linear_block(mpc, orc, golden_blocks, golden_specs):
+    g = golden_blocks
+    m = mpc.pointnet2_utils.Linear(12, 20, bn=False)
+    m.load_state_dict(synth(orc, golden_specs, "linear"))
+    m.cuda().train()
+    x = T(g["linear_x"]).cuda()
+    np.testing.assert_allclose(m(x).detach().cpu().numpy(), g["linear_train"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m.norm2.running_mean.cpu().numpy(), g["linear_rm"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.norm2.running_var.cpu().numpy(), g["linear_rv"], rtol=1e-5, atol=1e-6)
+    assert int(m.norm2.num_batches_tracked) == 1
+    m.eval()
+    np.testing.assert_allclose(m(x).detach().cpu().numpy(), g["linear_eval"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name,in_c,out_c,res,use_xyz,use_fps",
+                         [("xyz", 3, 32, True, True, True), ("feat", 16, 32, True, False, True),
+                          ("dec", 16, 16, False, False, False), ("xyz0", 3, 64, True, True, False)])
+def test_local_trans(mpc, orc, golden_blocks, golden_specs, name, in_c, out_c, res, use_xyz, use_fps):
+    g = golden_blocks
+    m = mpc.pointnet2_utils.LocalTrans(in_c, out_c, 8, residual=res)
+    m.load_state_dict(synth(orc, golden_specs, "lt_" + name))
+    m.cuda().train()
+    f = T(g["lt_xyz"] if use_xyz else g["lt_feat"]).cuda().requires_grad_(True)
+    idx = T(g["lt_idx"] if use_fps else g["lt_idx_self"]).cuda()
+    y = m(features=f, idx=idx, pos=None, FPS_idx=T(g["lt_fps"]).cuda() if use_fps else None, xyz=use_xyz)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g["lt_%s_out" % name], rtol=1e-4, atol=1e-5)
+    (y * T(g["lt_%s_w" % name]).cuda()).sum().backward()
+    np.testing.assert_allclose(f.grad.cpu().numpy(), g["lt_%s_gin" % name], rtol=1e-3, atol=1e-4)
+    n = 0
+    params = dict(m.named_parameters())
+    for k in g.files:
+        if k.startswith("lt_%s_g." % name):
+            key = k.split("_g.", 1)[1]
+            close_grad(params[key].grad.cpu().numpy(), g[k], key)
+            n += 1
+    assert n >= 8
+
+
+@pytest.mark.parametrize("variant", ["seg", "cls"])
+def test_local_merge(mpc, orc, golden_blocks, golden_specs, variant):
+    g = golden_blocks
+    mod = mpc.pointnet2_utils if variant == "seg" else mpc.repsurface_utils
+    m = mod.LocalMerge(16, 32, 8, residual=True)
+    m.load_state_dict(synth(orc, golden_specs, "lm_" + variant))
+    m.cuda().eval()
+    xyz, fpsi = T(g["lt_xyz"]).cuda(), T(g["lt_fps"]).cuda()
+    rec = []
+    with mpc.ops.index_tape(record=rec):
+        y, _, idx, dist = m(xyz=mpc.ops.index_points(xyz, fpsi), base_xyz=xyz, normal=xyz,
+                            feature=T(g["lt_feat"]).cuda(), FPS_idx=fpsi)
+    assert np.array_equal(idx.cpu().numpy(), g["lm_%s_idx" % variant])
+    assert np.array_equal(dist.cpu().numpy(), g["lm_%s_dist" % variant])
+    for (kind, ours), (gkind, theirs) in zip(rec, tape_of(g, "lm_%s_tape" % variant)):
+        assert kind == gkind and np.array_equal(ours.cpu().numpy(), theirs)  # incl. the feature-space kNN
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g["lm_%s_out" % variant], rtol=1e-4, atol=1e-5)
+
+
+def test_feature_propagation(mpc, orc, golden_blocks, golden_specs):
+    g = golden_blocks
+    m = mpc.pointnet2_utils.PointNetFeaturePropagation(16, [24], act=True)
+    m.load_state_dict(synth(orc, golden_specs, "fp"))
+    m.cuda().train()
+    xyz = T(g["lt_xyz"]).cuda()
+    sub = mpc.ops.index_points(xyz, T(g["lt_fps"]).cuda())
+    p2 = T(g["fp_p2"]).cuda().requires_grad_(True)
+    y = m(xyz, sub, None, p2)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g["fp_out"], rtol=1e-4, atol=1e-5)
+    (y * T(g["fp_w"]).cuda()).sum().backward()
+    np.testing.assert_allclose(p2.grad.cpu().numpy(), g["fp_gp2"], rtol=1e-3, atol=1e-5)
+
+
+def _starts(tape):
+    return [T(t[:, 0].copy()) for kind, t in tape if kind == "fps"]
+
+
+def _cls(mpc, orc, specs):
+    m = mpc.task_models.Model(argparse.Namespace(num_point=1024, return_dist=True, cuda_ops=True, num_class=40))
+    m.load_state_dict(synth(orc, specs, "cls"))
+    m.drop1.p = m.drop2.p = 0.0
+    return m.cuda()
+
+
+def _seg(mpc, orc, specs):
+    m = mpc.task_models.get_model(50)
+    m.load_state_dict(synth(orc, specs, "seg"))
+    m.drop1.p = m.drop2.p = 0.0
+    return m.cuda()
+
+
+def _index_agreement(rec, theirs):
+    """Fraction of kNN rows / FPS entries that differ from the reference run (no injection)."""
+    bad = tot = 0
+    for (k1, a), (k2, b) in zip(rec, theirs):
+        assert k1 == k2 and tuple(a.shape) == tuple(b.shape)
+        d = a.cpu().numpy() != b
+        rows = d.any(axis=-1) if k1 == "knn" else d
+        bad += int(rows.sum())
+        tot += rows.size
+    return bad / tot
+
+
+def test_cls_model_eval_free_running(mpc, orc, golden_models, golden_specs):
+    """No injection: the GPU path computes every index itself."""
+    g = golden_models
+    m = _cls(mpc, orc, golden_specs).eval()
+    theirs = tape_of(g, "cls_eval_tape")
+    rec = []
+    with torch.no_grad(), mpc.ops.index_tape(record=rec, fps_starts=_starts(theirs)):
+        y = m(T(g["cls_points"][:2]).cuda())
+    assert _index_agreement(rec, theirs) <= 2e-3
+    np.testing.assert_allclose(y.cpu().numpy(), g["cls_eval_out"], rtol=1e-3, atol=1e-3)
+
+
+def test_cls_model_train_grads(mpc, orc, golden_models, golden_specs):
+    g = golden_models
+    m = _cls(mpc, orc, golden_specs).train()
+    theirs = tape_of(g, "cls_train_tape")
+    with mpc.ops.index_tape(inject=[T(t) for _, t in theirs], fps_starts=_starts(theirs)):
+        y = m(T(g["cls_points"]).cuda())
+    loss = mpc.task_models.SmoothClsLoss()(y, T(g["cls_target"]).cuda())
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["cls_train_loss"], rtol=1e-4)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g["cls_train_out"], rtol=1e-3, atol=5e-4)
+    np.testing.assert_allclose(m.keepHigh.la1.fc2.norm2.running_mean.cpu().numpy(),
+                               g["cls_train_rm.keepHigh.la1.fc2.norm2"], rtol=1e-4, atol=1e-5)
+    params = dict(m.named_parameters())
+    n = 0
+    for k in g.files:
+        if k.startswith("cls_grad."):
+            key = k[len("cls_grad."):]
+            ours = params[key].grad
+            assert ours is not None, key
+            assert abs(float(ours.norm()) - g[k][0]) <= 1e-2 * g[k][0] + 5e-4, (key, float(ours.norm()), g[k][0])
+            n += 1
+    assert n >= 150
+    unused = [k for k, p in params.items() if p.grad is None]
+    assert all(("normal_Trans" in k or "norm1" in k or ".fc1." in k or "start" in k or "final." in k
+                or "la0.feature_Trans" in k) for k in unused), unused[:5]
+
+
+def test_seg_model_eval(mpc, orc, golden_models, golden_specs):
+    g = golden_models
+    m = _seg(mpc, orc, golden_specs).eval()
+    theirs = tape_of(g, "seg_eval_tape")
+    with torch.no_grad(), mpc.ops.index_tape(inject=[T(t) for _, t in theirs], fps_starts=_starts(theirs)):
+        y, _ = m(T(g["seg_xyz"][:1]).cuda(), T(g["seg_label"][:1]).cuda())
+    np.testing.assert_allclose(y.cpu().numpy(), g["seg_eval_out"], rtol=2e-3, atol=2e-3)
+    # free-running: coordinate-space kNN / FPS must agree exactly, feature-space ties may differ
+    rec = []
+    with torch.no_grad(), mpc.ops.index_tape(record=rec, fps_starts=_starts(theirs)):
+        y2, _ = m(T(g["seg_xyz"][:1]).cuda(), T(g["seg_label"][:1]).cuda())
+    assert _index_agreement(rec, theirs) <= 0.35
+    for (k1, a), (_, b) in zip(rec, theirs):
+        if k1 == "fps":
+            assert np.array_equal(a.cpu().numpy(), b)
+    np.testing.assert_allclose(y2.cpu().numpy(), g["seg_eval_out"], rtol=5e-3, atol=5e-3)
+
+
+def test_seg_model_train_grads(mpc, orc, golden_models, golden_specs):
+    g = golden_models
+    m = _seg(mpc, orc, golden_specs).train()
+    theirs = tape_of(g, "seg_train_tape")
+    with mpc.ops.index_tape(inject=[T(t) for _, t in theirs], fps_starts=_starts(theirs)):
+        y, _ = m(T(g["seg_xyz"]).cuda(), T(g["seg_label"]).cuda())
+    loss = mpc.task_models.get_loss()(y.reshape(-1, 50), T(g["seg_target"]).cuda(), None)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["seg_train_loss"], rtol=1e-4)
+    np.testing.assert_allclose(y.detach().cpu().numpy()[:, ::8], g["seg_train_out"], rtol=2e-3, atol=2e-3)
+    params = dict(m.named_parameters())
+    n = 0
+    for k in g.files:
+        if k.startswith("seg_grad."):
+            key = k[len("seg_grad."):]
+            ours = params[key].grad
+            assert ours is not None, key
+            assert abs(float(ours.norm()) - g[k][0]) <= 1e-2 * g[k][0] + 5e-4, (key, float(ours.norm()), g[k][0])
+            n += 1
+    assert n >= 400
+
+
+def test_seg_generalised_sizes_vs_oracle(mpc, orc, golden_specs):
+    """N = 1024 and N = 3000 (24k-block config shape, reduced): stage sizes follow N/2..N/16; compared with the
+    CPU oracle under index injection."""
+    for N in (1024, 3000):
+        P = synth(orc, golden_specs, "seg")
+        m = _seg(mpc, orc, golden_specs).eval()
+        gen = torch.Generator().manual_seed(N)
+        xyz = torch.rand(2, 3, N, generator=gen) * 2 - 1
+        lab = torch.eye(16)[torch.randint(0, 16, (2,), generator=gen)].unsqueeze(1)
+        ctx = orc.Ctx(train=False)
+        torch.manual_seed(3)
+        with torch.no_grad():
+            ref = orc.partseg_model(P, xyz, lab, ctx)
+        starts = [t[:, 0].clone() for k, t in ctx.tape if k == "fps"]
+        with torch.no_grad(), mpc.ops.index_tape(inject=[t for _, t in ctx.tape], fps_starts=starts):
+            y, _ = m(xyz.cuda(), lab.cuda())
+        torch.testing.assert_close(y.cpu(), ref, rtol=2e-3, atol=2e-3)
+
+
+def test_full_size_properties(mpc, orc, golden_specs):
+    """BASELINE config 2 shape (32 x 2048, train, fwd+bwd): size-independent properties."""
+    m = _seg(mpc, orc, golden_specs).train()
+    gen = torch.Generator().manual_seed(0)
+    xyz = (torch.rand(32, 3, 2048, generator=gen) * 2 - 1).cuda()
+    lab = torch.eye(16)[torch.randint(0, 16, (32,), generator=gen)].unsqueeze(1).cuda()
+    rec = []
+    with mpc.ops.index_tape(record=rec):
+        y, _ = m(xyz, lab)
+    loss = mpc.task_models.get_loss()(y.reshape(-1, 50), torch.randint(0, 50, (32 * 2048,), generator=gen).cuda(), None)
+    loss.backward()
+    assert y.shape == (32, 2048, 50) and torch.isfinite(y).all() and torch.isfinite(loss)
+    for kind, idx in rec:
+        if kind == "fps":  # FPS picks distinct points
+            s = idx.sort(dim=1)[0]
+            assert (s[:, 1:] != s[:, :-1]).all()
+        else:  # neighbours of one query are distinct
+            s = idx.sort(dim=2)[0]
+            assert (s[:, :, 1:] != s[:, :, :-1]).all()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    # transition: linear in its input, rows are means (a constant field maps to the constant on reached rows)
+    knn = [i for k, i in rec if k == "knn"][2]  # la1's coordinate kNN: 1024 queries inside 2048 points
+    a, b = torch.randn(32, 1024, 64, device="cuda"), torch.randn(32, 1024, 64, device="cuda")
+    up = mpc.ops.upsample
+    torch.testing.assert_close(up(a + 2 * b, knn), up(a, knn) + 2 * up(b, knn), rtol=1e-4, atol=1e-4)
+    ones = up(torch.ones(32, 1024, 64, device="cuda"), knn)
+    assert ((ones - 1).abs() < 1e-6).logical_or(ones == 0).all()

@@ -1,0 +1,358 @@
+"""Benchmark of the point-set hot path: point clouds/s on the part-segmentation training step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--profile-ops FILE]
+
+Workload (config.workload = BASELINE.json configs[1]): ShapeNetPart-shaped part segmentation, 32 clouds x 2048
+points per GPU, full Markov encoder + transition decoder, forward + backward, synthetic data, random-init weights.
+One "step" = zero the flat gradient buffer, forward, label-smoothed loss, backward, and for N > 1 the NCCL
+all-reduce of the flat fp32 gradient (the path's one real exchange step).  Per-GPU work is fixed as N grows
+(weak scaling): value = N * 32 * K clouds / max-over-ranks device time.
+
+Own arm:   `value` = device-resident inputs, timed with CUDA events around every step (L2 flushed between timed
+           steps, flush outside the events); `e2e` = the same step through the public module call with the step's
+           inputs copied from pinned host memory and the loss read back, copies inside the timed region.
+           `roofline` = the dominant kernel of ours inside the timed region (per-launch CUDA events on the launching
+           stream, algorithmic bytes from SURVEY.md 8d) against MEASURED_PEAKS.json.  `cpu_baseline` = the CPU
+           oracle (port of the reference path, torch CPU ops + C) on a bounded sample (rank 0, N = 1 only).
+--impl reference: the reference's CPU implementation of the same path.  /root/reference is pure Python and does
+           not exist on the GPU box, so this arm times the oracle port (oracle/markov_oracle.py) with all host
+           threads on a bounded sample (4 clouds x 2048 points per step) of the same workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "markov-process-analysis-on-point-cloud_b200"
+
+B_PER_GPU = 32
+N_POINTS = 2048
+N_CLASSES = 50
+CPU_SAMPLE_B = 4
+METRIC = "point clouds/s (part-seg 32x2048 fwd+bwd per GPU)"
+UNIT = "clouds/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_batch(B, gen):
+    xyz = torch.rand(B, 3, N_POINTS, generator=gen) * 2 - 1
+    label = torch.eye(16)[torch.randint(0, 16, (B,), generator=gen)].unsqueeze(1)
+    target = torch.randint(0, N_CLASSES, (B * N_POINTS,), generator=gen)
+    return xyz, label, target
+
+
+def fps_starts(B, gen):
+    """The four FPS start draws of one forward (pointnet2_utils.py:96: randint(0, N_state, (B,)) per call)."""
+    return [torch.randint(0, n, (B,), generator=gen, dtype=torch.long)
+            for n in (N_POINTS, N_POINTS // 2, N_POINTS // 4, N_POINTS // 8)]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores, bounded sample
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup):
+    from oracle import markov_oracle as orc
+
+    orc.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mpc = importlib.import_module(PKG)
+    torch.manual_seed(0)
+    model = mpc.task_models.get_model(N_CLASSES)  # only used as the source of a random-init state_dict (CPU)
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k)
+         for k, v in model.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    xyz, label, target = synth_batch(CPU_SAMPLE_B, gen)
+    times = []
+    for it in range(warmup + steps):
+        for p in P.values():
+            p.grad = None
+        t0 = time.perf_counter()
+        ctx = orc.Ctx(train=True, fps_starts=fps_starts(CPU_SAMPLE_B, gen))
+        out = orc.partseg_model(P, xyz, label, ctx)
+        loss = orc.partseg_loss(out.reshape(-1, N_CLASSES), target)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": CPU_SAMPLE_B / (ms / 1e3), "ms_per_step": ms, "cores": cores,
+            "sample": "%d clouds x %d points per step, fwd+bwd, %d steps after %d warm-up (oracle port, torch CPU "
+                      "ops + C)" % (CPU_SAMPLE_B, N_POINTS, steps, warmup)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ShapeNetPart-shaped part segmentation, 32x2048 fwd+bwd (BASELINE configs[1]); "
+                               "bounded CPU sample", "points": N_POINTS, "classes": N_CLASSES},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------------
+class Step:
+    """One training step of the part-seg model on one GPU through the drop-in modules."""
+
+    def __init__(self, mpc, device, world):
+        self.mpc = mpc
+        self.world = world
+        torch.manual_seed(0)
+        self.model = mpc.task_models.get_model(N_CLASSES).to(device).train()
+        self.loss_fn = mpc.task_models.get_loss()
+        params = [p for p in self.model.parameters()]
+        total = sum(p.numel() for p in params)
+        # flat fp32 gradient bucket: .grad of every parameter is a view into it (one memset, one all-reduce)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for p in params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def __call__(self, xyz, label, target, starts):
+        self.flat_grad.zero_()
+        with self.mpc.ops.index_tape(fps_starts=starts):
+            out, _ = self.model(xyz, label)
+        loss = self.loss_fn(out.reshape(-1, N_CLASSES), target, None)
+        loss.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad)
+            self.flat_grad.mul_(1.0 / self.world)
+        return loss
+
+
+def op_table(records):
+    rows = []
+    for name, recs in records.items():
+        ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        by = sum(c for _, _, c in recs)
+        rows.append((name, len(recs), ms, by))
+    rows.sort(key=lambda r: -r[2])
+    return rows
+
+
+def run_own(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    mpc = importlib.import_module(PKG)
+    mpc._lib.load()
+    step = Step(mpc, device, world)
+    gen = torch.Generator().manual_seed(1 + rank)
+    B = B_PER_GPU
+    xyz_h, label_h, target_h = (t.pin_memory() for t in synth_batch(B, gen))
+    xyz, label, target = xyz_h.to(device), label_h.to(device), target_h.to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def device_starts():
+        return [s.pin_memory().to(device, non_blocking=True) for s in fps_starts(B, gen)]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (>= 3), then one fully instrumented step to find the dominant kernel of ours
+    W = max(3, args.warmup)
+    for _ in range(W):
+        step(xyz, label, target, device_starts())
+    torch.cuda.synchronize()
+    mpc._lib.profiler = {"names": None, "records": {}}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    step(xyz, label, target, device_starts())
+    ev1.record()
+    torch.cuda.synchronize()
+    full = op_table(mpc._lib.profiler["records"])
+    instrumented_step_ms = ev0.elapsed_time(ev1)
+    mpc._lib.profiler = None
+    dominant = full[0][0]
+    if args.profile_ops and rank == 0:
+        with open(args.profile_ops, "w") as f:
+            f.write("# one instrumented step (%.3f ms incl. event overhead); per C-ABI entry point\n" % instrumented_step_ms)
+            f.write("%-34s %6s %10s %12s %9s\n" % ("entry point", "calls", "ms", "algo MB", "GB/s"))
+            for name, n, ms, by in full:
+                f.write("%-34s %6d %10.3f %12.2f %9.1f\n" % (name, n, ms, by / 1e6, by / 1e6 / max(ms, 1e-9)))
+            f.write("%-34s %6s %10.3f\n" % ("sum of ours", "", sum(r[2] for r in full)))
+
+    # ---- timed region: device-resident inputs, per-step events, L2 flush between steps (outside the events)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    mpc._lib.profiler = {"names": {dominant}, "records": {}}
+    k0 = mpc.ops.kernels_launched()
+    barrier()
+    events = []
+    for _ in range(args.steps):
+        flush.zero_()
+        starts = device_starts()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(xyz, label, target, starts)
+        b.record()
+        events.append((a, b))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in events)
+    launches = mpc.ops.kernels_launched() - k0
+    dom = op_table(mpc._lib.profiler["records"])[0]
+    mpc._lib.profiler = None
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> loss D2H, all inside the timed region
+    for _ in range(2):
+        step(xyz_h.to(device, non_blocking=True), label_h.to(device, non_blocking=True),
+             target_h.to(device, non_blocking=True), device_starts()).item()
+    barrier()
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        starts = [s.pin_memory() for s in fps_starts(B, gen)]
+        loss = step(xyz_h.to(device, non_blocking=True), label_h.to(device, non_blocking=True),
+                    target_h.to(device, non_blocking=True), [s.to(device, non_blocking=True) for s in starts])
+        loss_host = loss.item()  # device -> host read of the step's result (synchronises)
+        t_e2e += time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, t_e2e * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    clouds = world * B * args.steps
+    h2d = xyz_h.numel() * 4 + label_h.numel() * 4 + target_h.numel() * 8 + sum(8 * B for _ in range(4))
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        name, n_calls, ms, by = dom
+        achieved = by / 1e9 / (ms / 1e3) if ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": clouds / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ShapeNetPart-shaped part segmentation, 32x2048 per GPU, fwd+bwd (BASELINE "
+                                   "configs[1])", "clouds_per_gpu": B, "points": N_POINTS, "classes": N_CLASSES,
+                       "parallelism": "dp%d (batch shards; NCCL all-reduce of the flat fp32 gradient)" % world
+                       if world > 1 else "single GPU",
+                       "l2": "256 MiB flush buffer written between timed steps; step working set >> 126 MB L2"},
+            "e2e": {"value": clouds / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind + " (burst copy)",
+                         "launches": n_calls, "avg_launch_us": 1e3 * ms / max(n_calls, 1),
+                         "share_of_step": ms / dev_ms, "algo_bytes_per_step": by / args.steps},
+            "clocks": clocks,
+            "last_loss": loss_host,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(2, 1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile-ops", default=None, help="write the per-entry-point device-time table here")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,8 +38,20 @@ SIGNATURES = {
                            _i64, _i64, _ptr],
 }
 
+# kernels each entry point enqueues (cudaMemsetAsync calls not counted)
+KERNELS_PER_CALL = {
+    "mpc_fps_f32": 1, "mpc_knn_f32": 1, "mpc_ball_query_f32": 1, "mpc_gather_f32": 1, "mpc_gather_bwd_f32": 1,
+    "mpc_gather_i64": 1, "mpc_transition_fwd_f32": 3, "mpc_transition_bwd_f32": 1,
+    "mpc_three_interpolate_fwd_f32": 2, "mpc_three_interpolate_bwd_f32": 1, "mpc_attn_feat_fwd_f32": 1,
+    "mpc_attn_feat_bwd_f32": 1, "mpc_attn_xyz_fwd_f32": 1, "mpc_attn_xyz_bwd_f32": 1, "mpc_bn_stats_f32": 2,
+    "mpc_bn_act_fwd_f32": 1, "mpc_bn_act_bwd_f32": 2,
+}
+
 _lib = None
-launch_count = 0  # number of C-ABI calls that enqueued GPU work (bench.py reports it)
+launch_count = 0   # C-ABI calls that enqueued GPU work
+kernel_count = 0   # kernels of ours those calls launched (bench.py reports it as gpu_launches)
+# Optional per-op device timing for bench.py: {"names": set or None (= all), "records": {name: [(ev0, ev1, bytes)]}}
+profiler = None
 
 
 class MpcError(RuntimeError):
@@ -70,15 +82,25 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def call(name, *args):
-    """Call an entry point on the current torch CUDA stream and raise on a non-zero status."""
-    global launch_count
+def call(name, *args, algo_bytes=0):
+    """Call an entry point on the current torch CUDA stream and raise on a non-zero status.  algo_bytes is the
+    op's algorithmic HBM traffic (SURVEY.md 8d formulas), recorded only when bench.py's profiler is on."""
+    global launch_count, kernel_count
     lib = load()
+    prof = profiler
+    timed = prof is not None and (prof["names"] is None or name in prof["names"])
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         kind = {-1: "invalid arguments", -2: "unsupported shape"}.get(rc, "CUDA error %d" % rc)
         raise MpcError("%s failed: %s" % (name, kind))
+    if timed:
+        ev1.record()
+        prof["records"].setdefault(name, []).append((ev0, ev1, algo_bytes))
     launch_count += 1
+    kernel_count += KERNELS_PER_CALL[name]
 
 
 def require_cuda(*tensors):

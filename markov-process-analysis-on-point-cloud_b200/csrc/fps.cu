@@ -49,8 +49,11 @@ __device__ __forceinline__ void update_slice(const float (&px)[PPT], const float
             besti = base + i * stride;
         }
     }
-    bhi = __float_as_uint(best);
-    blo = (unsigned)(~besti);
+    // a thread that owns only padding must lose against every real candidate: key 0 (real keys have a
+    // non-zero low word); note -1.0f reinterpreted as unsigned would compare ABOVE every real distance
+    const bool any = best >= 0.0f;
+    bhi = any ? __float_as_uint(best) : 0u;
+    blo = any ? (unsigned)(~besti) : 0u;
 }
 
 // ---- variant A: one CTA per cloud, C == 3 ----------------------------------------------------------------
@@ -217,7 +220,8 @@ fps_generic_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ st
                 besti = n;
             }
         }
-        unsigned long long k = warp_max_key(__float_as_uint(best), (unsigned)(~besti));
+        const bool any = best >= 0.0f;  // threads beyond N own no point
+        unsigned long long k = warp_max_key(any ? __float_as_uint(best) : 0u, any ? (unsigned)(~besti) : 0u);
         if (lane == 0) slots[it & 1][warp] = k;
         __syncthreads();
         unsigned long long v = lane < NW ? slots[it & 1][lane] : 0ull;
@@ -231,7 +235,8 @@ static int launch_cta(const float* xyz, const int64_t* start, int64_t* out, int 
                       cudaStream_t st) {
     size_t smem = (size_t)N * 3 * sizeof(float);
     auto kern = fps_cta_kernel<PPT, THREADS>;
-    if (smem > 48 * 1024) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024)  // static shared memory (warp slots) counts against the default 48 KB too
+        MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B, THREADS, smem, st>>>(xyz, start, out, N, npoint);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -271,7 +276,7 @@ MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, in
     if (C != 3) {
         size_t smem = (size_t)(N + C) * sizeof(float);
         if (smem > 200 * 1024) return MPC_ERR_UNSUPPORTED;
-        if (smem > 48 * 1024)
+        if (smem > 40 * 1024)
             MPC_CUDA(cudaFuncSetAttribute(fps_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fps_generic_kernel<<<(int)B, 512, smem, st>>>(xyz, start, out, (int)N, (int)C, (int)npoint);
         MPC_LAUNCH_CHECK();

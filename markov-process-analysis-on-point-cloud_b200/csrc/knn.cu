@@ -200,7 +200,7 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
     size_t smem = ((size_t)KNNG_THREADS * (C + 1) + (size_t)C * KNNG_LD + KNNG_TR) * sizeof(float);
     if (smem > 220 * 1024) return MPC_ERR_UNSUPPORTED;
     auto kern = knng_kernel<K>;
-    if (smem > 48 * 1024) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(S, KNNG_THREADS), (unsigned)B);
     kern<<<grid, KNNG_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C);
     MPC_LAUNCH_CHECK();

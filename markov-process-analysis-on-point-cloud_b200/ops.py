@@ -50,7 +50,7 @@ _tape = _IndexTape()
 @contextlib.contextmanager
 def index_tape(inject=None, record=None, fps_starts=None):
     """inject: iterable of index tensors returned (in call order) by farthest_point_sample / knn_point
-    instead of computing them; record: list receiving ("fps"|"knn", idx); fps_starts: iterable of [B] start
+    instead of computing them; record: list receiving ("fps"|"knn"|"knnf", idx); fps_starts: iterable of [B] start
     indices used instead of drawing them from the CPU generator."""
     old = (_tape.inject, _tape.record, _tape.fps_starts)
     _tape.inject = list(inject) if inject is not None else None
@@ -100,7 +100,8 @@ def farthest_point_sample(xyz, npoint, cuda=False, start=None):
     xyz = _f32c(xyz.detach())
     start = _i64c(start.to(xyz.device))
     out = torch.empty(B, npoint, dtype=torch.int64, device=xyz.device)
-    call("mpc_fps_f32", ptr(xyz), ptr(start), ptr(out), _i64(B), _i64(N), _i64(C), _i64(npoint))
+    call("mpc_fps_f32", ptr(xyz), ptr(start), ptr(out), _i64(B), _i64(N), _i64(C), _i64(npoint),
+         algo_bytes=B * (N * C * 4 + npoint * 8))
     _record("fps", out)
     return out
 
@@ -129,12 +130,13 @@ def knn_point(nsample, xyz, new_xyz):
         raise ValueError("knn_point: k=%d with only N=%d reference points is not supported" % (nsample, N))
     dist = torch.empty(B, S, L, dtype=torch.float32, device=xyz.device)
     idx = torch.empty(B, S, L, dtype=torch.int64, device=xyz.device)
-    call("mpc_knn_f32", ptr(xyz), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N), _i64(S), _i64(C), _i64(L))
+    call("mpc_knn_f32", ptr(xyz), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N), _i64(S), _i64(C), _i64(L),
+         algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
     if L != nsample:
         dist, idx = dist[:, :, :nsample].contiguous(), idx[:, :, :nsample].contiguous()
     if taped is not None:
         idx = taped
-    _record("knn", idx)
+    _record("knn" if C == 3 else "knnf", idx)  # "knnf": feature-space search (tie-prone, see tests)
     return dist, idx
 
 
@@ -188,7 +190,8 @@ class _Gather(torch.autograd.Function):
         B, N, C = points.shape
         M = idx.numel() // B if B else 0
         out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
-        call("mpc_gather_f32", ptr(points), ptr(idx), ptr(out), _i64(B), _i64(N), _i64(M), _i64(C))
+        call("mpc_gather_f32", ptr(points), ptr(idx), ptr(out), _i64(B), _i64(N), _i64(M), _i64(C),
+             algo_bytes=B * M * (8 * C + 8))
         ctx.save_for_backward(idx)
         ctx.dims = (B, N, M, C)
         return out
@@ -199,7 +202,8 @@ class _Gather(torch.autograd.Function):
         B, N, M, C = ctx.dims
         grad_out = _f32c(grad_out)
         grad_points = torch.empty(B, N, C, dtype=torch.float32, device=grad_out.device)
-        call("mpc_gather_bwd_f32", ptr(grad_out), ptr(idx), ptr(grad_points), _i64(B), _i64(N), _i64(M), _i64(C))
+        call("mpc_gather_bwd_f32", ptr(grad_out), ptr(idx), ptr(grad_points), _i64(B), _i64(N), _i64(M), _i64(C),
+             algo_bytes=B * (M * (8 * C + 8) + N * C * 4))
         return grad_points, None
 
 
@@ -236,7 +240,7 @@ class _Transition(torch.autograd.Function):
         out = torch.empty(B, n_out, C, dtype=torch.float32, device=points.device)
         cnt = torch.empty(B, n_out, dtype=torch.float32, device=points.device)
         call("mpc_transition_fwd_f32", ptr(points), ptr(idx), ptr(out), ptr(cnt), _i64(B), _i64(S), _i64(K),
-             _i64(C), _i64(n_out))
+             _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8))
         ctx.save_for_backward(idx, cnt)
         ctx.dims = (B, S, K, C, n_out)
         return out
@@ -248,7 +252,7 @@ class _Transition(torch.autograd.Function):
         grad_out = _f32c(grad_out)
         g = torch.empty(B, S, C, dtype=torch.float32, device=grad_out.device)
         call("mpc_transition_bwd_f32", ptr(grad_out), ptr(idx), ptr(cnt), ptr(g), _i64(B), _i64(S), _i64(K),
-             _i64(C), _i64(n_out))
+             _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8 + n_out * 4))
         return g, None, None
 
 
@@ -287,7 +291,7 @@ class ThreeInterpolate(torch.autograd.Function):
         weight = torch.empty(B, N, 3, dtype=torch.float32, device=points2.device)
         out = torch.empty(B, N, C, dtype=torch.float32, device=points2.device)
         call("mpc_three_interpolate_fwd_f32", ptr(points2), ptr(dist), ptr(idx), ptr(weight), ptr(out), _i64(B),
-             _i64(N), _i64(S), _i64(C))
+             _i64(N), _i64(S), _i64(C), algo_bytes=B * (4 * N * C * 4 + N * 36))
         ctx.save_for_backward(idx, weight)
         ctx.dims = (B, N, S, C)
         return out
@@ -299,7 +303,7 @@ class ThreeInterpolate(torch.autograd.Function):
         grad_out = _f32c(grad_out)
         g = torch.empty(B, S, C, dtype=torch.float32, device=grad_out.device)
         call("mpc_three_interpolate_bwd_f32", ptr(grad_out), ptr(weight), ptr(idx), ptr(g), _i64(B), _i64(N),
-             _i64(S), _i64(C))
+             _i64(S), _i64(C), algo_bytes=B * (4 * N * C * 4 + N * 36 + S * C * 4))
         return g, None, None
 
 
@@ -322,7 +326,8 @@ class AttnFeat(torch.autograd.Function):
         K = idx.shape[2]
         out = torch.empty(B, S, C, dtype=torch.float32, device=q.device)
         call("mpc_attn_feat_fwd_f32", ptr(q), _i64(C), ptr(kv), ctypes.c_void_p(kv.data_ptr() + 4 * C),
-             _i64(2 * C), ptr(idx), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C))
+             _i64(2 * C), ptr(idx), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C),
+             algo_bytes=B * ((2 * N * C + 2 * S * C) * 4 + S * K * 8))
         ctx.save_for_backward(q, kv, idx)
         return out
 
@@ -337,7 +342,8 @@ class AttnFeat(torch.autograd.Function):
         gkv = torch.zeros_like(kv)
         call("mpc_attn_feat_bwd_f32", ptr(grad_ctx), ptr(q), _i64(C), ptr(kv),
              ctypes.c_void_p(kv.data_ptr() + 4 * C), _i64(2 * C), ptr(idx), ptr(gq), _i64(C), ptr(gkv),
-             ctypes.c_void_p(gkv.data_ptr() + 4 * C), _i64(2 * C), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C))
+             ctypes.c_void_p(gkv.data_ptr() + 4 * C), _i64(2 * C), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C),
+             algo_bytes=B * ((4 * N * C + 3 * S * C) * 4 + S * K * 8))
         return gq, gkv, None
 
 
@@ -352,7 +358,8 @@ class AttnXyz(torch.autograd.Function):
         C = wq.shape[0]
         out = torch.empty(B, S, C, dtype=torch.float32, device=feat.device)
         call("mpc_attn_xyz_fwd_f32", ptr(feat), ptr(center_idx), ptr(idx), ptr(wq), ptr(bq), ptr(wk), ptr(bk),
-             ptr(wv), ptr(bv), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C))
+             ptr(wv), ptr(bv), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C),
+             algo_bytes=B * (N * Cin * 4 + S * K * 8 + S * C * 4) + 3 * C * (Cin + 1) * 4)
         ctx.save_for_backward(feat, idx, wq, bq, wk, bk, wv, bv)
         ctx.center_idx = center_idx
         return out
@@ -370,7 +377,8 @@ class AttnXyz(torch.autograd.Function):
         gfeat = torch.zeros_like(feat) if ctx.needs_input_grad[0] else None
         call("mpc_attn_xyz_bwd_f32", ptr(grad_ctx), ptr(feat), ptr(center_idx), ptr(idx), ptr(wq), ptr(bq), ptr(wk),
              ptr(bk), ptr(wv), ptr(bv), ptr(gw[0]), ptr(gb[0]), ptr(gw[1]), ptr(gb[1]), ptr(gw[2]), ptr(gb[2]),
-             ptr(gfeat), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C))
+             ptr(gfeat), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C),
+             algo_bytes=B * (N * Cin * 4 + S * K * 8 + S * C * 4) + 6 * C * (Cin + 1) * 4)
         return gfeat, None, None, gw[0], gb[0], gw[1], gb[1], gw[2], gb[2]
 
 
@@ -394,13 +402,14 @@ class BNAct(torch.autograd.Function):
             scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
             stats = torch.empty(2 * C, dtype=torch.float32, device=dev)
             call("mpc_bn_stats_f32", ptr(y), ptr(stats), ptr(running_mean), ptr(running_var),
-                 ptr(num_batches_tracked), ctypes.c_float(momentum), ptr(scratch), _i64(M), _i64(C))
+                 ptr(num_batches_tracked), ctypes.c_float(momentum), ptr(scratch), _i64(M), _i64(C),
+                 algo_bytes=M * C * 4)
             mean, var = stats[:C], stats[C:]
         else:
             mean, var = running_mean, running_var
         out = torch.empty_like(y)
         call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
-             ctypes.c_float(slope), ptr(out), _i64(M), _i64(C))
+             ctypes.c_float(slope), ptr(out), _i64(M), _i64(C), algo_bytes=2 * M * C * 4)
         ctx.save_for_backward(y, mean, var, gamma, beta)
         ctx.cfg = (training, eps, slope)
         return out
@@ -417,7 +426,7 @@ class BNAct(torch.autograd.Function):
         scratch = torch.empty(2 * C, dtype=torch.float64, device=y.device)
         call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
-             ptr(gb), ptr(scratch), _i64(M), _i64(C))
+             ptr(gb), ptr(scratch), _i64(M), _i64(C), algo_bytes=3 * M * C * 4)
         return gy, gg, gb, None, None, None, None, None, None, None
 
 
@@ -432,3 +441,8 @@ def bn_act(y2d, gamma, beta, running_mean, running_var, num_batches_tracked, tra
 def launches():
     """C-ABI calls issued so far in this process (each enqueues one or more of our kernels)."""
     return _lib.launch_count
+
+
+def kernels_launched():
+    """Kernels of ours launched so far in this process."""
+    return _lib.kernel_count

@@ -163,7 +163,7 @@ int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t
  * R/modules/pointnet2_utils.py:413-425, on the [M,C] view (M = all leading axes), without the two
  * permute().contiguous() copies of :420.
  *   mpc_bn_stats_f32: stats[0:C] = mean, stats[C:2C] = biased variance of y over M rows (fp64 accumulation
- *     in `scratch`, 2*C doubles, zero-filled by the call).  If non-NULL, running_mean / running_var [C] get
+ *     in `scratch`, 2*C+1 doubles, zero-filled by the call).  If non-NULL, running_mean / running_var [C] get
  *     nn.BatchNorm1d's update (x = (1-momentum)*x + momentum*stat, unbiased variance) and
  *     *num_batches_tracked (device int64) is incremented.
  *   mpc_bn_act_fwd_f32: out = lrelu(gamma * (y - mean) * rsqrt(var + eps) + beta, slope); slope = 1 => no act.
@@ -181,6 +181,17 @@ int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean,
                        const float* gamma, const float* beta, float eps, float slope, int train,
                        float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, int64_t M,
                        int64_t C, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Shared-MLP projection on the tensor cores.  Replaces the nn.Linear inside `Linear` and the q/k/v projections
+ * of LocalTrans, R/modules/pointnet2_utils.py:408,415,489-491:   y[M,N] = x[M,K] w[N,K]^T + bias[N].
+ *   x rows have stride ldx floats, w rows ldw, y rows ldy (so operands / results may be column slices).
+ * tcgen05.mma kind::tf32 with the 3xTF32 operand split (hi/lo), fp32 accumulation in TMEM, TMA-fed: fp32-level
+ * accuracy (the parity tolerance is rtol 1e-4).  Requires K % 32 == 0, ldx % 4 == ldw % 4 == 0, 16-byte aligned
+ * x and w; other shapes return MPC_ERR_UNSUPPORTED and the host falls back to the library GEMM.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                       int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,138 @@ bn_sums_kernel(const float* __restrict__ y, double* __restrict__ s1, double* __r
     block_reduce_to_scratch(a, b, s1, s2, cbase, VEC4 ? C : min(C, cbase + 1));
 }
 
+// ---- fast path: C/4 is a power of two <= 256 (every BatchNorm width in both models) ------------------------
+// 256 threads = (256/CV) row slots x CV float4 columns; each thread streams its rows with 4 independent
+// 128-bit loads in flight, partials are reduced over the row slots in shared memory, one fp64 atomic per
+// (CTA, channel, quantity); the last CTA to finish (atomic ticket) finalises, so no second launch is needed.
+constexpr int RT = 256;
+
+struct StatsFinal {
+    float* stats;
+    float* running_mean;
+    float* running_var;
+    int64_t* num_batches_tracked;
+    float momentum;
+};
+
+__device__ __forceinline__ void finalize_channel(const double* s1, const double* s2, const StatsFinal& f, int64_t M,
+                                                 int C, int c) {
+    const double mean = __ldcg(s1 + c) / (double)M;
+    double var = __ldcg(s2 + c) / (double)M - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    f.stats[c] = (float)mean;
+    f.stats[C + c] = (float)var;
+    if (f.running_mean) f.running_mean[c] = (1.0f - f.momentum) * f.running_mean[c] + f.momentum * (float)mean;
+    if (f.running_var) {
+        const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+        f.running_var[c] = (1.0f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+    }
+}
+
+// MODE 0: (y, y*y) for the forward statistics.  MODE 1: (dz, dz*xhat) for the backward reductions.
+template <int MODE>
+__global__ void __launch_bounds__(RT)
+col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, const float* __restrict__ mean,
+                  const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float eps, float slope, double* __restrict__ s1, double* __restrict__ s2,
+                  unsigned* __restrict__ ticket, StatsFinal fin, int64_t M, int C, int CV) {
+    __shared__ float4 ra[RT], rb[RT];
+    __shared__ bool last;
+    const int v = threadIdx.x % CV, slot = threadIdx.x / CV, slots = RT / CV;
+    const int c0 = v * 4;
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu, g = mu, be = mu;
+    if (MODE == 1) {
+        mu = __ldg(reinterpret_cast<const float4*>(mean + c0));
+        const float4 vr = __ldg(reinterpret_cast<const float4*>(var + c0));
+        is = make_float4(1.0f / sqrtf(vr.x + eps), 1.0f / sqrtf(vr.y + eps), 1.0f / sqrtf(vr.z + eps),
+                         1.0f / sqrtf(vr.w + eps));
+        g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+        be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    const int64_t stride = (int64_t)gridDim.x * slots;
+    const float4* yp = reinterpret_cast<const float4*>(y);
+    const float4* gp = reinterpret_cast<const float4*>(gout);
+    auto accum = [&](const float4& yv, const float4& gv) {
+        if (MODE == 0) {
+            a.x += yv.x; a.y += yv.y; a.z += yv.z; a.w += yv.w;
+            b.x = fmaf(yv.x, yv.x, b.x); b.y = fmaf(yv.y, yv.y, b.y);
+            b.z = fmaf(yv.z, yv.z, b.z); b.w = fmaf(yv.w, yv.w, b.w);
+        } else {
+#define MPC_R(comp)                                                     \
+    {                                                                   \
+        const float xh = (yv.comp - mu.comp) * is.comp;                 \
+        const float z = fmaf(xh, g.comp, be.comp);                      \
+        const float dz = z > 0.f ? gv.comp : gv.comp * slope;           \
+        a.comp += dz;                                                   \
+        b.comp = fmaf(dz, xh, b.comp);                                  \
+    }
+            MPC_R(x) MPC_R(y) MPC_R(z) MPC_R(w)
+#undef MPC_R
+        }
+    };
+    int64_t r = (int64_t)blockIdx.x * slots + slot;
+    for (; r + 3 * stride < M; r += 4 * stride) {  // 4 (8 in MODE 1) independent 128-bit loads in flight
+        float4 y0 = __ldg(yp + r * CV + v), y1 = __ldg(yp + (r + stride) * CV + v);
+        float4 y2 = __ldg(yp + (r + 2 * stride) * CV + v), y3 = __ldg(yp + (r + 3 * stride) * CV + v);
+        float4 g0 = y0, g1 = y0, g2 = y0, g3 = y0;
+        if (MODE == 1) {
+            g0 = __ldg(gp + r * CV + v);
+            g1 = __ldg(gp + (r + stride) * CV + v);
+            g2 = __ldg(gp + (r + 2 * stride) * CV + v);
+            g3 = __ldg(gp + (r + 3 * stride) * CV + v);
+        }
+        accum(y0, g0);
+        accum(y1, g1);
+        accum(y2, g2);
+        accum(y3, g3);
+    }
+    for (; r < M; r += stride) {
+        const float4 y0 = __ldg(yp + r * CV + v);
+        const float4 g0 = MODE == 1 ? __ldg(gp + r * CV + v) : y0;
+        accum(y0, g0);
+    }
+    ra[threadIdx.x] = a;
+    rb[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x < CV) {
+        double A[4] = {0, 0, 0, 0}, Bv[4] = {0, 0, 0, 0};
+        for (int sl = 0; sl < slots; ++sl) {
+            const float4 u = ra[sl * CV + v], w = rb[sl * CV + v];
+            A[0] += u.x; A[1] += u.y; A[2] += u.z; A[3] += u.w;
+            Bv[0] += w.x; Bv[1] += w.y; Bv[2] += w.z; Bv[3] += w.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            atomicAdd(s1 + c0 + i, A[i]);
+            atomicAdd(s2 + c0 + i, Bv[i]);
+        }
+    }
+    if (MODE == 0) {  // last CTA done: finalise mean / var / running stats in the same launch
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            for (int c = threadIdx.x; c < C; c += RT) finalize_channel(s1, s2, fin, M, C, c);
+            if (threadIdx.x == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+        }
+    }
+}
+
+static inline bool fast_cv(int64_t C) {
+    if (C % 4) return false;
+    const int64_t cv = C / 4;
+    return cv >= 1 && cv <= 256 && (cv & (cv - 1)) == 0;
+}
+static inline unsigned col_reduce_grid(int64_t M, int CV) {
+    const int slots = RT / CV;
+    int64_t g = ceil_div(M, (int64_t)slots * 8);  // >= 8 rows per thread
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
 // mean / biased variance, plus nn.BatchNorm1d's running-statistics update (unbiased variance, momentum)
 __global__ void bn_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2,
                                    float* __restrict__ stats, float* __restrict__ running_mean,
@@ -241,7 +373,16 @@ MPC_API int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, 
                              mpc_stream_t stream) {
     if (!y || !stats || !scratch || M <= 0 || C <= 0 || C > INT32_MAX / 4) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)C, st));
+    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * (size_t)C + 1), st));
+    if (fast_cv(C) && al16(y)) {
+        const int CV = (int)(C / 4);
+        StatsFinal fin{stats, running_mean, running_var, num_batches_tracked, momentum};
+        col_reduce_kernel<0><<<col_reduce_grid(M, CV), RT, 0, st>>>(
+            y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, scratch, scratch + C,
+            reinterpret_cast<unsigned*>(scratch + 2 * C), fin, M, (int)C, CV);
+        MPC_LAUNCH_CHECK();
+        return MPC_OK;
+    }
     const bool v4 = C % 4 == 0 && al16(y);
     const Dims d = bn_dims(M, (int)(v4 ? C / 4 : C));
     if (v4)
@@ -284,8 +425,15 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
     const Dims d = bn_dims(M, (int)(v4 ? C / 4 : C));
     const int64_t total = M * (v4 ? C / 4 : C);
     if (v4) {
-        bn_bwd_sums_kernel<true><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, scratch,
-                                                            scratch + C, M, (int)C);
+        if (fast_cv(C) && al16(mean) && al16(var) && al16(gamma) && al16(beta)) {
+            const int CV = (int)(C / 4);
+            col_reduce_kernel<1><<<col_reduce_grid(M, CV), RT, 0, st>>>(y, grad_out, mean, var, gamma, beta, eps, slope,
+                                                                       scratch, scratch + C, nullptr, StatsFinal{}, M,
+                                                                       (int)C, CV);
+        } else {
+            bn_bwd_sums_kernel<true><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
+                                                                scratch, scratch + C, M, (int)C);
+        }
         MPC_LAUNCH_CHECK();
         bn_bwd_apply_kernel<true><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, train,
                                                                  scratch, scratch + C, grad_y, grad_gamma, grad_beta, M,

@@ -29,17 +29,45 @@ __device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bi)[K], float 
     }
 }
 
+// Candidates that beat a thread's current K-th distance are not inserted immediately: in a warp of 32
+// independent queries some lane passes the threshold on ~70% of the reference points, so an immediate
+// insertion network would run (mostly masked off) on almost every iteration.  Instead each thread appends the
+// candidate to a small per-thread queue in shared memory, and the warp drains all queues together when any of
+// them is close to full: the insertion network then runs ~20x less often and with most lanes busy.  Arrival
+// order (ascending index) is preserved, so equal distances still resolve to the lower index.
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_Q = 8;      // queue slots per thread
+constexpr int KNN_QFLUSH = 4; // drain when any lane holds more than this many (<= KNN_Q - unroll)
+
+struct CandQueue {
+    float d[KNN_Q][KNN_THREADS];
+    int i[KNN_Q][KNN_THREADS];
+};
+
+template <int K>
+__device__ __forceinline__ void drain_queue(CandQueue& q, int& qn, float (&bd)[K], int (&bi)[K], float& thr) {
+    const int m = __reduce_max_sync(0xffffffffu, qn);
+    for (int e = 0; e < m; ++e) {
+        if (e < qn) {
+            const float d = q.d[e][threadIdx.x];
+            if (d < bd[K - 1]) topk_insert<K>(bd, bi, d, q.i[e][threadIdx.x]);
+        }
+    }
+    qn = 0;
+    thr = bd[K - 1];
+}
+
 // ---- C == 3 ------------------------------------------------------------------------------------------------
-constexpr int KNN3_THREADS = 128;
 constexpr int KNN3_TILE = 2048;  // reference points per shared-memory tile (float4 x,y,z,|r|^2 = 32 KB)
 
 template <int K>
-__global__ void __launch_bounds__(KNN3_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS)
 knn3_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
             int64_t* __restrict__ idx_out, int N, int S) {
     __shared__ float4 tile[KNN3_TILE];
+    __shared__ CandQueue queue;
     const int b = blockIdx.y;
-    const int s = blockIdx.x * KNN3_THREADS + threadIdx.x;
+    const int s = blockIdx.x * KNN_THREADS + threadIdx.x;
     const bool active = s < S;
     const float* rb = ref + (size_t)b * N * 3;
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -57,27 +85,37 @@ knn3_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float*
         bd[k] = __int_as_float(0x7f800000);  // +inf
         bi[k] = 0;
     }
+    // inactive threads keep thr = -inf: they never enqueue but still take part in the warp votes
+    float thr = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+    int cnt = 0;
     for (int t0 = 0; t0 < N; t0 += KNN3_TILE) {
         const int tn = min(KNN3_TILE, N - t0);
         __syncthreads();
-        for (int j = threadIdx.x; j < tn; j += KNN3_THREADS) {
+        for (int j = threadIdx.x; j < tn; j += KNN_THREADS) {
             const float* r = rb + (size_t)(t0 + j) * 3;
             float x = r[0], y = r[1], z = r[2];
             tile[j] = make_float4(x, y, z, sqnorm3(x, y, z));
         }
         __syncthreads();
-        if (active) {
-#pragma unroll 4
-            for (int j = 0; j < tn; ++j) {
-                const float4 r = tile[j];  // broadcast read
+        for (int j0 = 0; j0 < tn; j0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                const float4 r = tile[j < tn ? j : tn - 1];  // broadcast read
                 float dot = __fmul_rn(qx, r.x);
                 dot = __fmaf_rn(qy, r.y, dot);
                 dot = __fmaf_rn(qz, r.z, dot);
                 const float d = sqdist_from_dot(dot, qn, r.w);
-                if (d < bd[K - 1]) topk_insert<K>(bd, bi, d, t0 + j);
+                if (j < tn && d < thr) {
+                    queue.d[cnt][threadIdx.x] = d;
+                    queue.i[cnt][threadIdx.x] = t0 + j;
+                    ++cnt;
+                }
             }
+            if (__any_sync(0xffffffffu, cnt > KNN_QFLUSH)) drain_queue<K>(queue, cnt, bd, bi, thr);
         }
     }
+    drain_queue<K>(queue, cnt, bd, bi, thr);
     if (active) {
         const size_t o = ((size_t)b * S + s) * K;
 #pragma unroll
@@ -88,11 +126,123 @@ knn3_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float*
     }
 }
 
-// ---- generic C (feature-space kNN, C = 64..256 in the live models) ---------------------------------------
+// ---- C == 64 (the feature width of every large feature-space search in both models) ------------------------
+// The query vector lives in 64 registers; reference tiles of 64 points are stored transposed [c][64+4] so one
+// broadcast LDS.128 feeds 4 reference points; a thread advances 16 reference points at once (16 independent
+// fma chains, each sequential in c exactly as the oracle prescribes).
+constexpr int KNN64_TR = 64;
+constexpr int KNN64_LD = KNN64_TR + 4;
+
+template <int K>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn64_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
+             int64_t* __restrict__ idx_out, int N, int S) {
+    constexpr int C = 64;
+    __shared__ __align__(16) float rt[C * KNN64_LD];
+    __shared__ float rn[KNN64_TR];
+    __shared__ CandQueue queue;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int s = blockIdx.x * KNN_THREADS + tid;
+    const bool active = s < S;
+    const float* rb = ref + (size_t)b * N * C;
+    float q[C];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(qry + ((size_t)b * S + (active ? s : 0)) * C);
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) {
+            const float4 v = __ldg(qp + c);
+            q[4 * c + 0] = v.x;
+            q[4 * c + 1] = v.y;
+            q[4 * c + 2] = v.z;
+            q[4 * c + 3] = v.w;
+        }
+    }
+    float qn = __fmul_rn(q[0], q[0]);
+#pragma unroll
+    for (int c = 1; c < C; ++c) qn = __fadd_rn(qn, __fmul_rn(q[c], q[c]));
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        bd[k] = __int_as_float(0x7f800000);
+        bi[k] = 0;
+    }
+    float thr = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+    int cnt = 0;
+    for (int t0 = 0; t0 < N; t0 += KNN64_TR) {
+        const int tn = min(KNN64_TR, N - t0);
+        __syncthreads();
+        // coalesced float4 reads of 64 rows x 64 channels, transposed into [c][j]
+        for (int i = tid; i < KNN64_TR * (C / 4); i += KNN_THREADS) {
+            const int j = i / (C / 4), c4 = (i - j * (C / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < tn) v = __ldg(reinterpret_cast<const float4*>(rb + (size_t)(t0 + j) * C + c4));
+            rt[(c4 + 0) * KNN64_LD + j] = v.x;
+            rt[(c4 + 1) * KNN64_LD + j] = v.y;
+            rt[(c4 + 2) * KNN64_LD + j] = v.z;
+            rt[(c4 + 3) * KNN64_LD + j] = v.w;
+        }
+        __syncthreads();
+        if (tid < KNN64_TR) {
+            float a = __fmul_rn(rt[tid], rt[tid]);
+#pragma unroll 8
+            for (int c = 1; c < C; ++c) {
+                const float v = rt[c * KNN64_LD + tid];
+                a = __fadd_rn(a, __fmul_rn(v, v));
+            }
+            rn[tid] = a;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int j0 = 0; j0 < KNN64_TR; j0 += 16) {
+            float acc[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float qv = q[c];
+                const float4* rp = reinterpret_cast<const float4*>(rt + c * KNN64_LD + j0);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const float4 r = rp[v4];
+                    acc[4 * v4 + 0] = __fmaf_rn(qv, r.x, acc[4 * v4 + 0]);
+                    acc[4 * v4 + 1] = __fmaf_rn(qv, r.y, acc[4 * v4 + 1]);
+                    acc[4 * v4 + 2] = __fmaf_rn(qv, r.z, acc[4 * v4 + 2]);
+                    acc[4 * v4 + 3] = __fmaf_rn(qv, r.w, acc[4 * v4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int u0 = 0; u0 < 16; u0 += 4) {
+#pragma unroll
+                for (int u = u0; u < u0 + 4; ++u) {
+                    const int j = j0 + u;
+                    const float d = sqdist_from_dot(acc[u], qn, rn[j]);
+                    if (j < tn && d < thr) {
+                        queue.d[cnt][tid] = d;
+                        queue.i[cnt][tid] = t0 + j;
+                        ++cnt;
+                    }
+                }
+                if (__any_sync(0xffffffffu, cnt > KNN_QFLUSH)) drain_queue<K>(queue, cnt, bd, bi, thr);
+            }
+        }
+    }
+    drain_queue<K>(queue, cnt, bd, bi, thr);
+    if (active) {
+        const size_t o = ((size_t)b * S + s) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (dist_out) dist_out[o + k] = bd[k];
+            idx_out[o + k] = bi[k];
+        }
+    }
+}
+
+// ---- generic C ------------------------------------------------------------------------------------------------
 // CTA = 128 queries.  Queries live in shared memory [q][C+1]; reference tiles of 32 points are stored
-// transposed [c][32+4] so that one broadcast LDS.128 feeds 4 reference points; a thread advances 8 reference
-// points at once (8 independent fma chains, each sequential in c as the oracle prescribes).
-constexpr int KNNG_THREADS = 128;
+// transposed [c][32+4]; a thread advances 8 reference points at once.
+constexpr int KNNG_THREADS = KNN_THREADS;
 constexpr int KNNG_TR = 32;           // reference points per tile
 constexpr int KNNG_LD = KNNG_TR + 4;  // padded row (floats), keeps 16-byte alignment
 
@@ -102,8 +252,9 @@ knng_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float*
             int64_t* __restrict__ idx_out, int N, int S, int C) {
     extern __shared__ __align__(16) float smem[];
     float* qs = smem;                                // [128][C+1]
-    float* rt = qs + KNNG_THREADS * (C + 1);         // [C][KNNG_LD]   (offset is a multiple of 4 floats, see launch)
+    float* rt = qs + KNNG_THREADS * (C + 1);         // [C][KNNG_LD]   (offset is a multiple of 4 floats)
     float* rn = rt + (size_t)C * KNNG_LD;            // [KNNG_TR]
+    __shared__ CandQueue queue;
     const int b = blockIdx.y;
     const int s0 = blockIdx.x * KNNG_THREADS;
     const int tid = threadIdx.x;
@@ -130,6 +281,8 @@ knng_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float*
         bd[k] = __int_as_float(0x7f800000);
         bi[k] = 0;
     }
+    float thr = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+    int cnt = 0;
     for (int t0 = 0; t0 < N; t0 += KNNG_TR) {
         const int tn = min(KNNG_TR, N - t0);
         __syncthreads();
@@ -147,35 +300,42 @@ knng_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float*
             rn[tid] = a;
         }
         __syncthreads();
-        if (active) {
 #pragma unroll 1
-            for (int j0 = 0; j0 < KNNG_TR; j0 += 8) {
-                float acc[8];
+        for (int j0 = 0; j0 < KNNG_TR; j0 += 8) {
+            float acc[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+            for (int u = 0; u < 8; ++u) acc[u] = 0.f;
 #pragma unroll 4
-                for (int c = 0; c < C; ++c) {
-                    const float qv = myq[c];
-                    const float4 r0 = *reinterpret_cast<const float4*>(rt + c * KNNG_LD + j0);
-                    const float4 r1 = *reinterpret_cast<const float4*>(rt + c * KNNG_LD + j0 + 4);
-                    acc[0] = __fmaf_rn(qv, r0.x, acc[0]);
-                    acc[1] = __fmaf_rn(qv, r0.y, acc[1]);
-                    acc[2] = __fmaf_rn(qv, r0.z, acc[2]);
-                    acc[3] = __fmaf_rn(qv, r0.w, acc[3]);
-                    acc[4] = __fmaf_rn(qv, r1.x, acc[4]);
-                    acc[5] = __fmaf_rn(qv, r1.y, acc[5]);
-                    acc[6] = __fmaf_rn(qv, r1.z, acc[6]);
-                    acc[7] = __fmaf_rn(qv, r1.w, acc[7]);
-                }
+            for (int c = 0; c < C; ++c) {
+                const float qv = myq[c];
+                const float4 r0 = *reinterpret_cast<const float4*>(rt + c * KNNG_LD + j0);
+                const float4 r1 = *reinterpret_cast<const float4*>(rt + c * KNNG_LD + j0 + 4);
+                acc[0] = __fmaf_rn(qv, r0.x, acc[0]);
+                acc[1] = __fmaf_rn(qv, r0.y, acc[1]);
+                acc[2] = __fmaf_rn(qv, r0.z, acc[2]);
+                acc[3] = __fmaf_rn(qv, r0.w, acc[3]);
+                acc[4] = __fmaf_rn(qv, r1.x, acc[4]);
+                acc[5] = __fmaf_rn(qv, r1.y, acc[5]);
+                acc[6] = __fmaf_rn(qv, r1.z, acc[6]);
+                acc[7] = __fmaf_rn(qv, r1.w, acc[7]);
+            }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+            for (int u0 = 0; u0 < 8; u0 += 4) {
+#pragma unroll
+                for (int u = u0; u < u0 + 4; ++u) {
                     const int j = j0 + u;
                     const float d = sqdist_from_dot(acc[u], qn, rn[j]);
-                    if (j < tn && d < bd[K - 1]) topk_insert<K>(bd, bi, d, t0 + j);
+                    if (j < tn && d < thr) {
+                        queue.d[cnt][tid] = d;
+                        queue.i[cnt][tid] = t0 + j;
+                        ++cnt;
+                    }
                 }
+                if (__any_sync(0xffffffffu, cnt > KNN_QFLUSH)) drain_queue<K>(queue, cnt, bd, bi, thr);
             }
         }
     }
+    drain_queue<K>(queue, cnt, bd, bi, thr);
     if (active) {
         const size_t o = ((size_t)b * S + s) * K;
 #pragma unroll
@@ -190,17 +350,23 @@ template <int K>
 static int launch_knn(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, int B, int N,
                       int S, int C, cudaStream_t st) {
     if (C == 3) {
-        dim3 grid((unsigned)ceil_div(S, KNN3_THREADS), (unsigned)B);
-        knn3_kernel<K><<<grid, KNN3_THREADS, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+        dim3 grid((unsigned)ceil_div(S, KNN_THREADS), (unsigned)B);
+        knn3_kernel<K><<<grid, KNN_THREADS, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+        MPC_LAUNCH_CHECK();
+        return MPC_OK;
+    }
+    if (C == 64 && (reinterpret_cast<uintptr_t>(ref) & 15u) == 0 && (reinterpret_cast<uintptr_t>(qry) & 15u) == 0) {
+        dim3 grid((unsigned)ceil_div(S, KNN_THREADS), (unsigned)B);
+        knn64_kernel<K><<<grid, KNN_THREADS, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
         MPC_LAUNCH_CHECK();
         return MPC_OK;
     }
     // qs occupies 128*(C+1) floats; round the rt offset up to a multiple of 4 floats by padding C+1 -> handled
     // here by requiring 128*(C+1) % 4 == 0, which holds for every C (128 is a multiple of 4).
     size_t smem = ((size_t)KNNG_THREADS * (C + 1) + (size_t)C * KNNG_LD + KNNG_TR) * sizeof(float);
-    if (smem > 220 * 1024) return MPC_ERR_UNSUPPORTED;
+    if (smem > 210 * 1024) return MPC_ERR_UNSUPPORTED;  // + 8 KB static candidate queue
     auto kern = knng_kernel<K>;
-    if (smem > 40 * 1024) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 36 * 1024) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(S, KNNG_THREADS), (unsigned)B);
     kern<<<grid, KNNG_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C);
     MPC_LAUNCH_CHECK();

@@ -1,0 +1,365 @@
+// Shared-MLP projection Y = X W^T + b on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) for sm_100a.
+// Replaces the nn.Linear inside the reference's `Linear` / q,k,v projections (pointnet2_utils.py:408,415,
+// 489-491) -- the one family of ops on this path that is a real dense contraction.
+//
+// Precision: the reference is fp32 and the parity bar for features is rtol 1e-5..1e-4, which a single TF32
+// pass (10-bit mantissa) cannot meet.  The kernel therefore runs the 3xTF32 split: every fp32 operand tile is
+// split in shared memory into hi = top 19 bits and lo = (x - hi) truncated to TF32, and each K step issues
+//      D += A_lo B_hi ; D += A_hi B_lo ; D += A_hi B_hi        (fp32 accumulation in TMEM)
+// which recovers ~fp32 accuracy at one third of the TF32 rate -- still ~5x the FP32 SIMT pipe, enough to put
+// every layer width of both models back under the HBM roofline.
+//
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
+//   warps 0-3  epilogue   : tcgen05.ld accumulator rows (TMEM lane = output row), + bias, 128-bit global stores
+//   warps 4-7  splitters  : wait for a TMA stage, split A and B tiles in place into hi / lo, fence to the
+//                           async proxy, hand the stage to the MMA warp
+//   warp  8    TMA producer (one elected lane): cp.async.bulk.tensor 2D, 128B swizzle, fp32 boxes 32 x 128 (A)
+//                           and 32 x BLOCK_N (B) per stage
+//   warp  9    MMA issuer (one elected lane) + TMEM allocation: 12 tcgen05.mma.kind::tf32 per stage
+//                           (4 K-steps of 8 x 3 split terms), tcgen05.commit frees the stage / publishes the tile
+// Pipelines: smem stages (full -> split -> empty), 2 TMEM accumulator stages (tmem_full / tmem_empty), so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mpc {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;               // fp32 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB
+constexpr int THREADS = 320;
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t TF32_MASK = 0xffffe000u;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1, layout SWIZZLE_128B (2).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct Params {
+    int M, N, K;
+    int block_n;      // accumulator columns per tile (multiple of 16, <= 256)
+    int n_tiles;      // ceil(N / block_n)
+    int m_tiles;      // ceil(M / 128)
+    int stages;
+    const float* bias;  // may be null
+    float* y;
+    int ldy;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[MAX_STAGES], bar_split[MAX_STAGES], bar_empty[MAX_STAGES];
+    __shared__ uint64_t bar_tmem_full[2], bar_tmem_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    // dynamic smem is requested with 1024 B of slack and aligned here (swizzle-128B atoms need 1024 B alignment)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_tile_bytes = p.block_n * BLOCK_K * 4;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_chunks = p.K / BLOCK_K;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_split[s], 128);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tmem_full[a], 1);
+            mbar_init(&bar_tmem_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {  // TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&bar_empty[s], ph ^ 1);
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&bar_full[s], A_TILE_BYTES + b_tile_bytes);
+                    tma_load_2d(&map_a, &bar_full[s], st, kc * BLOCK_K, mt * BLOCK_M);
+                    tma_load_2d(&map_b, &bar_full[s], st + 2 * A_TILE_BYTES, kc * BLOCK_K, nt * p.block_n);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== splitters: x -> (hi, lo) in place, 16 bytes per thread per step, conflict-free =====
+        const int t = threadIdx.x - 128;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                mbar_wait(&bar_full[s], ph);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                uint4* a_hi = reinterpret_cast<uint4*>(st);
+                uint4* a_lo = reinterpret_cast<uint4*>(st + A_TILE_BYTES);
+                uint4* b_hi = reinterpret_cast<uint4*>(st + 2 * A_TILE_BYTES);
+                uint4* b_lo = reinterpret_cast<uint4*>(st + 2 * A_TILE_BYTES + b_tile_bytes);
+                auto split = [](uint4 v, uint4& hi, uint4& lo) {
+                    hi.x = v.x & TF32_MASK; hi.y = v.y & TF32_MASK; hi.z = v.z & TF32_MASK; hi.w = v.w & TF32_MASK;
+                    lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x)) & TF32_MASK;
+                    lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y)) & TF32_MASK;
+                    lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z)) & TF32_MASK;
+                    lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w)) & TF32_MASK;
+                };
+#pragma unroll
+                for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+                    uint4 hi, lo;
+                    split(a_hi[t + i * 128], hi, lo);
+                    a_hi[t + i * 128] = hi;
+                    a_lo[t + i * 128] = lo;
+                }
+                for (int i = t; i < b_tile_bytes / 16; i += 128) {
+                    uint4 hi, lo;
+                    split(b_hi[i], hi, lo);
+                    b_hi[i] = hi;
+                    b_lo[i] = lo;
+                }
+                fence_async_proxy();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&bar_split[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10),
+            // both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+            int it = 0, tile_it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+                const int as = tile_it & 1;
+                const uint32_t aph = (tile_it >> 1) & 1;
+                mbar_wait(&bar_tmem_empty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
+                for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&bar_split[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_TILE_BYTES);
+                    const uint64_t b_hi = make_desc(st + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = make_desc(st + 2 * A_TILE_BYTES + b_tile_bytes);
+#pragma unroll
+                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);  // +32 B inside the swizzle row
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kc | kk) != 0);
+                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(&bar_empty[s]);  // the stage may be refilled once these MMAs have read it
+                }
+                umma_commit(&bar_tmem_full[as]);  // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows 32w..32w+31 of the tile =====
+        int tile_it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int as = tile_it & 1;
+            const uint32_t aph = (tile_it >> 1) & 1;
+            mbar_wait(&bar_tmem_full[as], aph);
+            tc_fence_after();
+            const int row = mt * BLOCK_M + warp * 32 + lane;
+            const int n0 = nt * p.block_n;
+            const uint32_t taddr = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(warp * 32) << 16);
+            float* yrow = p.y + (size_t)row * p.ldy + n0;
+            for (int c = 0; c < p.block_n; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c, r);
+                tmem_ld_wait();
+                if (row < p.M) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] = __uint_as_float(r[i]);
+                        if (p.bias && n0 + c + i < p.N) v[i] += __ldg(p.bias + n0 + c + i);
+                    }
+                    if (n0 + c + 16 <= p.N && (p.ldy & 3) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(yrow + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + c + i < p.N) yrow[c + i] = v[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_tmem_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2D fp32 row-major [rows, cols] (row stride ld floats), box = 32 columns x box_rows rows, 128B swizzle, zero fill
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return MPC_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MPC_OK : MPC_ERR_INVALID;
+}
+
+}  // namespace tc
+}  // namespace mpc
+
+MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                               int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+    using namespace mpc;
+    using namespace mpc::tc;
+    if (!x || !w || !y || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
+    if (K % BLOCK_K || ldx < K || ldw < K || ldy < N || (ldx & 3) || (ldw & 3)) return MPC_ERR_UNSUPPORTED;
+    if (((uintptr_t)x | (uintptr_t)w) & 15u) return MPC_ERR_UNSUPPORTED;
+    if (M > INT32_MAX || N > 65536 || K > 65536) return MPC_ERR_UNSUPPORTED;
+    Params p;
+    p.M = (int)M;
+    p.N = (int)N;
+    p.K = (int)K;
+    int bn = (int)(N < 256 ? N : 256);
+    bn = (bn + 15) & ~15;
+    p.block_n = bn;
+    p.n_tiles = (int)ceil_div(N, bn);
+    p.m_tiles = (int)ceil_div(M, BLOCK_M);
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return MPC_ERR_UNSUPPORTED;
+    p.stages = stages;
+    p.bias = bias;
+    p.y = y;
+    p.ldy = (int)ldy;
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, x, M, K, ldx, BLOCK_M);
+    if (rc) return rc;
+    rc = make_map(&map_b, w, N, K, ldw, bn);
+    if (rc) return rc;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MPC_CUDA(cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
+    linear_3xtf32_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}

@@ -399,7 +399,7 @@ class BNAct(torch.autograd.Function):
             if M <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s"
                                  % (tuple(y.shape),))
-            scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            scratch = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
             stats = torch.empty(2 * C, dtype=torch.float32, device=dev)
             call("mpc_bn_stats_f32", ptr(y), ptr(stats), ptr(running_mean), ptr(running_var),
                  ptr(num_batches_tracked), ctypes.c_float(momentum), ptr(scratch), _i64(M), _i64(C),
@@ -436,6 +436,73 @@ def bn_act(y2d, gamma, beta, running_mean, running_var, num_batches_tracked, tra
     require_cuda(y2d)
     return BNAct.apply(_f32c(y2d), gamma, beta, running_mean, running_var, num_batches_tracked, bool(training),
                        float(momentum), float(eps), float(slope))
+
+
+# ------------------------------------------------------------------------------------------------------
+# shared-MLP projection on the tensor cores
+# ------------------------------------------------------------------------------------------------------
+_GEMM_IMPL = os.environ.get("MPC_GEMM", "tcgen05")  # "cublas" forces the library GEMM (A/B comparisons)
+
+
+def _tc_ok(x2d, w):
+    K = x2d.shape[1]
+    return (_GEMM_IMPL == "tcgen05" and x2d.is_cuda and x2d.dtype == torch.float32 and K % 32 == 0
+            and x2d.shape[0] > 0)
+
+
+def _tc_gemm(x2d, w, bias, out):
+    """out[M,N] = x2d[M,K] @ w[N,K]^T (+ bias) through mpc_linear_fwd_f32 (3xTF32 tcgen05)."""
+    M, K = x2d.shape
+    N = w.shape[0]
+    call("mpc_linear_fwd_f32", ptr(x2d), _i64(x2d.stride(0)), ptr(w), _i64(w.stride(0)), ptr(bias), ptr(out),
+         _i64(out.stride(0)), _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+
+
+class LinearTC(torch.autograd.Function):
+    """y = x W^T + b.  Forward and grad-input run on the tcgen05 kernel (the two GEMMs whose large operand is
+    the activation stream); grad-weight (a [N,M]x[M,K] reduction over all points) uses the library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, bias):
+        M, K = x2d.shape
+        N = w.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
+        _tc_gemm(x2d, w, bias, y)
+        ctx.save_for_backward(x2d, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2d, w = ctx.saved_tensors
+        gy = _f32c(gy)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = w.t().contiguous()  # [K,N]: grad_x[M,K] = gy[M,N] @ wt[K,N]^T
+            if _tc_ok(gy, wt):
+                gx = torch.empty_like(x2d)
+                _tc_gemm(gy, wt, None, gx)
+            else:
+                gx = gy.mm(w)
+        if ctx.needs_input_grad[1]:
+            gw = gy.t().mm(x2d)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb
+
+
+def linear(x, weight, bias=None):
+    """nn.Linear's arithmetic on any [..., K] input: the tcgen05 3xTF32 kernel when K % 32 == 0, else the
+    library GEMM (K = 3 / 16 layers: a few kFLOP per point)."""
+    require_cuda(x)
+    shape = x.shape
+    x2d = x.reshape(-1, shape[-1])
+    if _tc_ok(x2d, weight):
+        x2d = _f32c(x2d)
+        y = LinearTC.apply(x2d, weight.contiguous(), bias)
+    else:
+        y = torch.nn.functional.linear(x2d, weight, bias)
+    return y.view(*shape[:-1], weight.shape[0])
 
 
 def launches():

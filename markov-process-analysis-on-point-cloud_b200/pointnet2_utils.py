@@ -37,7 +37,7 @@ class Linear(nn.Module):
 
     def forward(self, input):
         shape = input.shape
-        y = F.linear(input.reshape(-1, shape[-1]), self.linear.weight, self.linear.bias)
+        y = ops.linear(input.reshape(-1, shape[-1]), self.linear.weight, self.linear.bias)
         if self.bn_flag is True:
             y = self.norm1(y)
             if self.act_flag is True:
@@ -79,9 +79,9 @@ class LocalTrans(nn.Module):
                                         idx.contiguous(), self.q.weight, self.q.bias, self.k.weight, self.k.bias,
                                         self.v.weight, self.v.bias)
         else:
-            q = F.linear(center, self.q.weight, self.q.bias)
-            kv = F.linear(features, torch.cat((self.k.weight, self.v.weight), 0),
-                          torch.cat((self.k.bias, self.v.bias), 0))
+            q = ops.linear(center, self.q.weight, self.q.bias)
+            kv = ops.linear(features, torch.cat((self.k.weight, self.v.weight), 0),
+                            torch.cat((self.k.bias, self.v.bias), 0))
             context = ops.AttnFeat.apply(q.contiguous(), kv.contiguous(), idx.contiguous())
         return residual + self.ffn(context)
 

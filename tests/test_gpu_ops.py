@@ -225,3 +225,39 @@ def test_bn_act(mpc, M, C, train, slope):
     scale = float(g0.grad.abs().max())
     torch.testing.assert_close(g1.grad.cpu(), g0.grad, rtol=1e-4, atol=1e-5 * max(1.0, scale))
     torch.testing.assert_close(b1.grad.cpu(), b0.grad, rtol=1e-4, atol=1e-5 * max(1.0, float(b0.grad.abs().max())))
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,K,N", [(128, 32, 64), (1000, 64, 64), (65536, 64, 64), (4096, 256, 256), (333, 896, 512),
+                                   (128, 128, 50), (70000, 192, 64), (8192, 512, 1024), (5, 64, 128), (4096, 64, 16)])
+def test_linear_3xtf32(mpc, M, K, N):
+    """y = x W^T + b on the tensor cores must be fp32-accurate (the reference is fp32): compared with an fp64
+    product, the error has to be of the same order as the library fp32 GEMM's, far below one TF32 pass."""
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref = (x.double() @ w.double().t() + b.double())
+    y = mpc.ops.linear(x, w, b)
+    lib = torch.nn.functional.linear(x, w, b)
+    err = (y.double() - ref).abs().max().item()
+    err_lib = (lib.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 4e-6 * scale + 4 * err_lib, (err, err_lib, scale)
+    # gradients through the autograd Function
+    xg, wg, bg = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    go = torch.randn(M, N, generator=g).cuda()
+    (mpc.ops.linear(xg, wg, bg) * go).sum().backward()
+    torch.testing.assert_close(xg.grad, (go.double() @ w.double()).float(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(wg.grad, (go.double().t() @ x.double()).float(), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(bg.grad, go.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+
+
+def test_linear_3xtf32_strided_operands(mpc):
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(2000, 192, generator=g).cuda()
+    x = big[:, 64:128]  # a column slice: row stride 192
+    w = torch.randn(96, 64, generator=g).cuda()
+    out = torch.empty(2000, 96, device="cuda")
+    mpc.ops._tc_gemm(x, w, None, out)
+    torch.testing.assert_close(out, (x.double() @ w.double().t()).float(), rtol=1e-5, atol=1e-5)

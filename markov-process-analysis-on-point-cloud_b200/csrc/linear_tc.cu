@@ -339,7 +339,7 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.n_tiles = (int)ceil_div(N, bn);
     p.m_tiles = (int)ceil_div(M, BLOCK_M);
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
-    int stages = (200 * 1024) / stage_bytes;
+    int stages = (222 * 1024) / stage_bytes;  // dynamic smem opt-in is 224 KB, 1 KB is alignment slack
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
@@ -354,7 +354,7 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        MPC_CUDA(cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MPC_CUDA(cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
     const int total_tiles = p.m_tiles * p.n_tiles;

@@ -192,6 +192,11 @@ int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean,
  * ------------------------------------------------------------------------------------------------- */
 int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
                        int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+/* Weight gradient of the same layer (what autograd derives for nn.Linear):  gw[N,K] = gy[M,N]^T x[M,K].
+ * Same 3xTF32 tcgen05 pipeline with MN-major operand descriptors (no transposed copies), the reduction over the M
+ * points split across the SMs and combined with red.global.add into gw (zero-filled by the call).  K % 32 == 0. */
+int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t ldx, float* gw, int64_t ldw,
+                         int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mpc_bn_act_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _int, _ptr, _ptr, _ptr, _ptr,
                            _i64, _i64, _ptr],
     "mpc_linear_fwd_f32": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr],
+    "mpc_linear_wgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr],
 }
 
 # kernels each entry point enqueues (cudaMemsetAsync calls not counted)
@@ -46,6 +47,7 @@ KERNELS_PER_CALL = {
     "mpc_three_interpolate_fwd_f32": 2, "mpc_three_interpolate_bwd_f32": 1, "mpc_attn_feat_fwd_f32": 1,
     "mpc_attn_feat_bwd_f32": 1, "mpc_attn_xyz_fwd_f32": 1, "mpc_attn_xyz_bwd_f32": 1, "mpc_bn_stats_f32": 2,
     "mpc_bn_act_fwd_f32": 1, "mpc_bn_act_bwd_f32": 2, "mpc_linear_fwd_f32": 1,
+    "mpc_linear_wgrad_f32": 1,
 }
 
 _lib = None

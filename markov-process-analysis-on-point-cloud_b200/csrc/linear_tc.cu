@@ -99,6 +99,15 @@ __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major descriptor for the weight-gradient GEMM, whose operands are contiguous along the OUTPUT dimension:
+// 32-element (128 B) rows run along M/N, successive rows are successive reduction indices.  For 32-bit (tf32)
+// MN-major operands the only legal shared-memory layout is SWIZZLE_128B_BASE32B (layout type 1, Swizzle<2,5,2>:
+// 32-byte pieces of a 128-byte row XORed with row % 4), which is what TMA's SWIZZLE_128B_ATOM_32B writes.
+// One TMA box = 32 (M/N) x 32 (reduction) = 4 KB; LBO = distance between 32-wide M/N atoms = 4096 B,
+// SBO = distance between 4-row reduction groups = 512 B.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
 
 struct Params {
     int M, N, K;
@@ -109,6 +118,9 @@ struct Params {
     const float* bias;  // may be null
     float* y;
     int ldy;
+    int mn_major;     // 0: y = x w^T (operands K-major).  1: y[i,j] += sum_r a[r,i] b[r,j] (operands MN-major)
+    int splits;       // reduction split across CTAs (mn_major only; results are reduced with red.global.add)
+    int k_chunks;     // ceil(reduction length / 32)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -124,8 +136,17 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int b_tile_bytes = p.block_n * BLOCK_K * 4;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k_chunks = p.K / BLOCK_K;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+    const int chunks_per_split = (p.k_chunks + p.splits - 1) / p.splits;
+    // work item -> (row tile, column tile, reduction range)
+    auto decode = [&](int item, int& mt, int& nt, int& kc0, int& kc1) {
+        const int sp = item % p.splits;
+        const int t = item / p.splits;
+        mt = t / p.n_tiles;
+        nt = t - mt * p.n_tiles;
+        kc0 = sp * chunks_per_split;
+        kc1 = min(p.k_chunks, kc0 + chunks_per_split);
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -154,15 +175,24 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-                for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+                int mt, nt, kc0, kc1;
+                decode(tile, mt, nt, kc0, kc1);
+                for (int kc = kc0; kc < kc1; ++kc, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(&bar_empty[s], ph ^ 1);
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&bar_full[s], A_TILE_BYTES + b_tile_bytes);
-                    tma_load_2d(&map_a, &bar_full[s], st, kc * BLOCK_K, mt * BLOCK_M);
-                    tma_load_2d(&map_b, &bar_full[s], st + 2 * A_TILE_BYTES, kc * BLOCK_K, nt * p.block_n);
+                    if (!p.mn_major) {
+                        tma_load_2d(&map_a, &bar_full[s], st, kc * BLOCK_K, mt * BLOCK_M);
+                        tma_load_2d(&map_b, &bar_full[s], st + 2 * A_TILE_BYTES, kc * BLOCK_K, nt * p.block_n);
+                    } else {  // 4 KB boxes: 32 output indices x 32 reduction rows
+                        for (int a = 0; a < BLOCK_M / 32; ++a)
+                            tma_load_2d(&map_a, &bar_full[s], st + a * 4096, mt * BLOCK_M + a * 32, kc * BLOCK_K);
+                        for (int b = 0; b < p.block_n / 32; ++b)
+                            tma_load_2d(&map_b, &bar_full[s], st + 2 * A_TILE_BYTES + b * 4096, nt * p.block_n + b * 32,
+                                        kc * BLOCK_K);
+                    }
                 }
             }
         }
@@ -171,7 +201,9 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int t = threadIdx.x - 128;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+            int mt, nt, kc0, kc1;
+            decode(tile, mt, nt, kc0, kc1);
+            for (int kc = kc0; kc < kc1; ++kc, ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 mbar_wait(&bar_full[s], ph);
@@ -210,7 +242,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10),
             // both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
-                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+                                   ((uint32_t)(BLOCK_M >> 4) << 24) |
+                                   (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);  // a_major / b_major = MN
             int it = 0, tile_it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
                 const int as = tile_it & 1;
@@ -218,19 +251,25 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 mbar_wait(&bar_tmem_empty[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
-                for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+                int mt, nt, kc0, kc1;
+                decode(tile, mt, nt, kc0, kc1);
+                for (int kc = kc0; kc < kc1; ++kc, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(&bar_split[s], ph);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_TILE_BYTES);
-                    const uint64_t b_hi = make_desc(st + 2 * A_TILE_BYTES);
-                    const uint64_t b_lo = make_desc(st + 2 * A_TILE_BYTES + b_tile_bytes);
+                    const uint32_t o_alo = A_TILE_BYTES, o_bhi = 2 * A_TILE_BYTES, o_blo = 2 * A_TILE_BYTES + b_tile_bytes;
+                    const uint64_t a_hi = p.mn_major ? make_desc_mn(st) : make_desc(st);
+                    const uint64_t a_lo = p.mn_major ? make_desc_mn(st + o_alo) : make_desc(st + o_alo);
+                    const uint64_t b_hi = p.mn_major ? make_desc_mn(st + o_bhi) : make_desc(st + o_bhi);
+                    const uint64_t b_lo = p.mn_major ? make_desc_mn(st + o_blo) : make_desc(st + o_blo);
+                    // K-major: +32 B inside the swizzle row per K step; MN-major: +1024 B (next 8 reduction rows)
+                    const uint64_t step = p.mn_major ? (1024u >> 4) : ((UMMA_K * 4) >> 4);
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                        const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);  // +32 B inside the swizzle row
-                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kc | kk) != 0);
+                        const uint64_t adv = step * kk;
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kc != kc0 || kk != 0) ? 1u : 0u);
                         umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
                         umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
                     }
@@ -243,7 +282,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows 32w..32w+31 of the tile =====
         int tile_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
-            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            int mt, nt, kc0, kc1;
+            decode(tile, mt, nt, kc0, kc1);
             const int as = tile_it & 1;
             const uint32_t aph = (tile_it >> 1) & 1;
             mbar_wait(&bar_tmem_full[as], aph);
@@ -263,7 +303,17 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         v[i] = __uint_as_float(r[i]);
                         if (p.bias && n0 + c + i < p.N) v[i] += __ldg(p.bias + n0 + c + i);
                     }
-                    if (n0 + c + 16 <= p.N && (p.ldy & 3) == 0) {
+                    if (p.splits > 1) {  // partial sums of a split reduction
+                        if (n0 + c + 16 <= p.N && (p.ldy & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                red_add_f32x4(yrow + c + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n0 + c + i < p.N) red_add_f32(yrow + c + i, v[i]);
+                        }
+                    } else if (n0 + c + 16 <= p.N && (p.ldy & 3) == 0) {
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
                             *reinterpret_cast<float4*>(yrow + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -305,7 +355,9 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2D fp32 row-major [rows, cols] (row stride ld floats), box = 32 columns x box_rows rows, 128B swizzle, zero fill
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    bool mn_major = false) {
+    if (((uintptr_t)base & 15u) || (ld & 3)) return MPC_ERR_UNSUPPORTED;
     EncodeTiledFn fn = encode_fn();
     if (!fn) return MPC_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -313,9 +365,19 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? MPC_OK : MPC_ERR_INVALID;
+}
+
+static cudaError_t ensure_smem_optin() {
+    static bool done = false;  // idempotent attribute; a benign race at worst sets it twice
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    done = e == cudaSuccess;
+    return e;
 }
 
 }  // namespace tc
@@ -346,20 +408,76 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.bias = bias;
     p.y = y;
     p.ldy = (int)ldy;
+    p.mn_major = 0;
+    p.splits = 1;
+    p.k_chunks = (int)(K / BLOCK_K);
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, x, M, K, ldx, BLOCK_M);
     if (rc) return rc;
     rc = make_map(&map_b, w, N, K, ldw, bn);
     if (rc) return rc;
     const size_t smem = (size_t)stages * stage_bytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MPC_CUDA(cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        attr_set = true;
-    }
+    MPC_CUDA(ensure_smem_optin());
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
     linear_3xtf32_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+// grad_w[N,K] = gy[M,N]^T x[M,K]: both operands are contiguous along the OUTPUT dimensions (MN-major for the
+// tensor core), the reduction runs over all M points and is split across the SMs.
+MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t ldx, float* gw, int64_t ldw,
+                                 int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+    using namespace mpc;
+    using namespace mpc::tc;
+    if (!gy || !x || !gw || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
+    if (K % 32 || ldg < N || ldx < K || ldw < K || (ldg & 3) || (ldx & 3)) return MPC_ERR_UNSUPPORTED;
+    if (((uintptr_t)gy | (uintptr_t)x) & 15u) return MPC_ERR_UNSUPPORTED;
+    if (M > INT32_MAX || N > 65536 || K > 65536) return MPC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    Params p;
+    p.M = (int)N;  // output rows  = N (tile of 128, TMEM lanes)
+    p.N = (int)K;  // output cols  = K (accumulator columns)
+    p.K = (int)M;  // reduction    = M points
+    int bn = (int)(K < 256 ? K : 256);  // multiple of 32 because K % 32 == 0
+    p.block_n = bn;
+    p.n_tiles = (int)ceil_div(K, bn);
+    p.m_tiles = (int)ceil_div(N, BLOCK_M);
+    p.k_chunks = (int)ceil_div(M, BLOCK_K);
+    const int tiles = p.m_tiles * p.n_tiles;
+    int splits = kNumSMs / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > p.k_chunks) splits = p.k_chunks;
+    // every split must own at least one chunk: shrink until ceil-division leaves none empty
+    while (splits > 1 && (int)ceil_div(p.k_chunks, splits) * (splits - 1) >= p.k_chunks) --splits;
+    p.splits = splits;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
+    int stages = (222 * 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return MPC_ERR_UNSUPPORTED;
+    p.stages = stages;
+    p.bias = nullptr;
+    p.y = gw;
+    p.ldy = (int)ldw;
+    p.mn_major = 1;
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, gy, M, N, ldg, 32, true);  // dims {N, M}: inner = output index n, box 32 x 32
+    if (rc) return rc;
+    rc = make_map(&map_b, x, M, K, ldx, 32, true);
+    if (rc) return rc;
+    if (splits > 1) {
+        if (ldw == K) {
+            MPC_CUDA(cudaMemsetAsync(gw, 0, (size_t)N * K * sizeof(float), st));
+        } else {
+            MPC_CUDA(cudaMemset2DAsync(gw, (size_t)ldw * 4, 0, (size_t)K * 4, (size_t)N, st));
+        }
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    MPC_CUDA(ensure_smem_optin());
+    const int items = tiles * splits;
+    const int grid = items < kNumSMs ? items : kNumSMs;
+    linear_3xtf32_kernel<<<grid, THREADS, smem, st>>>(map_a, map_b, p);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

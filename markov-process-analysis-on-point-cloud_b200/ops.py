@@ -485,7 +485,14 @@ class LinearTC(torch.autograd.Function):
             else:
                 gx = gy.mm(w)
         if ctx.needs_input_grad[1]:
-            gw = gy.t().mm(x2d)
+            M, K = x2d.shape
+            N = w.shape[0]
+            if _GEMM_IMPL == "tcgen05" and K % 32 == 0 and N % 4 == 0:
+                gw = torch.empty(N, K, dtype=torch.float32, device=gy.device)
+                call("mpc_linear_wgrad_f32", ptr(gy), _i64(gy.stride(0)), ptr(x2d), _i64(x2d.stride(0)), ptr(gw),
+                     _i64(K), _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+            else:
+                gw = gy.t().mm(x2d)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(0)
         return gx, gw, gb

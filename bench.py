@@ -188,16 +188,51 @@ class Step:
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
             off += p.numel()
 
-    def __call__(self, xyz, label, target, starts):
+    def exchange(self):
+        """The path's one exchange step: mean of the flat gradient over the data-parallel ranks."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad)
+            self.flat_grad.mul_(1.0 / self.world)
+
+    def __call__(self, xyz, label, target, starts, collective=True):
         self.flat_grad.zero_()
         with self.mpc.ops.index_tape(fps_starts=starts):
             out, _ = self.model(xyz, label)
         loss = self.loss_fn(out.reshape(-1, N_CLASSES), target, None)
         loss.backward()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad)
-            self.flat_grad.mul_(1.0 / self.world)
+        if collective:
+            self.exchange()
         return loss
+
+
+class GraphedStep:
+    """The same step captured once into a CUDA graph (static input buffers, private memory pool) and replayed:
+    ~1800 kernel launches per step otherwise make the step CPU-launch-bound."""
+
+    def __init__(self, step, xyz, label, target, starts):
+        self.step = step
+        self.xyz, self.label, self.target = xyz.clone(), label.clone(), target.clone()
+        self.starts = [s.clone() for s in starts]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm the allocator / autograd on the capture stream
+            for _ in range(2):
+                step(self.xyz, self.label, self.target, self.starts)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = step(self.xyz, self.label, self.target, self.starts, collective=False)
+
+    def __call__(self, xyz, label, target, starts):
+        self.xyz.copy_(xyz, non_blocking=True)
+        self.label.copy_(label, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        for d, s in zip(self.starts, starts):
+            d.copy_(s, non_blocking=True)
+        self.graph.replay()
+        self.step.exchange()
+        return self.loss
 
 
 def op_table(records):
@@ -260,12 +295,33 @@ def run_own(args):
                 f.write("%-34s %6d %10.3f %12.2f %9.1f\n" % (name, n, ms, by / 1e6, by / 1e6 / max(ms, 1e-9)))
             f.write("%-34s %6s %10.3f\n" % ("sum of ours", "", sum(r[2] for r in full)))
 
+    # ---- eager, dominant op instrumented: per-launch CUDA events on the launching stream for the roofline
+    mpc._lib.profiler = {"names": {dominant}, "records": {}}
+    for _ in range(2):
+        flush.zero_()
+        step(xyz, label, target, device_starts())
+    torch.cuda.synchronize()
+    dom = op_table(mpc._lib.profiler["records"])[0]
+    dom_steps = 2
+    mpc._lib.profiler = None
+
+    run_step = step
+    graphed = False
+    if not args.no_graph:
+        try:
+            run_step = GraphedStep(step, xyz, label, target, device_starts())
+            graphed = True
+        except Exception as e:  # noqa: BLE001 -- report and fall back to eager launches
+            print("bench.py: CUDA graph capture failed (%s: %s); timing eager launches" % (type(e).__name__, e),
+                  file=sys.stderr)
+            torch.cuda.synchronize()
+            run_step = step
+
     # ---- timed region: device-resident inputs, per-step events, L2 flush between steps (outside the events)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    mpc._lib.profiler = {"names": {dominant}, "records": {}}
-    k0 = mpc.ops.kernels_launched()
+    kernels_per_step = sum(mpc._lib.KERNELS_PER_CALL[n] * c for n, c, _, _ in full)
     barrier()
     events = []
     torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed region (all threads)
@@ -274,20 +330,18 @@ def run_own(args):
         starts = device_starts()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step(xyz, label, target, starts)
+        run_step(xyz, label, target, starts)
         b.record()
         events.append((a, b))
     barrier()
     torch.cuda.profiler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in events)
-    launches = mpc.ops.kernels_launched() - k0
-    dom = op_table(mpc._lib.profiler["records"])[0]
-    mpc._lib.profiler = None
+    launches = kernels_per_step * args.steps  # kernels of ours per step (counted on the eager instrumented step)
 
     # ---- end to end: pinned host inputs -> H2D -> step -> loss D2H, all inside the timed region
     for _ in range(2):
-        step(xyz_h.to(device, non_blocking=True), label_h.to(device, non_blocking=True),
-             target_h.to(device, non_blocking=True), device_starts()).item()
+        run_step(xyz_h.to(device, non_blocking=True), label_h.to(device, non_blocking=True),
+                 target_h.to(device, non_blocking=True), device_starts()).item()
     barrier()
     t_e2e = 0.0
     for _ in range(args.steps):
@@ -295,8 +349,8 @@ def run_own(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         starts = [s.pin_memory() for s in fps_starts(B, gen)]
-        loss = step(xyz_h.to(device, non_blocking=True), label_h.to(device, non_blocking=True),
-                    target_h.to(device, non_blocking=True), [s.to(device, non_blocking=True) for s in starts])
+        loss = run_step(xyz_h.to(device, non_blocking=True), label_h.to(device, non_blocking=True),
+                        target_h.to(device, non_blocking=True), [s.to(device, non_blocking=True) for s in starts])
         loss_host = loss.item()  # device -> host read of the step's result (synchronises)
         t_e2e += time.perf_counter() - t0
     barrier()
@@ -321,14 +375,17 @@ def run_own(args):
                                    "configs[1])", "clouds_per_gpu": B, "points": N_POINTS, "classes": N_CLASSES,
                        "parallelism": "dp%d (batch shards; NCCL all-reduce of the flat fp32 gradient)" % world
                        if world > 1 else "single GPU",
-                       "l2": "256 MiB flush buffer written between timed steps; step working set >> 126 MB L2"},
+                       "l2": "256 MiB flush buffer written between timed steps; step working set >> 126 MB L2",
+                       "launch": "CUDA graph replay" if graphed else "eager launches"},
             "e2e": {"value": clouds / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind + " (burst copy)",
                          "launches": n_calls, "avg_launch_us": 1e3 * ms / max(n_calls, 1),
-                         "share_of_step": ms / dev_ms, "algo_bytes_per_step": by / args.steps},
+                         "share_of_step": (ms / dom_steps) / (dev_ms / args.steps),
+                         "algo_bytes_per_step": by / dom_steps,
+                         "how": "per-launch CUDA events over %d eager steps of the same workload" % dom_steps},
             "clocks": clocks,
             "last_loss": loss_host,
         }
@@ -349,6 +406,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile-ops", default=None, help="write the per-entry-point device-time table here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -58,16 +58,44 @@ __device__ __forceinline__ void drain_queue(CandQueue& q, int& qn, float (&bd)[K
 }
 
 // ---- C == 3 ------------------------------------------------------------------------------------------------
-constexpr int KNN3_TILE = 2048;  // reference points per shared-memory tile (float4 x,y,z,|r|^2 = 32 KB)
-
+// A CTA serves 32 queries with SPLIT warps: lane = query, warp w scans the w-th part of every reference tile
+// (so the shared-memory reads stay warp-wide broadcasts) and keeps its own sorted K-list; the lists are merged
+// at the end with a lexicographic (distance, index) comparison.  SPLIT is picked on the host so that even the
+// small query sets of the coarse states (128 queries per cloud) put ~150k threads in flight: with one thread per
+// query those calls were pure latency chains (one warp per scheduler, 2048 dependent iterations).
 template <int K>
-__global__ void __launch_bounds__(KNN_THREADS)
+__device__ __forceinline__ void topk_insert_lex(float (&bd)[K], int (&bi)[K], float d, int n) {
+    bd[K - 1] = d;
+    bi[K - 1] = n;
+#pragma unroll
+    for (int p = K - 1; p > 0; --p) {
+        const bool lt = bd[p] < bd[p - 1] || (bd[p] == bd[p - 1] && bi[p] < bi[p - 1]);
+        if (lt) {
+            float td = bd[p];
+            bd[p] = bd[p - 1];
+            bd[p - 1] = td;
+            int ti = bi[p];
+            bi[p] = bi[p - 1];
+            bi[p - 1] = ti;
+        }
+    }
+}
+
+template <int K, int SPLIT>
+__global__ void __launch_bounds__(32 * SPLIT)
 knn3_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
             int64_t* __restrict__ idx_out, int N, int S) {
-    __shared__ float4 tile[KNN3_TILE];
-    __shared__ CandQueue queue;
+    constexpr int THREADS = 32 * SPLIT;
+    constexpr int KNN3_TILE = SPLIT >= 16 ? 1024 : 2048;  // reference points per tile (float4 x,y,z,|r|^2)
+    // one static block <= 48 KB: [tile | candidate queues]; reused as the merge buffer at the end
+    // (SPLIT * K * 32 * 8 B, the host only launches combinations with SPLIT * K <= 128)
+    __shared__ __align__(16) unsigned char raw[KNN3_TILE * 16 + KNN_Q * THREADS * 8];
+    float4* tile = reinterpret_cast<float4*>(raw);
+    float (*qd)[THREADS] = reinterpret_cast<float (*)[THREADS]>(raw + KNN3_TILE * 16);
+    int (*qi)[THREADS] = reinterpret_cast<int (*)[THREADS]>(raw + KNN3_TILE * 16 + KNN_Q * THREADS * 4);
     const int b = blockIdx.y;
-    const int s = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
     const bool active = s < S;
     const float* rb = ref + (size_t)b * N * 3;
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -83,40 +111,76 @@ knn3_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float*
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         bd[k] = __int_as_float(0x7f800000);  // +inf
-        bi[k] = 0;
+        bi[k] = 0x7fffffff;
     }
-    // inactive threads keep thr = -inf: they never enqueue but still take part in the warp votes
     float thr = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
     int cnt = 0;
+    auto drain = [&]() {
+        const int m = __reduce_max_sync(0xffffffffu, cnt);
+        for (int e = 0; e < m; ++e) {
+            if (e < cnt) {
+                const float d = qd[e][threadIdx.x];
+                if (d < bd[K - 1]) topk_insert<K>(bd, bi, d, qi[e][threadIdx.x]);
+            }
+        }
+        cnt = 0;
+        thr = bd[K - 1];
+    };
     for (int t0 = 0; t0 < N; t0 += KNN3_TILE) {
         const int tn = min(KNN3_TILE, N - t0);
         __syncthreads();
-        for (int j = threadIdx.x; j < tn; j += KNN_THREADS) {
+        for (int j = threadIdx.x; j < tn; j += THREADS) {
             const float* r = rb + (size_t)(t0 + j) * 3;
             float x = r[0], y = r[1], z = r[2];
             tile[j] = make_float4(x, y, z, sqnorm3(x, y, z));
         }
         __syncthreads();
-        for (int j0 = 0; j0 < tn; j0 += 4) {
+        const int part = (((tn + SPLIT - 1) / SPLIT) + 3) & ~3;
+        const int jb = w * part, je = min(tn, jb + part);
+        for (int j0 = jb; j0 < je; j0 += 4) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = j0 + u;
-                const float4 r = tile[j < tn ? j : tn - 1];  // broadcast read
+                const float4 r = tile[j < je ? j : je - 1];  // warp-wide broadcast
                 float dot = __fmul_rn(qx, r.x);
                 dot = __fmaf_rn(qy, r.y, dot);
                 dot = __fmaf_rn(qz, r.z, dot);
                 const float d = sqdist_from_dot(dot, qn, r.w);
-                if (j < tn && d < thr) {
-                    queue.d[cnt][threadIdx.x] = d;
-                    queue.i[cnt][threadIdx.x] = t0 + j;
+                if (j < je && d < thr) {
+                    qd[cnt][threadIdx.x] = d;
+                    qi[cnt][threadIdx.x] = t0 + j;
                     ++cnt;
                 }
             }
-            if (__any_sync(0xffffffffu, cnt > KNN_QFLUSH)) drain_queue<K>(queue, cnt, bd, bi, thr);
+            if (__any_sync(0xffffffffu, cnt > KNN_QFLUSH)) drain();
         }
     }
-    drain_queue<K>(queue, cnt, bd, bi, thr);
-    if (active) {
+    drain();
+    if (SPLIT > 1) {  // merge the SPLIT partial lists of each query (warp 0 does the merge)
+        __syncthreads();
+        float* md = reinterpret_cast<float*>(raw);             // [SPLIT][K][32]
+        int* mi = reinterpret_cast<int*>(raw) + SPLIT * K * 32;
+        if (w > 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                md[(w * K + k) * 32 + lane] = bd[k];
+                mi[(w * K + k) * 32 + lane] = bi[k];
+            }
+        }
+        __syncthreads();
+        if (w == 0) {
+            for (int w2 = 1; w2 < SPLIT; ++w2) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float d = md[(w2 * K + k) * 32 + lane];
+                    const int n = mi[(w2 * K + k) * 32 + lane];
+                    const bool lt = d < bd[K - 1] || (d == bd[K - 1] && n < bi[K - 1]);
+                    if (lt) topk_insert_lex<K>(bd, bi, d, n);
+                }
+            }
+        }
+    }
+    if (active && w == 0) {
         const size_t o = ((size_t)b * S + s) * K;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -350,8 +414,18 @@ template <int K>
 static int launch_knn(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, int B, int N,
                       int S, int C, cudaStream_t st) {
     if (C == 3) {
-        dim3 grid((unsigned)ceil_div(S, KNN_THREADS), (unsigned)B);
-        knn3_kernel<K><<<grid, KNN_THREADS, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+        // threads per query: enough to put ~150k threads in flight, bounded by the merge buffer (SPLIT*K <= 128)
+        // and by the work available per warp (>= 64 reference points)
+        const int64_t queries = (int64_t)B * S;
+        int split = 1;
+        while (split < 16 && queries * split < 150000 && split * 4 * K <= 128 && N / (split * 4) >= 64) split *= 4;
+        dim3 grid((unsigned)ceil_div(S, 32), (unsigned)B);
+        if (split == 1)
+            knn3_kernel<K, 1><<<grid, 32, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+        else if (split == 4)
+            knn3_kernel<K, 4><<<grid, 128, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+        else
+            knn3_kernel<K, 16><<<grid, 512, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
         MPC_LAUNCH_CHECK();
         return MPC_OK;
     }

@@ -498,6 +498,93 @@ class LinearTC(torch.autograd.Function):
         return gx, gw, gb
 
 
+class LinearBNAct(torch.autograd.Function):
+    """The whole shared-MLP block of the reference (`Linear.forward`, R/modules/pointnet2_utils.py:413-425, with
+    bn=False => BatchNorm1d): y = x W^T + b on the tensor cores, batch statistics, normalise + LeakyReLU -- one
+    autograd node.  Backward: BN/activation backward (two streaming kernels), grad-input and grad-weight on the
+    tensor cores.  The Linear bias feeds a BatchNorm, so its gradient is known in closed form: exactly 0 with
+    batch statistics (BatchNorm removes any per-channel constant) and gamma * rsqrt(var + eps) * grad_beta with
+    running statistics -- no reduction over the M rows is needed."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, bias, gamma, beta, running_mean, running_var, num_batches_tracked, training, momentum,
+                eps, slope):
+        M, K = x2d.shape
+        N = w.shape[0]
+        dev = x2d.device
+        y = torch.empty(M, N, dtype=torch.float32, device=dev)
+        _tc_gemm(x2d, w, bias, y)
+        if training:
+            if M <= 1:
+                raise ValueError("Expected more than 1 value per channel when training, got input size %s"
+                                 % ((M, N),))
+            scratch = torch.empty(2 * N + 1, dtype=torch.float64, device=dev)
+            stats = torch.empty(2 * N, dtype=torch.float32, device=dev)
+            call("mpc_bn_stats_f32", ptr(y), ptr(stats), ptr(running_mean), ptr(running_var),
+                 ptr(num_batches_tracked), ctypes.c_float(momentum), ptr(scratch), _i64(M), _i64(N),
+                 algo_bytes=M * N * 4)
+            mean, var = stats[:N], stats[N:]
+        else:
+            mean, var = running_mean, running_var
+        out = torch.empty_like(y)
+        call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
+             ctypes.c_float(slope), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
+        ctx.save_for_backward(x2d, w, y, mean, var, gamma, beta)
+        ctx.cfg = (training, eps, slope, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x2d, w, y, mean, var, gamma, beta = ctx.saved_tensors
+        training, eps, slope, has_bias = ctx.cfg
+        M, K = x2d.shape
+        N = w.shape[0]
+        dev = y.device
+        grad_out = _f32c(grad_out)
+        gy = torch.empty_like(y)
+        gg = torch.empty(N, dtype=torch.float32, device=dev)
+        gb = torch.empty(N, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2 * N, dtype=torch.float64, device=dev)
+        call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
+             ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
+             ptr(gb), ptr(scratch), _i64(M), _i64(N), algo_bytes=3 * M * N * 4)
+        gx = gw = gbias = None
+        if ctx.needs_input_grad[0]:
+            wt = w.t().contiguous()
+            if _tc_ok(gy, wt):
+                gx = torch.empty_like(x2d)
+                _tc_gemm(gy, wt, None, gx)
+            else:
+                gx = gy.mm(w)
+        if ctx.needs_input_grad[1]:
+            if K % 32 == 0 and N % 4 == 0:
+                gw = torch.empty(N, K, dtype=torch.float32, device=dev)
+                call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(K), ptr(gw), _i64(K), _i64(M), _i64(K),
+                     _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+            else:
+                gw = gy.t().mm(x2d)
+        if has_bias and ctx.needs_input_grad[2]:
+            gbias = torch.zeros_like(gb) if training else gamma * torch.rsqrt(var + eps) * gb
+        return gx, gw, gbias, gg, gb, None, None, None, None, None, None, None
+
+
+def linear_bn_act(x, weight, bias, bn, training, slope):
+    """Linear -> BatchNorm1d(channels) -> LeakyReLU(slope) on any [..., K] input (slope = 1: no activation).
+    `bn` is the nn.BatchNorm1d holding gamma / beta / running statistics."""
+    require_cuda(x)
+    shape = x.shape
+    x2d = x.reshape(-1, shape[-1])
+    if _tc_ok(x2d, weight):
+        out = LinearBNAct.apply(_f32c(x2d), weight.contiguous(), bias, bn.weight, bn.bias, bn.running_mean,
+                                bn.running_var, bn.num_batches_tracked, bool(training), float(bn.momentum),
+                                float(bn.eps), float(slope))
+    else:
+        y = torch.nn.functional.linear(x2d, weight, bias)
+        out = bn_act(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, training,
+                     momentum=bn.momentum, eps=bn.eps, slope=slope)
+    return out.view(*shape[:-1], weight.shape[0])
+
+
 def linear(x, weight, bias=None):
     """nn.Linear's arithmetic on any [..., K] input: the tcgen05 3xTF32 kernel when K % 32 == 0, else the
     library GEMM (K = 3 / 16 layers: a few kFLOP per point)."""

@@ -36,18 +36,11 @@ class Linear(nn.Module):
         self.act = nn.LeakyReLU(negative_slope=0.2)
 
     def forward(self, input):
-        shape = input.shape
-        y = ops.linear(input.reshape(-1, shape[-1]), self.linear.weight, self.linear.bias)
-        if self.bn_flag is True:
-            y = self.norm1(y)
-            if self.act_flag is True:
-                y = self.act(y)
-        else:
-            n = self.norm2
-            y = ops.bn_act(y, n.weight, n.bias, n.running_mean, n.running_var, n.num_batches_tracked,
-                           training=self.training, momentum=n.momentum, eps=n.eps,
-                           slope=0.2 if self.act_flag is True else 1.0)
-        return y.view(*shape[:-1], y.shape[-1])
+        if self.bn_flag is True:  # LayerNorm branch: never taken by a shipped model
+            y = self.norm1(ops.linear(input, self.linear.weight, self.linear.bias))
+            return self.act(y) if self.act_flag is True else y
+        return ops.linear_bn_act(input, self.linear.weight, self.linear.bias, self.norm2, self.training,
+                                 0.2 if self.act_flag is True else 1.0)
 
 
 class LocalTrans(nn.Module):

@@ -198,6 +198,11 @@ int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw,
 int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t ldx, float* gw, int64_t ldw,
                          int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
 
+/* Debug facility (not part of the data path): when set to a device buffer of 1024 int64, CTA 0 of the tensor-core
+ * kernels records a clock64() timeline per warp role (producer / splitter / MMA / epilogue: 256 slots each).
+ * Pass NULL to switch it off (the default).  Process-global. */
+int mpc_debug_trace_buffer(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ SIGNATURES = {
                            _i64, _i64, _ptr],
     "mpc_linear_fwd_f32": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr],
     "mpc_linear_wgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr],
+    "mpc_debug_trace_buffer": [_ptr],
 }
 
 # kernels each entry point enqueues (cudaMemsetAsync calls not counted)

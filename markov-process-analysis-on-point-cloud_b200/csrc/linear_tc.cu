@@ -94,6 +94,24 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int STAGING_BYTES = BLOCK_M * 128;  // one 32-column slab of a tile: 128 rows x 128 B
+constexpr int EPI_SMEM_BYTES = STAGING_BYTES + 1024;  // + bias for up to 256 columns
+
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1, layout SWIZZLE_128B (2).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -121,20 +139,31 @@ struct Params {
     int mn_major;     // 0: y = x w^T (operands K-major).  1: y[i,j] += sum_r a[r,i] b[r,j] (operands MN-major)
     int splits;       // reduction split across CTAs (mn_major only; results are reduced with red.global.add)
     int k_chunks;     // ceil(reduction length / 32)
+    long long* trace; // debug: per-role clock64() timeline of CTA 0 (null in production)
+    int tma_out;      // 1: results leave through a swizzled staging slab + TMA store / TMA reduce-add
 };
+
+// debug timeline: role r in [0,4) records up to 255 timestamps
+#define MPC_TRACE(role, n)                                                              \
+    do {                                                                                \
+        if (p.trace && blockIdx.x == 0 && (n) < 255) p.trace[(role) * 256 + (n)++] = clock64(); \
+    } while (0)
 
 __global__ void __launch_bounds__(THREADS, 1)
 linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const Params p) {
+                     const __grid_constant__ CUtensorMap map_y, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_full[MAX_STAGES], bar_split[MAX_STAGES], bar_empty[MAX_STAGES];
     __shared__ uint64_t bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
     // dynamic smem is requested with 1024 B of slack and aligned here (swizzle-128B atoms need 1024 B alignment)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (pointer arithmetic on the __shared__ array, not an integer round-trip, so accesses stay LDS/STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int b_tile_bytes = p.block_n * BLOCK_K * 4;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+    uint8_t* staging = smem + (size_t)p.stages * stage_bytes;                 // 16 KB, 1024-aligned
+    float* bias_s = reinterpret_cast<float*>(staging + STAGING_BYTES);        // 256 floats
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int chunks_per_split = (p.k_chunks + p.splits - 1) / p.splits;
@@ -173,7 +202,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 8) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int it = 0;
+            int it = 0, tn_ = 0;
+            MPC_TRACE(0, tn_);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int mt, nt, kc0, kc1;
                 decode(tile, mt, nt, kc0, kc1);
@@ -181,6 +211,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(&bar_empty[s], ph ^ 1);
+                    MPC_TRACE(0, tn_);
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&bar_full[s], A_TILE_BYTES + b_tile_bytes);
                     if (!p.mn_major) {
@@ -199,7 +230,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else if (warp >= 4 && warp < 8) {
         // ===== splitters: x -> (hi, lo) in place, 16 bytes per thread per step, conflict-free =====
         const int t = threadIdx.x - 128;
-        int it = 0;
+        int it = 0, tn_ = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mt, nt, kc0, kc1;
             decode(tile, mt, nt, kc0, kc1);
@@ -207,6 +238,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 mbar_wait(&bar_full[s], ph);
+                if (t == 0) MPC_TRACE(1, tn_);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 uint4* a_hi = reinterpret_cast<uint4*>(st);
                 uint4* a_lo = reinterpret_cast<uint4*>(st + A_TILE_BYTES);
@@ -219,21 +251,35 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z)) & TF32_MASK;
                     lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w)) & TF32_MASK;
                 };
+                {   // all loads first (independent), then split + store: one shared-memory latency, not eight
+                    uint4 v[A_TILE_BYTES / 16 / 128];
 #pragma unroll
-                for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
-                    uint4 hi, lo;
-                    split(a_hi[t + i * 128], hi, lo);
-                    a_hi[t + i * 128] = hi;
-                    a_lo[t + i * 128] = lo;
+                    for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) v[i] = a_hi[t + i * 128];
+#pragma unroll
+                    for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+                        uint4 hi, lo;
+                        split(v[i], hi, lo);
+                        a_hi[t + i * 128] = hi;
+                        a_lo[t + i * 128] = lo;
+                    }
                 }
-                for (int i = t; i < b_tile_bytes / 16; i += 128) {
-                    uint4 hi, lo;
-                    split(b_hi[i], hi, lo);
-                    b_hi[i] = hi;
-                    b_lo[i] = lo;
+                for (int i0 = t; i0 < b_tile_bytes / 16; i0 += 4 * 128) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u * 128 < b_tile_bytes / 16) v[u] = b_hi[i0 + u * 128];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u * 128 < b_tile_bytes / 16) {
+                            uint4 hi, lo;
+                            split(v[u], hi, lo);
+                            b_hi[i0 + u * 128] = hi;
+                            b_lo[i0 + u * 128] = lo;
+                        }
                 }
                 fence_async_proxy();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&bar_split[s]);
+                if (t == 0) MPC_TRACE(1, tn_);
             }
         }
     } else if (warp == 9) {
@@ -244,11 +290,12 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                                    ((uint32_t)(BLOCK_M >> 4) << 24) |
                                    (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);  // a_major / b_major = MN
-            int it = 0, tile_it = 0;
+            int it = 0, tile_it = 0, tn_ = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
                 const int as = tile_it & 1;
                 const uint32_t aph = (tile_it >> 1) & 1;
                 mbar_wait(&bar_tmem_empty[as], aph ^ 1);
+                MPC_TRACE(2, tn_);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
                 int mt, nt, kc0, kc1;
@@ -257,6 +304,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(&bar_split[s], ph);
+                    MPC_TRACE(2, tn_);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t o_alo = A_TILE_BYTES, o_bhi = 2 * A_TILE_BYTES, o_blo = 2 * A_TILE_BYTES + b_tile_bytes;
@@ -280,17 +328,55 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows 32w..32w+31 of the tile =====
-        int tile_it = 0;
+        int tile_it = 0, tn_ = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             int mt, nt, kc0, kc1;
             decode(tile, mt, nt, kc0, kc1);
             const int as = tile_it & 1;
             const uint32_t aph = (tile_it >> 1) & 1;
             mbar_wait(&bar_tmem_full[as], aph);
+            if (threadIdx.x == 0) MPC_TRACE(3, tn_);
             tc_fence_after();
             const int row = mt * BLOCK_M + warp * 32 + lane;
             const int n0 = nt * p.block_n;
             const uint32_t taddr = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(warp * 32) << 16);
+            if (p.tma_out) {
+                // bias of this tile's columns -> shared (broadcast reads below); also orders reuse of bias_s
+                epi_barrier();
+                for (int i = threadIdx.x; i < p.block_n; i += 128)
+                    bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+                epi_barrier();
+                const int r_in = warp * 32 + lane;  // row inside the tile = TMEM lane
+                uint4* srow = reinterpret_cast<uint4*>(staging + r_in * 128);
+                for (int c = 0; c < p.block_n; c += 32) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(taddr + c, r0);
+                    tmem_ld16(taddr + c + 16, r1);
+                    tmem_ld_wait();
+                    // the previous slab's TMA store must have finished READING the staging buffer
+                    if (threadIdx.x == 0) bulk_wait_read0();
+                    epi_barrier();
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {  // 8 x 16 B of this row, 128B-swizzled like the TMA box expects
+                        const uint32_t* src = q4 < 4 ? &r0[q4 * 4] : &r1[(q4 - 4) * 4];
+                        uint4 o;
+                        o.x = __float_as_uint(__uint_as_float(src[0]) + bias_s[c + q4 * 4 + 0]);
+                        o.y = __float_as_uint(__uint_as_float(src[1]) + bias_s[c + q4 * 4 + 1]);
+                        o.z = __float_as_uint(__uint_as_float(src[2]) + bias_s[c + q4 * 4 + 2]);
+                        o.w = __float_as_uint(__uint_as_float(src[3]) + bias_s[c + q4 * 4 + 3]);
+                        srow[q4 ^ (r_in & 7)] = o;
+                    }
+                    fence_async_proxy();
+                    epi_barrier();
+                    if (threadIdx.x == 0) {
+                        if (p.splits > 1)
+                            tma_reduce_add_2d(&map_y, staging, n0 + c, mt * BLOCK_M);
+                        else
+                            tma_store_2d(&map_y, staging, n0 + c, mt * BLOCK_M);
+                        bulk_commit();
+                    }
+                }
+            } else {
             float* yrow = p.y + (size_t)row * p.ldy + n0;
             for (int c = 0; c < p.block_n; c += 16) {
                 uint32_t r[16];
@@ -324,11 +410,14 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                 }
             }
+            }
             tc_fence_before();
             mbar_arrive(&bar_tmem_empty[as]);
+            if (threadIdx.x == 0) MPC_TRACE(3, tn_);
         }
     }
 
+    if (threadIdx.x == 0 && p.tma_out) bulk_wait0();  // staged results have left shared memory
     tc_fence_before();
     __syncthreads();
     if (warp == 9) {
@@ -372,6 +461,8 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     return r == CUDA_SUCCESS ? MPC_OK : MPC_ERR_INVALID;
 }
 
+static long long* g_trace = nullptr;  // debug only, see mpc_debug_trace_buffer
+
 static cudaError_t ensure_smem_optin() {
     static bool done = false;  // idempotent attribute; a benign race at worst sets it twice
     if (done) return cudaSuccess;
@@ -395,13 +486,16 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.M = (int)M;
     p.N = (int)N;
     p.K = (int)K;
+    // results leave through TMA when y rows are 16-byte aligned; the accumulator tile is then a multiple of 32 columns
+    const int tma_out = ((ldy & 3) == 0 && ((uintptr_t)y & 15u) == 0) ? 1 : 0;
     int bn = (int)(N < 256 ? N : 256);
-    bn = (bn + 15) & ~15;
+    bn = tma_out ? ((bn + 31) & ~31) : ((bn + 15) & ~15);
     p.block_n = bn;
     p.n_tiles = (int)ceil_div(N, bn);
     p.m_tiles = (int)ceil_div(M, BLOCK_M);
+    p.tma_out = tma_out;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
-    int stages = (222 * 1024) / stage_bytes;  // dynamic smem opt-in is 224 KB, 1 KB is alignment slack
+    int stages = (222 * 1024 - EPI_SMEM_BYTES) / stage_bytes;  // opt-in is 224 KB; 1 KB alignment slack
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
@@ -411,16 +505,22 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.mn_major = 0;
     p.splits = 1;
     p.k_chunks = (int)(K / BLOCK_K);
+    p.trace = g_trace;
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, x, M, K, ldx, BLOCK_M);
     if (rc) return rc;
     rc = make_map(&map_b, w, N, K, ldw, bn);
     if (rc) return rc;
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    CUtensorMap map_y = map_a;  // placeholder when results are stored directly
+    if (tma_out) {
+        rc = make_map(&map_y, y, M, N, ldy, BLOCK_M);  // box 32 columns x 128 rows, 128B swizzle
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + EPI_SMEM_BYTES + 1024;
     MPC_CUDA(ensure_smem_optin());
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
-    linear_3xtf32_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    linear_3xtf32_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, p);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }
@@ -453,7 +553,7 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     while (splits > 1 && (int)ceil_div(p.k_chunks, splits) * (splits - 1) >= p.k_chunks) --splits;
     p.splits = splits;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
-    int stages = (222 * 1024) / stage_bytes;
+    int stages = (222 * 1024 - EPI_SMEM_BYTES) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
@@ -461,6 +561,8 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     p.y = gw;
     p.ldy = (int)ldw;
     p.mn_major = 1;
+    p.tma_out = ((ldw & 3) == 0 && ((uintptr_t)gw & 15u) == 0) ? 1 : 0;
+    p.trace = g_trace;
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, gy, M, N, ldg, 32, true);  // dims {N, M}: inner = output index n, box 32 x 32
     if (rc) return rc;
@@ -473,11 +575,21 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
             MPC_CUDA(cudaMemset2DAsync(gw, (size_t)ldw * 4, 0, (size_t)K * 4, (size_t)N, st));
         }
     }
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    CUtensorMap map_y = map_a;
+    if (p.tma_out) {
+        rc = make_map(&map_y, gw, N, K, ldw, BLOCK_M);  // TMA reduce-add (or store) of 32 x 128 slabs
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + EPI_SMEM_BYTES + 1024;
     MPC_CUDA(ensure_smem_optin());
     const int items = tiles * splits;
     const int grid = items < kNumSMs ? items : kNumSMs;
-    linear_3xtf32_kernel<<<grid, THREADS, smem, st>>>(map_a, map_b, p);
+    linear_3xtf32_kernel<<<grid, THREADS, smem, st>>>(map_a, map_b, map_y, p);
     MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_debug_trace_buffer(void* device_buffer) {
+    mpc::tc::g_trace = static_cast<long long*>(device_buffer);
     return MPC_OK;
 }

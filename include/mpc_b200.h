@@ -146,17 +146,20 @@ int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t ldq, co
  *   wq,wk,wv [C,Cin] (nn.Linear layout), bq,bk,bv [C]; ctx_out [B,S,C].
  * Backward: grad_w* [C,Cin] and grad_b* [C] are ACCUMULATED (caller zero-fills); grad_feat [B,N,Cin] may
  * be NULL (coordinates are data in the reference's training scripts) else it is ACCUMULATED too.
+ * Optional fused residual projection (conv_res.linear of the same block, :515 -> :415): if wr [C,Cin] / br [C] are
+ * given, res_out [B,S,C] = Wr centre + br (pre-BatchNorm) is produced by the same kernel; the backward then takes
+ * grad_res [B,S,C] and accumulates grad_wr / grad_br (and the centre's share of grad_feat).  Pass NULL to skip.
  * ------------------------------------------------------------------------------------------------- */
 int mpc_attn_xyz_fwd_f32(const float* feat, const int64_t* center_idx, const int64_t* idx, const float* wq,
                          const float* bq, const float* wk, const float* bk, const float* wv, const float* bv,
-                         float* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
-                         mpc_stream_t stream);
+                         const float* wr, const float* br, float* ctx_out, float* res_out, int64_t B, int64_t S,
+                         int64_t N, int64_t K, int64_t Cin, int64_t C, mpc_stream_t stream);
 int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t* center_idx,
                          const int64_t* idx, const float* wq, const float* bq, const float* wk,
-                         const float* bk, const float* wv, const float* bv, float* grad_wq, float* grad_bq,
-                         float* grad_wk, float* grad_bk, float* grad_wv, float* grad_bv, float* grad_feat,
-                         int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
-                         mpc_stream_t stream);
+                         const float* bk, const float* wv, const float* bv, const float* wr, const float* grad_res,
+                         float* grad_wq, float* grad_bq, float* grad_wk, float* grad_bk, float* grad_wv,
+                         float* grad_bv, float* grad_wr, float* grad_br, float* grad_feat, int64_t B, int64_t S,
+                         int64_t N, int64_t K, int64_t Cin, int64_t C, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Shared-MLP block tail.  Replaces the BatchNorm1d-over-channels + LeakyReLU(0.2) of `Linear.forward`,
@@ -174,6 +177,9 @@ int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t
 int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float momentum, double* scratch, int64_t M, int64_t C,
                      mpc_stream_t stream);
+/* out[c] = sum over the M rows of y[:,c] (fp64 accumulation; scratch: 2*C+1 doubles).  The bias gradient of a
+ * projection that is not followed by BatchNorm (q / k / v of LocalTrans).  C/4 must be a power of two <= 256. */
+int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t M, int64_t C, mpc_stream_t stream);
 int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, const float* gamma,
                        const float* beta, float eps, float slope, float* out, int64_t M, int64_t C,
                        mpc_stream_t stream);
@@ -192,6 +198,10 @@ int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean,
  * ------------------------------------------------------------------------------------------------- */
 int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
                        int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+/* Input gradient of the same layer:  gx[M,K] = gy[M,N] w[N,K].  The weight matrix is consumed as stored (MN-major
+ * tensor-core operand), no transposed copy.  K % 32 == 0, ldg % 4 == 0. */
+int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t ldw, float* gx, int64_t ldx,
+                         int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
 /* Weight gradient of the same layer (what autograd derives for nn.Linear):  gw[N,K] = gy[M,N]^T x[M,K].
  * Same 3xTF32 tcgen05 pipeline with MN-major operand descriptors (no transposed copies), the reduction over the M
  * points split across the SMs and combined with red.global.add into gw (zero-filled by the call).  K % 32 == 0. */

@@ -21,26 +21,30 @@ static inline unsigned attn_grid(int64_t work_items, int threads) {
 }
 
 // One channel of the core.  e[j] holds q - k_j on entry.  Returns ctx; fills a[j] (softmax) and O = sum a.
+// rs = 1/sqrt(C).  Scaling and normalisation multiply by reciprocals (one IEEE division per channel instead of
+// 2K of them: the division sequence was ~half of the kernel's instructions); the result differs from the
+// reference's divide-by-sqrt(C) by at most 1 ulp per term, far inside the 1e-5 feature tolerance.
 template <int K>
-__device__ __forceinline__ float attn_channel(const float (&e)[K], const float (&v)[K], float sqrtc,
+__device__ __forceinline__ float attn_channel(const float (&e)[K], const float (&v)[K], float rs,
                                               float (&a)[K], float& O, int& jstar) {
     float s[K];
     float m = -__int_as_float(0x7f800000);
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        s[j] = __fdiv_rn(e[j], sqrtc);
+        s[j] = e[j] * rs;
         m = fmaxf(m, s[j]);
     }
     float Z = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        a[j] = expf(s[j] - m);
+        a[j] = __expf(s[j] - m);
         Z += a[j];
     }
+    const float rZ = __fdiv_rn(1.0f, Z);
     O = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        a[j] = __fdiv_rn(a[j], Z);
+        a[j] *= rZ;
         O += a[j];
     }
     float best = -__int_as_float(0x7f800000);
@@ -60,7 +64,7 @@ __device__ __forceinline__ float attn_channel(const float (&e)[K], const float (
 // and dv (for v_{jstar}).  ctx = (a_{j*} - sum_i a_i) * v_{j*}.
 template <int K>
 __device__ __forceinline__ void attn_channel_bwd(float g, const float (&a)[K], float O, int jstar,
-                                                 const float (&v)[K], float sqrtc, float (&de)[K], float& dv) {
+                                                 const float (&v)[K], float rs, float (&de)[K], float& dv) {
     float vstar = 0.f, astar = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j)
@@ -75,7 +79,7 @@ __device__ __forceinline__ void attn_channel_bwd(float g, const float (&a)[K], f
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         const float da = (j == jstar ? gv : 0.f) - gv;
-        de[j] = __fdiv_rn(a[j] * (da - dot), sqrtc);
+        de[j] = a[j] * (da - dot) * rs;
     }
 }
 
@@ -172,22 +176,24 @@ __global__ void __launch_bounds__(256)
 attn_xyz_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ cidx,
                     const int64_t* __restrict__ idx, const float* __restrict__ wq, const float* __restrict__ bq,
                     const float* __restrict__ wk, const float* __restrict__ bk, const float* __restrict__ wv,
-                    const float* __restrict__ bv, float* __restrict__ ctx, int64_t rows, int S, int N, int C,
+                    const float* __restrict__ bv, const float* __restrict__ wr, const float* __restrict__ br,
+                    float* __restrict__ ctx, float* __restrict__ res_out, int64_t rows, int S, int N, int C,
                     int cin_rt, float sqrtc) {
     const int cin = CIN > 0 ? CIN : cin_rt;
     constexpr int CM = CIN > 0 ? CIN : 16;
     const int Cb = C < 256 ? C : 256;  // channels per CTA; C > 256 is split along gridDim.y (C % 256 == 0)
     const int c = blockIdx.y * Cb + threadIdx.x % Cb;
     const int rpb = blockDim.x / Cb;
-    float Wq[CM], Wk[CM], Wv[CM];
+    float Wq[CM], Wk[CM], Wv[CM], Wr[CM];
 #pragma unroll
     for (int i = 0; i < CM; ++i)
         if (i < cin) {
             Wq[i] = wq[c * cin + i];
             Wk[i] = wk[c * cin + i];
             Wv[i] = wv[c * cin + i];
+            Wr[i] = wr ? wr[c * cin + i] : 0.f;
         }
-    const float Bq = bq[c], Bk = bk[c], Bv = bv[c];
+    const float Bq = bq[c], Bk = bk[c], Bv = bv[c], Br = wr ? br[c] : 0.f;
     for (int64_t row = (int64_t)blockIdx.x * rpb + threadIdx.x / Cb; row < rows; row += (int64_t)gridDim.x * rpb) {
         const int64_t b = row / S;
         const int cn = cidx ? clamp_index(__ldg(cidx + row), N) : (int)(row - b * S);
@@ -196,11 +202,15 @@ attn_xyz_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ 
 #pragma unroll
         for (int i = 0; i < CM; ++i)
             if (i < cin) cen[i] = __ldg(cp + i);
-        float qv = 0.f;
+        float qv = 0.f, rv = 0.f;
 #pragma unroll
         for (int i = 0; i < CM; ++i)
-            if (i < cin) qv = fmaf(cen[i], Wq[i], qv);
+            if (i < cin) {
+                qv = fmaf(cen[i], Wq[i], qv);
+                rv = fmaf(cen[i], Wr[i], rv);
+            }
         qv += Bq;
+        if (res_out) res_out[row * C + c] = rv + Br;  // conv_res.linear(centre), pre-BatchNorm
         float e[K], v[K], a[K], O;
         int js;
 #pragma unroll
@@ -227,8 +237,10 @@ attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ fe
                     const int64_t* __restrict__ cidx, const int64_t* __restrict__ idx,
                     const float* __restrict__ wq, const float* __restrict__ bq, const float* __restrict__ wk,
                     const float* __restrict__ bk, const float* __restrict__ wv, const float* __restrict__ bv,
+                    const float* __restrict__ wr, const float* __restrict__ gres,
                     float* __restrict__ gwq, float* __restrict__ gbq, float* __restrict__ gwk,
                     float* __restrict__ gbk, float* __restrict__ gwv, float* __restrict__ gbv,
+                    float* __restrict__ gwr, float* __restrict__ gbr,
                     float* __restrict__ gfeat, int64_t rows, int S, int N, int C, int cin_rt, float sqrtc) {
     const int cin = CIN > 0 ? CIN : cin_rt;
     constexpr int CM = CIN > 0 ? CIN : 16;
@@ -236,18 +248,19 @@ attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ fe
     const int c = blockIdx.y * Cb + threadIdx.x % Cb;
     const int rpb = blockDim.x / Cb;
     const bool warp_uniform_row = (C % 32) == 0;  // all 32 lanes of a warp work on the same centre row
-    float Wq[CM], Wk[CM], Wv[CM], GWq[CM], GWk[CM], GWv[CM];
+    float Wq[CM], Wk[CM], Wv[CM], Wr[CM], GWq[CM], GWk[CM], GWv[CM], GWr[CM];
 #pragma unroll
     for (int i = 0; i < CM; ++i) {
-        GWq[i] = GWk[i] = GWv[i] = 0.f;
+        GWq[i] = GWk[i] = GWv[i] = GWr[i] = 0.f;
         if (i < cin) {
             Wq[i] = wq[c * cin + i];
             Wk[i] = wk[c * cin + i];
             Wv[i] = wv[c * cin + i];
+            Wr[i] = gres ? wr[c * cin + i] : 0.f;
         }
     }
     const float Bq = bq[c], Bk = bk[c], Bv = bv[c];
-    float GBq = 0.f, GBk = 0.f, GBv = 0.f;
+    float GBq = 0.f, GBk = 0.f, GBv = 0.f, GBr = 0.f;
     for (int64_t row = (int64_t)blockIdx.x * rpb + threadIdx.x / Cb; row < rows; row += (int64_t)gridDim.x * rpb) {
         const int64_t b = row / S;
         const int cn = cidx ? clamp_index(__ldg(cidx + row), N) : (int)(row - b * S);
@@ -313,12 +326,15 @@ attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ fe
                 }
         }
         GBq += dq;
+        const float gr = gres ? __ldg(gres + row * C + c) : 0.f;  // grad of conv_res.linear(centre)
+        GBr += gr;
 #pragma unroll
         for (int i = 0; i < CM; ++i)
             if (i < cin) {
                 GWq[i] = fmaf(dq, cen[i], GWq[i]);
+                GWr[i] = fmaf(gr, cen[i], GWr[i]);
                 if (gfeat) {
-                    float gd = gcen[i] + dq * Wq[i];
+                    float gd = gcen[i] + dq * Wq[i] + gr * Wr[i];
                     if (warp_uniform_row) {
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) gd += __shfl_xor_sync(0xffffffffu, gd, o);
@@ -336,7 +352,9 @@ attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ fe
             red_add_f32(gwq + c * cin + i, GWq[i]);
             red_add_f32(gwk + c * cin + i, GWk[i]);
             red_add_f32(gwv + c * cin + i, GWv[i]);
+            if (gres) red_add_f32(gwr + c * cin + i, GWr[i]);
         }
+    if (gres) red_add_f32(gbr + c, GBr);
     red_add_f32(gbq + c, GBq);
     red_add_f32(gbk + c, GBk);
     red_add_f32(gbv + c, GBv);
@@ -372,7 +390,7 @@ MPC_API int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, 
     if (B == 0 || S == 0) return MPC_OK;
     const int CV = (int)(C / 4);
     const int64_t total = B * S * CV;
-    const float sqrtc = sqrtf((float)C);
+    const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
     MPC_DISPATCH_K(K, (attn_feat_fwd_kernel<KK><<<attn_grid(total, AT), AT, 0, st>>>(
                           q, ldq, kf, vf, ldkv, idx, ctx_out, (int)S, (int)N, CV, sqrtc, total)));
@@ -395,7 +413,7 @@ MPC_API int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t
     if (B == 0 || S == 0) return MPC_OK;
     const int CV = (int)(C / 4);
     const int64_t total = B * S * CV;
-    const float sqrtc = sqrtf((float)C);
+    const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
     MPC_DISPATCH_K(K, (attn_feat_bwd_kernel<KK><<<attn_grid(total, AT), AT, 0, st>>>(
                           grad_ctx, q, ldq, kf, vf, ldkv, idx, grad_q, ldgq, grad_kf, grad_vf, ldgkv, (int)S, (int)N,
@@ -406,9 +424,10 @@ MPC_API int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t
 
 MPC_API int mpc_attn_xyz_fwd_f32(const float* feat, const int64_t* center_idx, const int64_t* idx, const float* wq,
                                  const float* bq, const float* wk, const float* bk, const float* wv, const float* bv,
-                                 float* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
-                                 mpc_stream_t stream) {
+                                 const float* wr, const float* br, float* ctx_out, float* res_out, int64_t B,
+                                 int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C, mpc_stream_t stream) {
     if (!feat || !idx || !wq || !bq || !wk || !bk || !wv || !bv || !ctx_out) return MPC_ERR_INVALID;
+    if ((wr != nullptr) != (res_out != nullptr) || (wr != nullptr) != (br != nullptr)) return MPC_ERR_INVALID;
     if (B < 0 || S < 0 || N <= 0 || K <= 0 || Cin <= 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (!center_idx && S != N) return MPC_ERR_INVALID;
     if (K > KMAX || C > 1024 || Cin > 16) return MPC_ERR_UNSUPPORTED;
@@ -418,16 +437,16 @@ MPC_API int mpc_attn_xyz_fwd_f32(const float* feat, const int64_t* center_idx, c
     const int rpb = C >= 256 ? 1 : threads / (int)C;
     const int64_t rows = B * S;
     const dim3 grid(attn_grid(ceil_div(rows, rpb) * threads, threads), C > 256 ? (unsigned)(C / 256) : 1u);
-    const float sqrtc = sqrtf((float)C);
+    const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 3) {
         MPC_DISPATCH_K(K, (attn_xyz_fwd_kernel<KK, 3><<<grid, threads, 0, st>>>(
-                              feat, center_idx, idx, wq, bq, wk, bk, wv, bv, ctx_out, rows, (int)S, (int)N, (int)C, 3,
-                              sqrtc)));
+                              feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, br, ctx_out, res_out, rows, (int)S,
+                              (int)N, (int)C, 3, sqrtc)));
     } else {
         MPC_DISPATCH_K(K, (attn_xyz_fwd_kernel<KK, 0><<<grid, threads, 0, st>>>(
-                              feat, center_idx, idx, wq, bq, wk, bk, wv, bv, ctx_out, rows, (int)S, (int)N, (int)C,
-                              (int)Cin, sqrtc)));
+                              feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, br, ctx_out, res_out, rows, (int)S,
+                              (int)N, (int)C, (int)Cin, sqrtc)));
     }
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -435,11 +454,13 @@ MPC_API int mpc_attn_xyz_fwd_f32(const float* feat, const int64_t* center_idx, c
 
 MPC_API int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t* center_idx,
                                  const int64_t* idx, const float* wq, const float* bq, const float* wk,
-                                 const float* bk, const float* wv, const float* bv, float* grad_wq, float* grad_bq,
-                                 float* grad_wk, float* grad_bk, float* grad_wv, float* grad_bv, float* grad_feat,
+                                 const float* bk, const float* wv, const float* bv, const float* wr,
+                                 const float* grad_res, float* grad_wq, float* grad_bq, float* grad_wk, float* grad_bk,
+                                 float* grad_wv, float* grad_bv, float* grad_wr, float* grad_br, float* grad_feat,
                                  int64_t B, int64_t S, int64_t N, int64_t K, int64_t Cin, int64_t C,
                                  mpc_stream_t stream) {
     if (!grad_ctx || !feat || !idx || !wq || !bq || !wk || !bk || !wv || !bv) return MPC_ERR_INVALID;
+    if (grad_res && (!wr || !grad_wr || !grad_br)) return MPC_ERR_INVALID;
     if (!grad_wq || !grad_bq || !grad_wk || !grad_bk || !grad_wv || !grad_bv) return MPC_ERR_INVALID;
     if (B < 0 || S < 0 || N <= 0 || K <= 0 || Cin <= 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (!center_idx && S != N) return MPC_ERR_INVALID;
@@ -453,16 +474,18 @@ MPC_API int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const
     int64_t g = ceil_div(rows, rpb);
     const int64_t cap = (int64_t)kNumSMs * 4;
     const dim3 grid((unsigned)(g > cap ? cap : g), C > 256 ? (unsigned)(C / 256) : 1u);
-    const float sqrtc = sqrtf((float)C);
+    const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 3) {
         MPC_DISPATCH_K(K, (attn_xyz_bwd_kernel<KK, 3><<<grid, threads, 0, st>>>(
-                              grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, grad_wq, grad_bq, grad_wk,
-                              grad_bk, grad_wv, grad_bv, grad_feat, rows, (int)S, (int)N, (int)C, 3, sqrtc)));
+                              grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, grad_res, grad_wq, grad_bq,
+                              grad_wk, grad_bk, grad_wv, grad_bv, grad_wr, grad_br, grad_feat, rows, (int)S, (int)N,
+                              (int)C, 3, sqrtc)));
     } else {
         MPC_DISPATCH_K(K, (attn_xyz_bwd_kernel<KK, 0><<<grid, threads, 0, st>>>(
-                              grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, grad_wq, grad_bq, grad_wk,
-                              grad_bk, grad_wv, grad_bv, grad_feat, rows, (int)S, (int)N, (int)C, (int)Cin, sqrtc)));
+                              grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, grad_res, grad_wq, grad_bq,
+                              grad_wk, grad_bk, grad_wv, grad_bv, grad_wr, grad_br, grad_feat, rows, (int)S, (int)N,
+                              (int)C, (int)Cin, sqrtc)));
     }
     MPC_LAUNCH_CHECK();
     return MPC_OK;

@@ -109,6 +109,7 @@ __device__ __forceinline__ void finalize_channel(const double* s1, const double*
 }
 
 // MODE 0: (y, y*y) for the forward statistics.  MODE 1: (dz, dz*xhat) for the backward reductions.
+// MODE 2: plain column sums (bias gradient of a projection that is not followed by BatchNorm).
 template <int MODE>
 __global__ void __launch_bounds__(RT)
 col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, const float* __restrict__ mean,
@@ -137,6 +138,8 @@ col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, c
             a.x += yv.x; a.y += yv.y; a.z += yv.z; a.w += yv.w;
             b.x = fmaf(yv.x, yv.x, b.x); b.y = fmaf(yv.y, yv.y, b.y);
             b.z = fmaf(yv.z, yv.z, b.z); b.w = fmaf(yv.w, yv.w, b.w);
+        } else if (MODE == 2) {
+            a.x += yv.x; a.y += yv.y; a.z += yv.z; a.w += yv.w;
         } else {
 #define MPC_R(comp)                                                     \
     {                                                                   \
@@ -187,15 +190,19 @@ col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, c
             atomicAdd(s2 + c0 + i, Bv[i]);
         }
     }
-    if (MODE == 0) {  // last CTA done: finalise mean / var / running stats in the same launch
+    if (MODE == 0 || MODE == 2) {  // last CTA done: finalise in the same launch
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
         __syncthreads();
         if (last) {
             __threadfence();
-            for (int c = threadIdx.x; c < C; c += RT) finalize_channel(s1, s2, fin, M, C, c);
-            if (threadIdx.x == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+            if (MODE == 0) {
+                for (int c = threadIdx.x; c < C; c += RT) finalize_channel(s1, s2, fin, M, C, c);
+                if (threadIdx.x == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+            } else {
+                for (int c = threadIdx.x; c < C; c += RT) fin.stats[c] = (float)__ldcg(s1 + c);
+            }
         }
     }
 }
@@ -446,6 +453,21 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
                                                                   train, scratch, scratch + C, grad_y, grad_gamma,
                                                                   grad_beta, M, (int)C, total);
     }
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t M, int64_t C, mpc_stream_t stream) {
+    if (!y || !out || !scratch || M <= 0 || C <= 0) return MPC_ERR_INVALID;
+    if (!fast_cv(C) || !al16(y)) return MPC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * (size_t)C + 1), st));
+    const int CV = (int)(C / 4);
+    StatsFinal fin{out, nullptr, nullptr, nullptr, 0.f};
+    col_reduce_kernel<2><<<col_reduce_grid(M, CV), RT, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,
+                                                               scratch, scratch + C,
+                                                               reinterpret_cast<unsigned*>(scratch + 2 * C), fin, M, (int)C,
+                                                               CV);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

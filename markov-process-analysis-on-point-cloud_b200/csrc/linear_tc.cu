@@ -136,8 +136,9 @@ struct Params {
     const float* bias;  // may be null
     float* y;
     int ldy;
-    int mn_major;     // 0: y = x w^T (operands K-major).  1: y[i,j] += sum_r a[r,i] b[r,j] (operands MN-major)
-    int splits;       // reduction split across CTAs (mn_major only; results are reduced with red.global.add)
+    int a_mn, b_mn;   // operand layouts: 0 = K-major (reduction index contiguous), 1 = MN-major (output index
+                      // contiguous).  fwd: 0/0 (y = x w^T); dgrad: 0/1 (gx = gy w); wgrad: 1/1 (gw = gy^T x)
+    int splits;       // reduction split across CTAs (wgrad; partial results are combined with TMA reduce-add)
     int k_chunks;     // ceil(reduction length / 32)
     long long* trace; // debug: per-role clock64() timeline of CTA 0 (null in production)
     int tma_out;      // 1: results leave through a swizzled staging slab + TMA store / TMA reduce-add
@@ -214,12 +215,17 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     MPC_TRACE(0, tn_);
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&bar_full[s], A_TILE_BYTES + b_tile_bytes);
-                    if (!p.mn_major) {
+                    // K-major: one box of 32 reduction columns x rows.  MN-major: 4 KB boxes of 32 output
+                    // indices x 32 reduction rows.
+                    if (!p.a_mn) {
                         tma_load_2d(&map_a, &bar_full[s], st, kc * BLOCK_K, mt * BLOCK_M);
-                        tma_load_2d(&map_b, &bar_full[s], st + 2 * A_TILE_BYTES, kc * BLOCK_K, nt * p.block_n);
-                    } else {  // 4 KB boxes: 32 output indices x 32 reduction rows
+                    } else {
                         for (int a = 0; a < BLOCK_M / 32; ++a)
                             tma_load_2d(&map_a, &bar_full[s], st + a * 4096, mt * BLOCK_M + a * 32, kc * BLOCK_K);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(&map_b, &bar_full[s], st + 2 * A_TILE_BYTES, kc * BLOCK_K, nt * p.block_n);
+                    } else {
                         for (int b = 0; b < p.block_n / 32; ++b)
                             tma_load_2d(&map_b, &bar_full[s], st + 2 * A_TILE_BYTES + b * 4096, nt * p.block_n + b * 32,
                                         kc * BLOCK_K);
@@ -289,7 +295,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             // both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                                    ((uint32_t)(BLOCK_M >> 4) << 24) |
-                                   (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);  // a_major / b_major = MN
+                                   (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);  // a_major / b_major
             int it = 0, tile_it = 0, tn_ = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
                 const int as = tile_it & 1;
@@ -308,18 +314,19 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t o_alo = A_TILE_BYTES, o_bhi = 2 * A_TILE_BYTES, o_blo = 2 * A_TILE_BYTES + b_tile_bytes;
-                    const uint64_t a_hi = p.mn_major ? make_desc_mn(st) : make_desc(st);
-                    const uint64_t a_lo = p.mn_major ? make_desc_mn(st + o_alo) : make_desc(st + o_alo);
-                    const uint64_t b_hi = p.mn_major ? make_desc_mn(st + o_bhi) : make_desc(st + o_bhi);
-                    const uint64_t b_lo = p.mn_major ? make_desc_mn(st + o_blo) : make_desc(st + o_blo);
+                    const uint64_t a_hi = p.a_mn ? make_desc_mn(st) : make_desc(st);
+                    const uint64_t a_lo = p.a_mn ? make_desc_mn(st + o_alo) : make_desc(st + o_alo);
+                    const uint64_t b_hi = p.b_mn ? make_desc_mn(st + o_bhi) : make_desc(st + o_bhi);
+                    const uint64_t b_lo = p.b_mn ? make_desc_mn(st + o_blo) : make_desc(st + o_blo);
                     // K-major: +32 B inside the swizzle row per K step; MN-major: +1024 B (next 8 reduction rows)
-                    const uint64_t step = p.mn_major ? (1024u >> 4) : ((UMMA_K * 4) >> 4);
+                    const uint64_t step_a = p.a_mn ? (1024u >> 4) : ((UMMA_K * 4) >> 4);
+                    const uint64_t step_b = p.b_mn ? (1024u >> 4) : ((UMMA_K * 4) >> 4);
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                        const uint64_t adv = step * kk;
-                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kc != kc0 || kk != 0) ? 1u : 0u);
-                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                        const uint64_t ada = step_a * kk, adb = step_b * kk;
+                        umma_tf32(tmem_d, a_lo + ada, b_hi + adb, idesc, (kc != kc0 || kk != 0) ? 1u : 0u);
+                        umma_tf32(tmem_d, a_hi + ada, b_lo + adb, idesc, 1u);
+                        umma_tf32(tmem_d, a_hi + ada, b_hi + adb, idesc, 1u);
                     }
                     umma_commit(&bar_empty[s]);  // the stage may be refilled once these MMAs have read it
                 }
@@ -502,7 +509,8 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.bias = bias;
     p.y = y;
     p.ldy = (int)ldy;
-    p.mn_major = 0;
+    p.a_mn = 0;
+    p.b_mn = 0;
     p.splits = 1;
     p.k_chunks = (int)(K / BLOCK_K);
     p.trace = g_trace;
@@ -560,7 +568,8 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     p.bias = nullptr;
     p.y = gw;
     p.ldy = (int)ldw;
-    p.mn_major = 1;
+    p.a_mn = 1;
+    p.b_mn = 1;
     p.tma_out = ((ldw & 3) == 0 && ((uintptr_t)gw & 15u) == 0) ? 1 : 0;
     p.trace = g_trace;
     CUtensorMap map_a, map_b;
@@ -591,5 +600,56 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
 
 MPC_API int mpc_debug_trace_buffer(void* device_buffer) {
     mpc::tc::g_trace = static_cast<long long*>(device_buffer);
+    return MPC_OK;
+}
+
+// grad_x[M,K] = gy[M,N] w[N,K]: A = gy is K-major (the reduction index n is contiguous), B = w is MN-major (the
+// output index k is contiguous), so the weight matrix is consumed as stored -- no transposed copy.
+MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t ldw, float* gx, int64_t ldx,
+                                 int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+    using namespace mpc;
+    using namespace mpc::tc;
+    if (!gy || !w || !gx || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
+    if (K % 32 || ldg < N || ldw < K || ldx < K || (ldg & 3) || (ldw & 3)) return MPC_ERR_UNSUPPORTED;
+    if (((uintptr_t)gy | (uintptr_t)w) & 15u) return MPC_ERR_UNSUPPORTED;
+    if (M > INT32_MAX || N > 65536 || K > 65536) return MPC_ERR_UNSUPPORTED;
+    Params p;
+    p.M = (int)M;  // output rows
+    p.N = (int)K;  // output cols = layer input width
+    p.K = (int)N;  // reduction   = layer output width
+    const int bn = (int)(K < 256 ? K : 256);  // multiple of 32
+    p.block_n = bn;
+    p.n_tiles = (int)ceil_div(K, bn);
+    p.m_tiles = (int)ceil_div(M, BLOCK_M);
+    p.k_chunks = (int)ceil_div(N, BLOCK_K);
+    p.splits = 1;
+    p.tma_out = ((ldx & 3) == 0 && ((uintptr_t)gx & 15u) == 0) ? 1 : 0;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
+    int stages = (222 * 1024 - EPI_SMEM_BYTES) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return MPC_ERR_UNSUPPORTED;
+    p.stages = stages;
+    p.bias = nullptr;
+    p.y = gx;
+    p.ldy = (int)ldx;
+    p.a_mn = 0;
+    p.b_mn = 1;
+    p.trace = g_trace;
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, gy, M, N, ldg, BLOCK_M);        // K-major: box 32 reduction columns x 128 rows
+    if (rc) return rc;
+    rc = make_map(&map_b, w, N, K, ldw, 32, true);            // MN-major: box 32 output columns x 32 reduction rows
+    if (rc) return rc;
+    CUtensorMap map_y = map_a;
+    if (p.tma_out) {
+        rc = make_map(&map_y, gx, M, K, ldx, BLOCK_M);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + EPI_SMEM_BYTES + 1024;
+    MPC_CUDA(ensure_smem_optin());
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
+    linear_3xtf32_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, p);
+    MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

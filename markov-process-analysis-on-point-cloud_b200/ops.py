@@ -349,37 +349,50 @@ class AttnFeat(torch.autograd.Function):
 
 class AttnXyz(torch.autograd.Function):
     """LocalTrans core, coordinate branch (R/modules/pointnet2_utils.py:520-544) with the q/k/v projections
-    of the Cin-channel differences computed inside the kernel."""
+    of the Cin-channel differences computed inside the kernel.  If the residual projection's weights (wr, br =
+    conv_res.linear of the same block, :515) are given, the kernel also returns res = Wr centre + br (pre-BatchNorm),
+    so the 3-channel GEMM, its weight-gradient reduction over all points and its bias reduction never run as
+    separate library calls.  Returns (ctx, res or None)."""
 
     @staticmethod
-    def forward(ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv):
+    def forward(ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, br):
         B, N, Cin = feat.shape
         S, K = idx.shape[1], idx.shape[2]
         C = wq.shape[0]
         out = torch.empty(B, S, C, dtype=torch.float32, device=feat.device)
+        res = torch.empty(B, S, C, dtype=torch.float32, device=feat.device) if wr is not None else None
         call("mpc_attn_xyz_fwd_f32", ptr(feat), ptr(center_idx), ptr(idx), ptr(wq), ptr(bq), ptr(wk), ptr(bk),
-             ptr(wv), ptr(bv), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C),
-             algo_bytes=B * (N * Cin * 4 + S * K * 8 + S * C * 4) + 3 * C * (Cin + 1) * 4)
-        ctx.save_for_backward(feat, idx, wq, bq, wk, bk, wv, bv)
+             ptr(wv), ptr(bv), ptr(wr), ptr(br), ptr(out), ptr(res), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin),
+             _i64(C), algo_bytes=B * (N * Cin * 4 + S * K * 8 + S * C * 4 * (2 if wr is not None else 1))
+             + 4 * C * (Cin + 1) * 4)
+        ctx.save_for_backward(feat, idx, wq, bq, wk, bk, wv, bv, wr)
         ctx.center_idx = center_idx
-        return out
+        return out, res
 
     @staticmethod
-    def backward(ctx, grad_ctx):
-        feat, idx, wq, bq, wk, bk, wv, bv = ctx.saved_tensors
+    def backward(ctx, grad_ctx, grad_res):
+        feat, idx, wq, bq, wk, bk, wv, bv, wr = ctx.saved_tensors
         center_idx = ctx.center_idx
         B, N, Cin = feat.shape
         S, K = idx.shape[1], idx.shape[2]
         C = wq.shape[0]
-        grad_ctx = _f32c(grad_ctx)
-        gw = torch.zeros(3, C, Cin, dtype=torch.float32, device=feat.device)
-        gb = torch.zeros(3, C, dtype=torch.float32, device=feat.device)
+        dev = feat.device
+        grad_ctx = _f32c(grad_ctx) if grad_ctx is not None else torch.zeros(B, S, C, device=dev)
+        if wr is not None:
+            grad_res = _f32c(grad_res) if grad_res is not None else torch.zeros(B, S, C, device=dev)
+        else:
+            grad_res = None
+        gw = torch.zeros(4, C, Cin, dtype=torch.float32, device=dev)
+        gb = torch.zeros(4, C, dtype=torch.float32, device=dev)
         gfeat = torch.zeros_like(feat) if ctx.needs_input_grad[0] else None
         call("mpc_attn_xyz_bwd_f32", ptr(grad_ctx), ptr(feat), ptr(center_idx), ptr(idx), ptr(wq), ptr(bq), ptr(wk),
-             ptr(bk), ptr(wv), ptr(bv), ptr(gw[0]), ptr(gb[0]), ptr(gw[1]), ptr(gb[1]), ptr(gw[2]), ptr(gb[2]),
-             ptr(gfeat), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin), _i64(C),
-             algo_bytes=B * (N * Cin * 4 + S * K * 8 + S * C * 4) + 6 * C * (Cin + 1) * 4)
-        return gfeat, None, None, gw[0], gb[0], gw[1], gb[1], gw[2], gb[2]
+             ptr(bk), ptr(wv), ptr(bv), ptr(wr), ptr(grad_res), ptr(gw[0]), ptr(gb[0]), ptr(gw[1]), ptr(gb[1]),
+             ptr(gw[2]), ptr(gb[2]), ptr(gw[3]) if wr is not None else ptr(None),
+             ptr(gb[3]) if wr is not None else ptr(None), ptr(gfeat), _i64(B), _i64(S), _i64(N), _i64(K), _i64(Cin),
+             _i64(C), algo_bytes=B * (N * Cin * 4 + S * K * 8 + S * C * 4 * (2 if wr is not None else 1))
+             + 8 * C * (Cin + 1) * 4)
+        return (gfeat, None, None, gw[0], gb[0], gw[1], gb[1], gw[2], gb[2],
+                gw[3] if wr is not None else None, gb[3] if wr is not None else None)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -458,6 +471,19 @@ def _tc_gemm(x2d, w, bias, out):
          _i64(out.stride(0)), _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
 
 
+def _tc_dgrad(gy, w, x_like):
+    """grad_x[M,K] = gy[M,N] @ w[N,K] on the tensor cores (weights consumed as stored); library GEMM when the
+    shape is outside the kernel's reach."""
+    M, N = gy.shape
+    K = w.shape[1]
+    if _GEMM_IMPL == "tcgen05" and K % 32 == 0 and N % 4 == 0 and M > 0:
+        gx = torch.empty(M, K, dtype=torch.float32, device=gy.device)
+        call("mpc_linear_dgrad_f32", ptr(gy), _i64(gy.stride(0)), ptr(w), _i64(w.stride(0)), ptr(gx), _i64(K),
+             _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+        return gx
+    return gy.mm(w)
+
+
 class LinearTC(torch.autograd.Function):
     """y = x W^T + b.  Forward and grad-input run on the tcgen05 kernel (the two GEMMs whose large operand is
     the activation stream); grad-weight (a [N,M]x[M,K] reduction over all points) uses the library GEMM."""
@@ -478,12 +504,7 @@ class LinearTC(torch.autograd.Function):
         gy = _f32c(gy)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = w.t().contiguous()  # [K,N]: grad_x[M,K] = gy[M,N] @ wt[K,N]^T
-            if _tc_ok(gy, wt):
-                gx = torch.empty_like(x2d)
-                _tc_gemm(gy, wt, None, gx)
-            else:
-                gx = gy.mm(w)
+            gx = _tc_dgrad(gy, w, x2d)
         if ctx.needs_input_grad[1]:
             M, K = x2d.shape
             N = w.shape[0]
@@ -494,7 +515,14 @@ class LinearTC(torch.autograd.Function):
             else:
                 gw = gy.t().mm(x2d)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
+            M, N = gy.shape
+            cv = N // 4
+            if N % 4 == 0 and 1 <= cv <= 256 and (cv & (cv - 1)) == 0:
+                gb = torch.empty(N, dtype=torch.float32, device=gy.device)
+                scratch = torch.empty(2 * N + 1, dtype=torch.float64, device=gy.device)
+                call("mpc_col_sum_f32", ptr(gy), ptr(gb), ptr(scratch), _i64(M), _i64(N), algo_bytes=M * N * 4)
+            else:
+                gb = gy.sum(0)
         return gx, gw, gb
 
 
@@ -550,12 +578,7 @@ class LinearBNAct(torch.autograd.Function):
              ptr(gb), ptr(scratch), _i64(M), _i64(N), algo_bytes=3 * M * N * 4)
         gx = gw = gbias = None
         if ctx.needs_input_grad[0]:
-            wt = w.t().contiguous()
-            if _tc_ok(gy, wt):
-                gx = torch.empty_like(x2d)
-                _tc_gemm(gy, wt, None, gx)
-            else:
-                gx = gy.mm(w)
+            gx = _tc_dgrad(gy, w, x2d)
         if ctx.needs_input_grad[1]:
             if K % 32 == 0 and N % 4 == 0:
                 gw = torch.empty(N, K, dtype=torch.float32, device=dev)

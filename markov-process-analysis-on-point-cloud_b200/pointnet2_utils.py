@@ -64,18 +64,32 @@ class LocalTrans(nn.Module):
             # the reference's tanh branch (:535-537) multiplies [B,S,K,C] by [B,S,K,C] with matmul, which
             # cannot run for K != C; no shipped configuration enables it.
             raise NotImplementedError("LocalTrans(usetanh=True) is dead code in the reference")
+        if xyz is True:
+            # coordinate branch: q/k/v projections of the differences AND the residual projection
+            # conv_res.linear(centre) are computed inside one kernel; BatchNorm + LeakyReLU of conv_res follow
+            fused_res = self.residual is True and self.conv_res.bn_flag is not True
+            lin = self.conv_res.linear
+            context, res = ops.AttnXyz.apply(features.contiguous(),
+                                             FPS_idx.contiguous() if FPS_idx is not None else None,
+                                             idx.contiguous(), self.q.weight, self.q.bias, self.k.weight, self.k.bias,
+                                             self.v.weight, self.v.bias, lin.weight if fused_res else None,
+                                             lin.bias if fused_res else None)
+            if fused_res:
+                n = self.conv_res.norm2
+                shape = res.shape
+                residual = ops.bn_act(res.view(-1, shape[-1]), n.weight, n.bias, n.running_mean, n.running_var,
+                                      n.num_batches_tracked, self.training, momentum=n.momentum, eps=n.eps,
+                                      slope=0.2 if self.conv_res.act_flag is True else 1.0).view(shape)
+            else:
+                center = index_points(features, FPS_idx) if FPS_idx is not None else features
+                residual = self.conv_res(center) if self.residual is True else center
+            return residual + self.ffn(context)
         center = index_points(features, FPS_idx) if FPS_idx is not None else features
         residual = self.conv_res(center) if self.residual is True else center
-        if xyz is True:
-            context = ops.AttnXyz.apply(features.contiguous(),
-                                        FPS_idx.contiguous() if FPS_idx is not None else None,
-                                        idx.contiguous(), self.q.weight, self.q.bias, self.k.weight, self.k.bias,
-                                        self.v.weight, self.v.bias)
-        else:
-            q = ops.linear(center, self.q.weight, self.q.bias)
-            kv = ops.linear(features, torch.cat((self.k.weight, self.v.weight), 0),
-                            torch.cat((self.k.bias, self.v.bias), 0))
-            context = ops.AttnFeat.apply(q.contiguous(), kv.contiguous(), idx.contiguous())
+        q = ops.linear(center, self.q.weight, self.q.bias)
+        kv = ops.linear(features, torch.cat((self.k.weight, self.v.weight), 0),
+                        torch.cat((self.k.bias, self.v.bias), 0))
+        context = ops.AttnFeat.apply(q.contiguous(), kv.contiguous(), idx.contiguous())
         return residual + self.ffn(context)
 
 

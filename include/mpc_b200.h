@@ -127,6 +127,8 @@ int mpc_three_interpolate_bwd_f32(const float* grad_out, const float* weight, co
  *   column slices of one fused projection buffer); idx [B,S,K] i64; ctx_out [B,S,C] dense.
  * Backward recomputes the softmax: given grad_ctx [B,S,C] it writes grad_q [B,S,C] (stride ldgq) and
  * ACCUMULATES (red.global) into grad_kf / grad_vf [B,N,C] (stride ldgkv), which the caller zero-fills.
+ * grad_bias (optional, [3][C], ACCUMULATED) receives the column sums of grad_q / grad_k / grad_v, i.e. the bias
+ * gradients of the q / k / v projections, so no separate reduction over the points is needed.
  * C % 4 == 0, C <= 1024, K <= 32 (K = 8 is the specialised fast path).
  * ------------------------------------------------------------------------------------------------- */
 int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, const float* vf, int64_t ldkv,
@@ -134,8 +136,8 @@ int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, const fl
                           int64_t C, mpc_stream_t stream);
 int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t ldq, const float* kf,
                           const float* vf, int64_t ldkv, const int64_t* idx, float* grad_q, int64_t ldgq,
-                          float* grad_kf, float* grad_vf, int64_t ldgkv, int64_t B, int64_t S, int64_t N,
-                          int64_t K, int64_t C, mpc_stream_t stream);
+                          float* grad_kf, float* grad_vf, int64_t ldgkv, float* grad_bias, int64_t B, int64_t S,
+                          int64_t N, int64_t K, int64_t C, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Difference-wise attention core, coordinate branch.  Replaces LocalTrans.forward with xyz=True,
@@ -195,9 +197,16 @@ int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean,
  * tcgen05.mma kind::tf32 with the 3xTF32 operand split (hi/lo), fp32 accumulation in TMEM, TMA-fed: fp32-level
  * accuracy (the parity tolerance is rtol 1e-4).  Requires K % 32 == 0, ldx % 4 == ldw % 4 == 0, 16-byte aligned
  * x and w; other shapes return MPC_ERR_UNSUPPORTED and the host falls back to the library GEMM.
+ * stat_scratch (optional, 2*N+1 doubles, zero-filled by the call): the epilogue also accumulates the per-column sum
+ * and sum of squares of y over the M rows -- the BatchNorm batch statistics of the `Linear` block -- from the tile
+ * while it is still in shared memory; mpc_bn_finalize_f32 turns them into mean / variance / running statistics.
  * ------------------------------------------------------------------------------------------------- */
 int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
-                       int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+                       int64_t ldy, double* stat_scratch, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+/* stats[0:C] = mean, stats[C:2C] = biased variance from sums[0:C] = sum(y), sums[C:2C] = sum(y*y) over M rows;
+ * running statistics / num_batches_tracked updated like nn.BatchNorm1d when non-NULL. */
+int mpc_bn_finalize_f32(const double* sums, float* stats, float* running_mean, float* running_var,
+                        int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C, mpc_stream_t stream);
 /* Input gradient of the same layer:  gx[M,K] = gy[M,N] w[N,K].  The weight matrix is consumed as stored (MN-major
  * tensor-core operand), no transposed copy.  K % 32 == 0, ldg % 4 == 0. */
 int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t ldw, float* gx, int64_t ldx,

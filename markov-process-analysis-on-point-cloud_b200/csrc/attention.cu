@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(AT)
 attn_feat_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ q, int64_t ldq,
                      const float* __restrict__ kf, const float* __restrict__ vf, int64_t ldkv,
                      const int64_t* __restrict__ idx, float* __restrict__ gq, int64_t ldgq,
-                     float* __restrict__ gkf, float* __restrict__ gvf, int64_t ldgkv, int S, int N, int CV,
-                     float sqrtc, int64_t total) {
+                     float* __restrict__ gkf, float* __restrict__ gvf, int64_t ldgkv, float* __restrict__ gbias,
+                     int S, int N, int CV, float sqrtc, int64_t total) {
+    // column sums of grad_q / grad_k / grad_v (= the bias gradients of the three projections): AT % CV == 0, so a
+    // thread's channel group never changes across its grid-stride rows and the sums live in registers
+    float4 sq = make_float4(0.f, 0.f, 0.f, 0.f), sk = sq, sv = sq;
     for (int64_t t = (int64_t)blockIdx.x * AT + threadIdx.x; t < total; t += (int64_t)gridDim.x * AT) {
         const int64_t row = t / CV;
         const int c4 = (int)(t - row * CV) * 4;
@@ -155,6 +158,9 @@ attn_feat_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ q
         dq.comp += de[j];                                                                  \
         dk[j].comp = -de[j];                                                               \
     }                                                                                      \
+    sq.comp += dq.comp;                                                                    \
+    sk.comp -= dq.comp;                                                                    \
+    sv.comp += dv;                                                                         \
     {                                                                                      \
         int n = nb[0];                                                                     \
         _Pragma("unroll") for (int j = 1; j < K; ++j) n = (j == js) ? nb[j] : n;           \
@@ -165,6 +171,24 @@ attn_feat_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ q
         *reinterpret_cast<float4*>(gq + row * ldgq + c4) = dq;
 #pragma unroll
         for (int j = 0; j < K; ++j) red_add_f32x4(gkf + ((size_t)b * N + nb[j]) * ldgkv + c4, dk[j]);
+    }
+    if (gbias) {  // gbias [3][C]: q, k, v
+        __shared__ float4 red[3][AT];
+        red[0][threadIdx.x] = sq;
+        red[1][threadIdx.x] = sk;
+        red[2][threadIdx.x] = sv;
+        __syncthreads();
+        if (threadIdx.x < CV) {
+            const int C = CV * 4;
+            for (int w = 0; w < 3; ++w) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = threadIdx.x; i < AT; i += CV) {
+                    const float4 u = red[w][i];
+                    acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+                }
+                red_add_f32x4(gbias + w * C + threadIdx.x * 4, acc);
+            }
+        }
     }
 }
 
@@ -400,8 +424,8 @@ MPC_API int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, 
 
 MPC_API int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t ldq, const float* kf,
                                   const float* vf, int64_t ldkv, const int64_t* idx, float* grad_q, int64_t ldgq,
-                                  float* grad_kf, float* grad_vf, int64_t ldgkv, int64_t B, int64_t S, int64_t N,
-                                  int64_t K, int64_t C, mpc_stream_t stream) {
+                                  float* grad_kf, float* grad_vf, int64_t ldgkv, float* grad_bias, int64_t B, int64_t S,
+                                  int64_t N, int64_t K, int64_t C, mpc_stream_t stream) {
     if (!grad_ctx || !q || !kf || !vf || !idx || !grad_q || !grad_kf || !grad_vf) return MPC_ERR_INVALID;
     if (B < 0 || S < 0 || N <= 0 || K <= 0 || C <= 0 || C % 4 || ldq % 4 || ldkv % 4 || ldgq % 4 || ldgkv % 4)
         return MPC_ERR_INVALID;
@@ -410,14 +434,15 @@ MPC_API int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t
          (uintptr_t)grad_kf | (uintptr_t)grad_vf) & 15u)
         return MPC_ERR_INVALID;
     if (K > KMAX || C > 1024) return MPC_ERR_UNSUPPORTED;
+    if (grad_bias && (AT % (C / 4) != 0 || ((uintptr_t)grad_bias & 15u))) return MPC_ERR_UNSUPPORTED;
     if (B == 0 || S == 0) return MPC_OK;
     const int CV = (int)(C / 4);
     const int64_t total = B * S * CV;
     const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
     MPC_DISPATCH_K(K, (attn_feat_bwd_kernel<KK><<<attn_grid(total, AT), AT, 0, st>>>(
-                          grad_ctx, q, ldq, kf, vf, ldkv, idx, grad_q, ldgq, grad_kf, grad_vf, ldgkv, (int)S, (int)N,
-                          CV, sqrtc, total)));
+                          grad_ctx, q, ldq, kf, vf, ldkv, idx, grad_q, ldgq, grad_kf, grad_vf, ldgkv, grad_bias, (int)S,
+                          (int)N, CV, sqrtc, total)));
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

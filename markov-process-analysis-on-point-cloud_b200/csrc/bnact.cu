@@ -457,6 +457,16 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
     return MPC_OK;
 }
 
+MPC_API int mpc_bn_finalize_f32(const double* sums, float* stats, float* running_mean, float* running_var,
+                                int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C,
+                                mpc_stream_t stream) {
+    if (!sums || !stats || M <= 0 || C <= 0) return MPC_ERR_INVALID;
+    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+        sums, sums + C, stats, running_mean, running_var, num_batches_tracked, momentum, M, (int)C);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
 MPC_API int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t M, int64_t C, mpc_stream_t stream) {
     if (!y || !out || !scratch || M <= 0 || C <= 0) return MPC_ERR_INVALID;
     if (!fast_cv(C) || !al16(y)) return MPC_ERR_UNSUPPORTED;

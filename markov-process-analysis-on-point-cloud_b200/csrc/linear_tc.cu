@@ -142,6 +142,8 @@ struct Params {
     int k_chunks;     // ceil(reduction length / 32)
     long long* trace; // debug: per-role clock64() timeline of CTA 0 (null in production)
     int tma_out;      // 1: results leave through a swizzled staging slab + TMA store / TMA reduce-add
+    double* stat_sum; // optional [2][N]: per-column sum and sum of squares of y (BatchNorm batch statistics),
+                      // accumulated from the staged tile while it is still in shared memory
 };
 
 // debug timeline: role r in [0,4) records up to 255 timestamps
@@ -157,6 +159,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __shared__ uint64_t bar_full[MAX_STAGES], bar_split[MAX_STAGES], bar_empty[MAX_STAGES];
     __shared__ uint64_t bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float stat_red[2][4][32];
 
     // dynamic smem is requested with 1024 B of slack and aligned here (swizzle-128B atoms need 1024 B alignment)
     // (pointer arithmetic on the __shared__ array, not an integer round-trip, so accesses stay LDS/STS)
@@ -382,6 +385,33 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             tma_store_2d(&map_y, staging, n0 + c, mt * BLOCK_M);
                         bulk_commit();
                     }
+                    if (p.stat_sum) {
+                        // BatchNorm statistics of this slab straight from shared memory: lane = column, warp =
+                        // group of 32 rows (conflict-free: one 128-byte row per step), rows beyond M excluded
+                        const float* sf = reinterpret_cast<const float*>(staging);
+                        const int rows_valid = min(BLOCK_M, p.M - mt * BLOCK_M);
+                        float su = 0.f, sq2 = 0.f;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const int rr = warp * 32 + r;
+                            if (rr < rows_valid) {
+                                const float v = sf[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+                                su += v;
+                                sq2 = fmaf(v, v, sq2);
+                            }
+                        }
+                        stat_red[0][warp][lane] = su;
+                        stat_red[1][warp][lane] = sq2;
+                        epi_barrier();
+                        if (warp == 0 && n0 + c + lane < p.N) {
+                            const double a = (double)stat_red[0][0][lane] + (double)stat_red[0][1][lane] +
+                                             (double)stat_red[0][2][lane] + (double)stat_red[0][3][lane];
+                            const double b = (double)stat_red[1][0][lane] + (double)stat_red[1][1][lane] +
+                                             (double)stat_red[1][2][lane] + (double)stat_red[1][3][lane];
+                            atomicAdd(p.stat_sum + n0 + c + lane, a);
+                            atomicAdd(p.stat_sum + p.N + n0 + c + lane, b);
+                        }
+                    }
                 }
             } else {
             float* yrow = p.y + (size_t)row * p.ldy + n0;
@@ -482,7 +512,8 @@ static cudaError_t ensure_smem_optin() {
 }  // namespace mpc
 
 MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
-                               int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+                               int64_t ldy, double* stat_scratch, int64_t M, int64_t K, int64_t N,
+                               mpc_stream_t stream) {
     using namespace mpc;
     using namespace mpc::tc;
     if (!x || !w || !y || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
@@ -501,6 +532,11 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.n_tiles = (int)ceil_div(N, bn);
     p.m_tiles = (int)ceil_div(M, BLOCK_M);
     p.tma_out = tma_out;
+    p.stat_sum = stat_scratch;
+    if (stat_scratch) {
+        if (!tma_out) return MPC_ERR_UNSUPPORTED;
+        MPC_CUDA(cudaMemsetAsync(stat_scratch, 0, sizeof(double) * (2 * (size_t)N + 1), (cudaStream_t)stream));
+    }
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
     int stages = (222 * 1024 - EPI_SMEM_BYTES) / stage_bytes;  // opt-in is 224 KB; 1 KB alignment slack
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -570,6 +606,7 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     p.ldy = (int)ldw;
     p.a_mn = 1;
     p.b_mn = 1;
+    p.stat_sum = nullptr;
     p.tma_out = ((ldw & 3) == 0 && ((uintptr_t)gw & 15u) == 0) ? 1 : 0;
     p.trace = g_trace;
     CUtensorMap map_a, map_b;
@@ -634,6 +671,7 @@ MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, i
     p.ldy = (int)ldx;
     p.a_mn = 0;
     p.b_mn = 1;
+    p.stat_sum = nullptr;
     p.trace = g_trace;
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, gy, M, N, ldg, BLOCK_M);        // K-major: box 32 reduction columns x 128 rows

@@ -342,9 +342,71 @@ class AttnFeat(torch.autograd.Function):
         gkv = torch.zeros_like(kv)
         call("mpc_attn_feat_bwd_f32", ptr(grad_ctx), ptr(q), _i64(C), ptr(kv),
              ctypes.c_void_p(kv.data_ptr() + 4 * C), _i64(2 * C), ptr(idx), ptr(gq), _i64(C), ptr(gkv),
-             ctypes.c_void_p(gkv.data_ptr() + 4 * C), _i64(2 * C), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C),
-             algo_bytes=B * ((4 * N * C + 3 * S * C) * 4 + S * K * 8))
+             ctypes.c_void_p(gkv.data_ptr() + 4 * C), _i64(2 * C), ptr(None), _i64(B), _i64(S), _i64(N), _i64(K),
+             _i64(C), algo_bytes=B * ((4 * N * C + 3 * S * C) * 4 + S * K * 8))
         return gq, gkv, None
+
+
+def feat_attention_fusable(center, wq):
+    """FeatAttention needs the tensor-core GEMMs (Cin % 32 == 0) and a channel count the bias-sum path covers
+    (C/4 divides 256)."""
+    Cin, C = center.shape[-1], wq.shape[0]
+    return (_GEMM_IMPL == "tcgen05" and center.is_cuda and center.dtype == torch.float32 and Cin % 32 == 0
+            and C % 4 == 0 and 256 % (C // 4) == 0 and C <= 1024)
+
+
+class FeatAttention(torch.autograd.Function):
+    """One autograd node for the feature branch of LocalTrans (R/modules/pointnet2_utils.py:548-569): q projection
+    of the centres, fused k|v projection of all points (tcgen05 GEMMs), and the difference-wise attention core.
+    The backward's attention kernel also emits the three bias gradients (column sums of grad_q / grad_k / grad_v),
+    so nothing reduces over the points a second time."""
+
+    @staticmethod
+    def forward(ctx, center, features, idx, wq, bq, wk, bk, wv, bv):
+        B, S, Cin = center.shape
+        N = features.shape[1]
+        C = wq.shape[0]
+        K = idx.shape[2]
+        dev = center.device
+        c2d, f2d = center.reshape(-1, Cin), features.reshape(-1, Cin)
+        wkv = torch.cat((wk, wv), 0)
+        bkv = torch.cat((bk, bv), 0)
+        q = torch.empty(B * S, C, dtype=torch.float32, device=dev)
+        kv = torch.empty(B * N, 2 * C, dtype=torch.float32, device=dev)
+        _tc_gemm(c2d, wq, bq, q)
+        _tc_gemm(f2d, wkv, bkv, kv)
+        out = torch.empty(B, S, C, dtype=torch.float32, device=dev)
+        call("mpc_attn_feat_fwd_f32", ptr(q), _i64(C), ptr(kv), ctypes.c_void_p(kv.data_ptr() + 4 * C),
+             _i64(2 * C), ptr(idx), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C),
+             algo_bytes=B * ((2 * N * C + 2 * S * C) * 4 + S * K * 8))
+        ctx.save_for_backward(c2d, f2d, idx, wq, wkv, q, kv)
+        ctx.shapes = (B, S, N, Cin, C, K, center.data_ptr() == features.data_ptr() and S == N)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_ctx):
+        c2d, f2d, idx, wq, wkv, q, kv = ctx.saved_tensors
+        B, S, N, Cin, C, K, same = ctx.shapes
+        dev = q.device
+        grad_ctx = _f32c(grad_ctx)
+        gq = torch.empty_like(q)
+        gkv = torch.zeros_like(kv)
+        gbias = torch.zeros(3 * C, dtype=torch.float32, device=dev)
+        call("mpc_attn_feat_bwd_f32", ptr(grad_ctx), ptr(q), _i64(C), ptr(kv),
+             ctypes.c_void_p(kv.data_ptr() + 4 * C), _i64(2 * C), ptr(idx), ptr(gq), _i64(C), ptr(gkv),
+             ctypes.c_void_p(gkv.data_ptr() + 4 * C), _i64(2 * C), ptr(gbias), _i64(B), _i64(S), _i64(N), _i64(K),
+             _i64(C), algo_bytes=B * ((4 * N * C + 3 * S * C) * 4 + S * K * 8))
+        g_center = g_feat = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            g_center = _tc_dgrad(gq, wq, c2d).view(B, S, Cin)
+            g_feat = _tc_dgrad(gkv, wkv, f2d).view(B, N, Cin)
+        gwq = torch.empty(C, Cin, dtype=torch.float32, device=dev)
+        gwkv = torch.empty(2 * C, Cin, dtype=torch.float32, device=dev)
+        call("mpc_linear_wgrad_f32", ptr(gq), _i64(C), ptr(c2d), _i64(Cin), ptr(gwq), _i64(Cin), _i64(B * S),
+             _i64(Cin), _i64(C), algo_bytes=(B * S * (Cin + C) + C * Cin) * 4)
+        call("mpc_linear_wgrad_f32", ptr(gkv), _i64(2 * C), ptr(f2d), _i64(Cin), ptr(gwkv), _i64(Cin), _i64(B * N),
+             _i64(Cin), _i64(2 * C), algo_bytes=(B * N * (Cin + 2 * C) + 2 * C * Cin) * 4)
+        return (g_center, g_feat, None, gwq, gbias[:C], gwkv[:C], gbias[C:2 * C], gwkv[C:], gbias[2 * C:])
 
 
 class AttnXyz(torch.autograd.Function):
@@ -463,12 +525,14 @@ def _tc_ok(x2d, w):
             and x2d.shape[0] > 0)
 
 
-def _tc_gemm(x2d, w, bias, out):
-    """out[M,N] = x2d[M,K] @ w[N,K]^T (+ bias) through mpc_linear_fwd_f32 (3xTF32 tcgen05)."""
+def _tc_gemm(x2d, w, bias, out, stat_scratch=None):
+    """out[M,N] = x2d[M,K] @ w[N,K]^T (+ bias) through mpc_linear_fwd_f32 (3xTF32 tcgen05).  stat_scratch
+    (2N+1 doubles) additionally receives the per-column sum / sum of squares of `out` from the epilogue."""
     M, K = x2d.shape
     N = w.shape[0]
     call("mpc_linear_fwd_f32", ptr(x2d), _i64(x2d.stride(0)), ptr(w), _i64(w.stride(0)), ptr(bias), ptr(out),
-         _i64(out.stride(0)), _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+         _i64(out.stride(0)), ptr(stat_scratch), _i64(M), _i64(K), _i64(N),
+         algo_bytes=(M * K + M * N + N * K) * 4)
 
 
 def _tc_dgrad(gy, w, x_like):
@@ -541,18 +605,19 @@ class LinearBNAct(torch.autograd.Function):
         N = w.shape[0]
         dev = x2d.device
         y = torch.empty(M, N, dtype=torch.float32, device=dev)
-        _tc_gemm(x2d, w, bias, y)
         if training:
             if M <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s"
                                  % ((M, N),))
+            # batch statistics come out of the GEMM epilogue (the tile is summed while still in shared memory)
             scratch = torch.empty(2 * N + 1, dtype=torch.float64, device=dev)
             stats = torch.empty(2 * N, dtype=torch.float32, device=dev)
-            call("mpc_bn_stats_f32", ptr(y), ptr(stats), ptr(running_mean), ptr(running_var),
-                 ptr(num_batches_tracked), ctypes.c_float(momentum), ptr(scratch), _i64(M), _i64(N),
-                 algo_bytes=M * N * 4)
+            _tc_gemm(x2d, w, bias, y, stat_scratch=scratch)
+            call("mpc_bn_finalize_f32", ptr(scratch), ptr(stats), ptr(running_mean), ptr(running_var),
+                 ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M), _i64(N))
             mean, var = stats[:N], stats[N:]
         else:
+            _tc_gemm(x2d, w, bias, y)
             mean, var = running_mean, running_var
         out = torch.empty_like(y)
         call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),

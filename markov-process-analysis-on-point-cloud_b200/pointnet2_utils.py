@@ -86,10 +86,15 @@ class LocalTrans(nn.Module):
             return residual + self.ffn(context)
         center = index_points(features, FPS_idx) if FPS_idx is not None else features
         residual = self.conv_res(center) if self.residual is True else center
-        q = ops.linear(center, self.q.weight, self.q.bias)
-        kv = ops.linear(features, torch.cat((self.k.weight, self.v.weight), 0),
-                        torch.cat((self.k.bias, self.v.bias), 0))
-        context = ops.AttnFeat.apply(q.contiguous(), kv.contiguous(), idx.contiguous())
+        if ops.feat_attention_fusable(center, self.q.weight):
+            context = ops.FeatAttention.apply(center.contiguous(), features.contiguous(), idx.contiguous(),
+                                              self.q.weight, self.q.bias, self.k.weight, self.k.bias,
+                                              self.v.weight, self.v.bias)
+        else:
+            q = ops.linear(center, self.q.weight, self.q.bias)
+            kv = ops.linear(features, torch.cat((self.k.weight, self.v.weight), 0),
+                            torch.cat((self.k.bias, self.v.bias), 0))
+            context = ops.AttnFeat.apply(q.contiguous(), kv.contiguous(), idx.contiguous())
         return residual + self.ffn(context)
 
 

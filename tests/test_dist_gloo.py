@@ -1,0 +1,51 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2): batch sharding and the gradient exchange step."""
+import importlib
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+PKG = "markov-process-analysis-on-point-cloud_b200"
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mpc = importlib.import_module(PKG)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    unused = torch.nn.Linear(2, 2)  # never receives a gradient, like the reference's dead sub-modules
+    data = torch.arange(40, dtype=torch.float32).reshape(8, 5) / 10.0
+    lo, hi = mpc.dist.shard_batch(8, rank, world)
+    lin(data[lo:hi]).pow(2).sum().backward()
+    local = [p.grad.clone() for p in lin.parameters()]
+    n = mpc.dist.allreduce_mean_grads(list(lin.parameters()) + list(unused.parameters()), world)
+    torch.save({"n": n, "local": local, "avg": [p.grad.clone() for p in lin.parameters()], "shard": (lo, hi)},
+               os.path.join(out_dir, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_shard_batch_covers_everything(mpc):
+    for B in (1, 7, 8, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [mpc.dist.shard_batch(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_gradient_exchange_gloo_world2(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(str(tmp_path), "r%d.pt" % r)) for r in (0, 1))
+    assert r0["shard"] == (0, 4) and r1["shard"] == (4, 8)
+    assert r0["n"] == 2 and r1["n"] == 2  # the two parameters with a gradient; the unused module is skipped
+    for a0, a1, l0, l1 in zip(r0["avg"], r1["avg"], r0["local"], r1["local"]):
+        assert torch.equal(a0, a1)  # every rank ends with the same averaged gradient ...
+        torch.testing.assert_close(a0, (l0 + l1) / 2)  # ... the mean of the per-shard gradients

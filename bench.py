@@ -231,6 +231,26 @@ class GraphedStep:
         return self.loss
 
 
+# C-ABI entry point -> the CUDA kernel that does its work (the three GEMM entry points share one kernel)
+KERNEL_OF = {"mpc_linear_fwd_f32": "linear_3xtf32_kernel", "mpc_linear_dgrad_f32": "linear_3xtf32_kernel",
+             "mpc_linear_wgrad_f32": "linear_3xtf32_kernel"}
+
+
+def kernel_table(rows):
+    """Aggregate the per-entry-point table by kernel; returns [(kernel, entry points, calls, ms, bytes)] by time."""
+    agg = {}
+    for name, n, ms, by in rows:
+        k = KERNEL_OF.get(name, name)
+        e = agg.setdefault(k, [set(), 0, 0.0, 0])
+        e[0].add(name)
+        e[1] += n
+        e[2] += ms
+        e[3] += by
+    out = [(k, sorted(v[0]), v[1], v[2], v[3]) for k, v in agg.items()]
+    out.sort(key=lambda r: -r[3])
+    return out
+
+
 def op_table(records):
     rows = []
     for name, recs in records.items():
@@ -282,7 +302,7 @@ def run_own(args):
     full = op_table(mpc._lib.profiler["records"])
     instrumented_step_ms = ev0.elapsed_time(ev1)
     mpc._lib.profiler = None
-    dominant = full[0][0]
+    dominant_kernel, dominant_entries = kernel_table(full)[0][:2]
     if args.profile_ops and rank == 0:
         with open(args.profile_ops, "w") as f:
             f.write("# one instrumented step (%.3f ms incl. event overhead); per C-ABI entry point\n" % instrumented_step_ms)
@@ -292,12 +312,15 @@ def run_own(args):
             f.write("%-34s %6s %10.3f\n" % ("sum of ours", "", sum(r[2] for r in full)))
 
     # ---- eager, dominant op instrumented: per-launch CUDA events on the launching stream for the roofline
-    mpc._lib.profiler = {"names": {dominant}, "records": {}}
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    mpc._lib.profiler = {"names": set(dominant_entries), "records": {}}
     for _ in range(2):
         flush.zero_()
         step(xyz, label, target, device_starts())
     torch.cuda.synchronize()
-    dom = op_table(mpc._lib.profiler["records"])[0]
+    dom = kernel_table(op_table(mpc._lib.profiler["records"]))[0]
     dom_steps = 2
     mpc._lib.profiler = None
 
@@ -314,9 +337,6 @@ def run_own(args):
             run_step = step
 
     # ---- timed region: device-resident inputs, per-step events, L2 flush between steps (outside the events)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     kernels_per_step = sum(mpc._lib.KERNELS_PER_CALL[n] * c for n, c, _, _ in full)
     barrier()
     events = []
@@ -361,7 +381,7 @@ def run_own(args):
 
     if rank == 0:
         pk, pk_kind = peaks()
-        name, n_calls, ms, by = dom
+        name, entries, n_calls, ms, by = dom
         achieved = by / 1e9 / (ms / 1e3) if ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": clouds / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -376,7 +396,8 @@ def run_own(args):
             "e2e": {"value": clouds / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": name, "entry_points": entries, "achieved": achieved,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind + " (burst copy)",
                          "launches": n_calls, "avg_launch_us": 1e3 * ms / max(n_calls, 1),
                          "share_of_step": (ms / dom_steps) / (dev_ms / args.steps),

@@ -118,7 +118,7 @@ attn_feat_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __re
 }
 
 template <int K>
-__global__ void __launch_bounds__(AT)
+__global__ void __launch_bounds__(AT, 2)
 attn_feat_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ q, int64_t ldq,
                      const float* __restrict__ kf, const float* __restrict__ vf, int64_t ldkv,
                      const int64_t* __restrict__ idx, float* __restrict__ gq, int64_t ldgq,
@@ -256,7 +256,7 @@ attn_xyz_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ 
 }
 
 template <int K, int CIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ feat,
                     const int64_t* __restrict__ cidx, const int64_t* __restrict__ idx,
                     const float* __restrict__ wq, const float* __restrict__ bq, const float* __restrict__ wk,

@@ -271,6 +271,90 @@ bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, c
     }
 }
 
+// ---- fast elementwise paths: 1024 % C == 0, so with 256 threads x float4 a thread's 4 channels never change across
+// its grid-stride elements and every per-channel coefficient lives in registers (the generic kernels below
+// re-derive them -- rsqrt, divisions, fp64 -> fp32 -- for every element: ~300 instructions per float4).
+__global__ void __launch_bounds__(256)
+bn_act_fwd_fast_kernel(const float4* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ var,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
+                       float4* __restrict__ out, int C, int64_t total) {
+    const int c = (threadIdx.x * 4) % C;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 vr = __ldg(reinterpret_cast<const float4*>(var + c));
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 sc = make_float4(g.x * (1.0f / sqrtf(vr.x + eps)), g.y * (1.0f / sqrtf(vr.y + eps)),
+                                  g.z * (1.0f / sqrtf(vr.z + eps)), g.w * (1.0f / sqrtf(vr.w + eps)));
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    auto apply = [&](const float4& v) {
+        float4 o;
+        float z;
+        z = fmaf(v.x - mu.x, sc.x, be.x); o.x = z > 0.f ? z : z * slope;
+        z = fmaf(v.y - mu.y, sc.y, be.y); o.y = z > 0.f ? z : z * slope;
+        z = fmaf(v.z - mu.z, sc.z, be.z); o.z = z > 0.f ? z : z * slope;
+        z = fmaf(v.w - mu.w, sc.w, be.w); o.w = z > 0.f ? z : z * slope;
+        return o;
+    };
+    for (; t + 3 * stride < total; t += 4 * stride) {  // 4 independent 128-bit loads in flight
+        const float4 v0 = __ldg(y + t), v1 = __ldg(y + t + stride), v2 = __ldg(y + t + 2 * stride),
+                     v3 = __ldg(y + t + 3 * stride);
+        out[t] = apply(v0);
+        out[t + stride] = apply(v1);
+        out[t + 2 * stride] = apply(v2);
+        out[t + 3 * stride] = apply(v3);
+    }
+    for (; t < total; t += stride) out[t] = apply(__ldg(y + t));
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restrict__ y,
+                         const float* __restrict__ mean, const float* __restrict__ var,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
+                         int train, const double* __restrict__ s1, const double* __restrict__ s2,
+                         float4* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta, int64_t M,
+                         int C, int64_t total) {
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < C; i += 256) {
+            gbeta[i] = (float)s1[i];
+            ggamma[i] = (float)s2[i];
+        }
+    const int c = (threadIdx.x * 4) % C;
+    const float invM = train ? (float)(1.0 / (double)M) : 0.f;
+    float mu[4], is[4], g[4], be[4], c1[4], c2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        mu[i] = mean[c + i];
+        is[i] = 1.0f / sqrtf(var[c + i] + eps);
+        g[i] = gamma[c + i];
+        be[i] = beta[c + i];
+        c1[i] = invM * (float)s1[c + i];
+        c2[i] = invM * (float)s2[c + i];
+    }
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    auto apply = [&](const float4& yv, const float4& gv) {
+        const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float xh = (ya[i] - mu[i]) * is[i];
+            const float z = fmaf(xh, g[i], be[i]);
+            const float dz = z > 0.f ? ga[i] : ga[i] * slope;
+            o[i] = g[i] * is[i] * (dz - (c1[i] + xh * c2[i]));
+        }
+        return make_float4(o[0], o[1], o[2], o[3]);
+    };
+    for (; t + stride < total; t += 2 * stride) {  // 4 independent 128-bit loads in flight
+        const float4 y0 = __ldg(y + t), g0 = __ldg(gout + t), y1 = __ldg(y + t + stride), g1 = __ldg(gout + t + stride);
+        gy[t] = apply(y0, g0);
+        gy[t + stride] = apply(y1, g1);
+    }
+    for (; t < total; t += stride) gy[t] = apply(__ldg(y + t), __ldg(gout + t));
+}
+
+static inline bool fast_ew(int64_t C) { return C % 4 == 0 && C <= 1024 && 1024 % C == 0; }
+
 // backward pass A: per channel sum(dz) and sum(dz * xhat)
 template <bool VEC4>
 __global__ void __launch_bounds__(BN_TX* BN_TY)
@@ -411,7 +495,10 @@ MPC_API int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* v
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = C % 4 == 0 && al16(y) && al16(out) && al16(mean) && al16(var) && al16(gamma) && al16(beta);
     const int64_t total = M * (v4 ? C / 4 : C);
-    if (v4)
+    if (v4 && fast_ew(C))
+        bn_act_fwd_fast_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float4*>(y), mean, var, gamma, beta,
+                                                              eps, slope, reinterpret_cast<float4*>(out), (int)C, total);
+    else if (v4)
         bn_act_fwd_kernel<true><<<ew_grid(total), 256, 0, st>>>(y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
     else
         bn_act_fwd_kernel<false><<<ew_grid(total), 256, 0, st>>>(y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
@@ -442,9 +529,15 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
                                                                 scratch, scratch + C, M, (int)C);
         }
         MPC_LAUNCH_CHECK();
-        bn_bwd_apply_kernel<true><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, train,
-                                                                 scratch, scratch + C, grad_y, grad_gamma, grad_beta, M,
-                                                                 (int)C, total);
+        if (fast_ew(C))
+            bn_bwd_apply_fast_kernel<<<ew_grid(total), 256, 0, st>>>(
+                reinterpret_cast<const float4*>(grad_out), reinterpret_cast<const float4*>(y), mean, var, gamma, beta, eps,
+                slope, train, scratch, scratch + C, reinterpret_cast<float4*>(grad_y), grad_gamma, grad_beta, M, (int)C,
+                total);
+        else
+            bn_bwd_apply_kernel<true><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
+                                                                     train, scratch, scratch + C, grad_y, grad_gamma,
+                                                                     grad_beta, M, (int)C, total);
     } else {
         bn_bwd_sums_kernel<false><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, scratch,
                                                              scratch + C, M, (int)C);

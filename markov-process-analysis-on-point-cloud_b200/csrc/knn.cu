@@ -303,6 +303,151 @@ knn64_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float
     }
 }
 
+// ---- C == 64, two queries per thread ----------------------------------------------------------------------------
+// knn64_kernel is shared-memory-issue bound (one broadcast LDS.128 per 4 FFMA; ncu: 74% of the LSU shared
+// wavefront peak).  Holding TWO query vectors in registers halves the loads per FMA: per channel step a thread
+// issues 2 LDS.128 (8 reference points) and 16 FFMA.  CTAs are 64 threads (128 queries) so that the mid-sized
+// query sets still spread over every SM; used when that gives at least one CTA per SM.
+constexpr int KNN64X2_THREADS = 64;
+
+template <int K>
+__global__ void __launch_bounds__(KNN64X2_THREADS, 4)
+knn64x2_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
+               int64_t* __restrict__ idx_out, int N, int S) {
+    constexpr int C = 64, T = KNN64X2_THREADS;
+    __shared__ __align__(16) float rt[C * KNN64_LD];
+    __shared__ float rn[KNN64_TR];
+    __shared__ float qd[2][KNN_Q][T];
+    __shared__ int qi[2][KNN_Q][T];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int s0 = blockIdx.x * (2 * T) + tid, s1 = s0 + T;
+    const bool act0 = s0 < S, act1 = s1 < S;
+    const float* rb = ref + (size_t)b * N * C;
+    float q0[C], q1[C];
+    {
+        const float4* p0 = reinterpret_cast<const float4*>(qry + ((size_t)b * S + (act0 ? s0 : 0)) * C);
+        const float4* p1 = reinterpret_cast<const float4*>(qry + ((size_t)b * S + (act1 ? s1 : 0)) * C);
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) {
+            const float4 u = __ldg(p0 + c), v = __ldg(p1 + c);
+            q0[4 * c + 0] = u.x; q0[4 * c + 1] = u.y; q0[4 * c + 2] = u.z; q0[4 * c + 3] = u.w;
+            q1[4 * c + 0] = v.x; q1[4 * c + 1] = v.y; q1[4 * c + 2] = v.z; q1[4 * c + 3] = v.w;
+        }
+    }
+    float qn0 = __fmul_rn(q0[0], q0[0]), qn1 = __fmul_rn(q1[0], q1[0]);
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+        qn0 = __fadd_rn(qn0, __fmul_rn(q0[c], q0[c]));
+        qn1 = __fadd_rn(qn1, __fmul_rn(q1[c], q1[c]));
+    }
+    float bd0[K], bd1[K];
+    int bi0[K], bi1[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        bd0[k] = bd1[k] = __int_as_float(0x7f800000);
+        bi0[k] = bi1[k] = 0;
+    }
+    const float ninf = -__int_as_float(0x7f800000);
+    float thr0 = act0 ? -ninf : ninf, thr1 = act1 ? -ninf : ninf;
+    int cnt0 = 0, cnt1 = 0;
+    auto drain = [&](int which, int& cnt, float (&bd)[K], int (&bi)[K], float& thr) {
+        const int m = __reduce_max_sync(0xffffffffu, cnt);
+        for (int e = 0; e < m; ++e) {
+            if (e < cnt) {
+                const float d = qd[which][e][tid];
+                if (d < bd[K - 1]) topk_insert<K>(bd, bi, d, qi[which][e][tid]);
+            }
+        }
+        cnt = 0;
+        thr = bd[K - 1];
+    };
+    for (int t0 = 0; t0 < N; t0 += KNN64_TR) {
+        const int tn = min(KNN64_TR, N - t0);
+        __syncthreads();
+        for (int i = tid; i < KNN64_TR * (C / 4); i += T) {
+            const int j = i / (C / 4), c4 = (i - j * (C / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < tn) v = __ldg(reinterpret_cast<const float4*>(rb + (size_t)(t0 + j) * C + c4));
+            rt[(c4 + 0) * KNN64_LD + j] = v.x;
+            rt[(c4 + 1) * KNN64_LD + j] = v.y;
+            rt[(c4 + 2) * KNN64_LD + j] = v.z;
+            rt[(c4 + 3) * KNN64_LD + j] = v.w;
+        }
+        __syncthreads();
+        {
+            const int j = tid;  // T == KNN64_TR == 64: one reference norm per thread
+            float a = __fmul_rn(rt[j], rt[j]);
+#pragma unroll 8
+            for (int c = 1; c < C; ++c) {
+                const float v = rt[c * KNN64_LD + j];
+                a = __fadd_rn(a, __fmul_rn(v, v));
+            }
+            rn[j] = a;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int j0 = 0; j0 < KNN64_TR; j0 += 8) {
+            float a0[8], a1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a0[u] = a1[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float4 ra = *reinterpret_cast<const float4*>(rt + c * KNN64_LD + j0);
+                const float4 rb4 = *reinterpret_cast<const float4*>(rt + c * KNN64_LD + j0 + 4);
+                const float u = q0[c], v = q1[c];
+                a0[0] = __fmaf_rn(u, ra.x, a0[0]); a0[1] = __fmaf_rn(u, ra.y, a0[1]);
+                a0[2] = __fmaf_rn(u, ra.z, a0[2]); a0[3] = __fmaf_rn(u, ra.w, a0[3]);
+                a0[4] = __fmaf_rn(u, rb4.x, a0[4]); a0[5] = __fmaf_rn(u, rb4.y, a0[5]);
+                a0[6] = __fmaf_rn(u, rb4.z, a0[6]); a0[7] = __fmaf_rn(u, rb4.w, a0[7]);
+                a1[0] = __fmaf_rn(v, ra.x, a1[0]); a1[1] = __fmaf_rn(v, ra.y, a1[1]);
+                a1[2] = __fmaf_rn(v, ra.z, a1[2]); a1[3] = __fmaf_rn(v, ra.w, a1[3]);
+                a1[4] = __fmaf_rn(v, rb4.x, a1[4]); a1[5] = __fmaf_rn(v, rb4.y, a1[5]);
+                a1[6] = __fmaf_rn(v, rb4.z, a1[6]); a1[7] = __fmaf_rn(v, rb4.w, a1[7]);
+            }
+#pragma unroll
+            for (int u0 = 0; u0 < 8; u0 += 4) {
+#pragma unroll
+                for (int u = u0; u < u0 + 4; ++u) {
+                    const int j = j0 + u;
+                    const float d0 = sqdist_from_dot(a0[u], qn0, rn[j]);
+                    const float d1 = sqdist_from_dot(a1[u], qn1, rn[j]);
+                    if (j < tn && d0 < thr0) {
+                        qd[0][cnt0][tid] = d0;
+                        qi[0][cnt0][tid] = t0 + j;
+                        ++cnt0;
+                    }
+                    if (j < tn && d1 < thr1) {
+                        qd[1][cnt1][tid] = d1;
+                        qi[1][cnt1][tid] = t0 + j;
+                        ++cnt1;
+                    }
+                }
+                if (__any_sync(0xffffffffu, cnt0 > KNN_QFLUSH)) drain(0, cnt0, bd0, bi0, thr0);
+                if (__any_sync(0xffffffffu, cnt1 > KNN_QFLUSH)) drain(1, cnt1, bd1, bi1, thr1);
+            }
+        }
+    }
+    drain(0, cnt0, bd0, bi0, thr0);
+    drain(1, cnt1, bd1, bi1, thr1);
+    if (act0) {
+        const size_t o = ((size_t)b * S + s0) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (dist_out) dist_out[o + k] = bd0[k];
+            idx_out[o + k] = bi0[k];
+        }
+    }
+    if (act1) {
+        const size_t o = ((size_t)b * S + s1) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (dist_out) dist_out[o + k] = bd1[k];
+            idx_out[o + k] = bi1[k];
+        }
+    }
+}
+
 // ---- generic C ------------------------------------------------------------------------------------------------
 // CTA = 128 queries.  Queries live in shared memory [q][C+1]; reference tiles of 32 points are stored
 // transposed [c][32+4]; a thread advances 8 reference points at once.
@@ -430,6 +575,12 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
         return MPC_OK;
     }
     if (C == 64 && (reinterpret_cast<uintptr_t>(ref) & 15u) == 0 && (reinterpret_cast<uintptr_t>(qry) & 15u) == 0) {
+        if (K <= 16 && (int64_t)B * ceil_div(S, 2 * KNN64X2_THREADS) >= kNumSMs) {
+            dim3 grid2((unsigned)ceil_div(S, 2 * KNN64X2_THREADS), (unsigned)B);
+            knn64x2_kernel<(K <= 16 ? K : 16)><<<grid2, KNN64X2_THREADS, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+            MPC_LAUNCH_CHECK();
+            return MPC_OK;
+        }
         dim3 grid((unsigned)ceil_div(S, KNN_THREADS), (unsigned)B);
         knn64_kernel<K><<<grid, KNN_THREADS, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
         MPC_LAUNCH_CHECK();

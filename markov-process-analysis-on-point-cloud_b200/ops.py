@@ -687,6 +687,58 @@ def linear(x, weight, bias=None):
     return y.view(*shape[:-1], weight.shape[0])
 
 
+# ------------------------------------------------------------------------------------------------------
+# stream-level concurrency for independent branches
+# ------------------------------------------------------------------------------------------------------
+_STREAMS_ENABLED = os.environ.get("MPC_STREAMS", "1") == "1"
+_stream_pool = {}
+
+
+def _side_streams(device, n, avoid):
+    pool = _stream_pool.setdefault(device, [])
+    while len(pool) < 8:
+        pool.append(torch.cuda.Stream(device=device))
+    out = [st for st in pool if st != avoid]
+    return out[:n]
+
+
+def _tensors_of(obj):
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, (tuple, list)):
+        for o in obj:
+            yield from _tensors_of(o)
+
+
+def parallel(*thunks):
+    """Run independent branches concurrently: thunk 0 on the current stream, the others each on a side stream
+    forked from it and joined back before returning (under CUDA-graph capture these become parallel graph
+    branches).  The many small kernels of one Markov stage (three attention branches, the four source
+    projections of a Fuse) are each latency-bound on their own; side by side they fill the machine.  Autograd
+    runs every backward op on its forward op's stream, so the backward pass overlaps the same way.
+    Results are returned in thunk order.  MPC_STREAMS=0 runs them one after the other."""
+    if not _STREAMS_ENABLED or len(thunks) < 2 or not torch.cuda.is_available():
+        return [t() for t in thunks]
+    cur = torch.cuda.current_stream()
+    streams = _side_streams(cur.device, len(thunks) - 1, cur)
+    if len(streams) < len(thunks) - 1:
+        return [t() for t in thunks]
+    results = [None] * len(thunks)
+    for st in streams:
+        st.wait_stream(cur)
+    for i, st in enumerate(streams):
+        with torch.cuda.stream(st):
+            results[i + 1] = thunks[i + 1]()
+    results[0] = thunks[0]()
+    for st in streams:
+        cur.wait_stream(st)
+    for r in results[1:]:
+        for t in _tensors_of(r):
+            if t.is_cuda:
+                t.record_stream(cur)  # produced on a side stream, consumed (and later freed) on this one
+    return results
+
+
 def launches():
     """C-ABI calls issued so far in this process (each enqueues one or more of our kernels)."""
     return _lib.launch_count

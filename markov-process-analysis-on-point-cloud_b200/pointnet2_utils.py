@@ -117,11 +117,19 @@ class LocalMerge(nn.Module):
         if feature is None:
             merge_features = self.xyz_Trans(features=xyz, idx=idx, pos=base_xyz, FPS_idx=FPS_idx, xyz=True)
         else:
-            fs = index_points(feature, FPS_idx) if FPS_idx is not None else feature
-            _, idx_feature = knn_point(self.knn, feature, fs)
-            xyz_f = self.xyz_Trans(features=base_xyz, idx=idx, pos=base_xyz, FPS_idx=FPS_idx, xyz=True)
-            features1 = self.feature_Trans1(features=feature, idx=idx, pos=base_xyz, FPS_idx=FPS_idx)
-            features2 = self.feature_Trans2(features=feature, idx=idx_feature, pos=base_xyz, FPS_idx=FPS_idx)
+            # three independent branches (the feature-space kNN belongs to the third): run side by side
+            def branch_xyz():
+                return self.xyz_Trans(features=base_xyz, idx=idx, pos=base_xyz, FPS_idx=FPS_idx, xyz=True)
+
+            def branch_f1():
+                return self.feature_Trans1(features=feature, idx=idx, pos=base_xyz, FPS_idx=FPS_idx)
+
+            def branch_f2():
+                fs = index_points(feature, FPS_idx) if FPS_idx is not None else feature
+                _, idx_feature = knn_point(self.knn, feature, fs)
+                return self.feature_Trans2(features=feature, idx=idx_feature, pos=base_xyz, FPS_idx=FPS_idx)
+
+            features2, features1, xyz_f = ops.parallel(branch_f2, branch_f1, branch_xyz)
             merge_features = self.fc2(torch.cat((xyz_f, features1, features2), dim=2))
         if FPS_idx is not None and normal is not None:
             normal = index_points(normal, FPS_idx)
@@ -156,21 +164,28 @@ class Fuse(nn.Module):
             return f0, f1, f2, f3, f4  # the reference's `if num_point == ...` chain falls through unchanged
         t = targets[0]
         n_t = f[t].shape[1]
+
+        def source(j):
+            def run():
+                if j < t:  # finer state -> target through the composed FPS indices (:617-632)
+                    comp = fps[t - 1]
+                    for m in range(t - 2, j - 1, -1):
+                        comp = index_points(fps[m].unsqueeze(-1), comp).squeeze(-1)
+                    src = index_points(f[j], comp)
+                elif j == t + 1:  # adjacent coarser state: reuse the encoder's kNN (:650,663,678,693)
+                    src = upsample(f[j], knn_enc[j], n_out=n_t)
+                else:  # non-adjacent coarser state: fresh coordinate kNN (:667,681,685,696,700,704)
+                    _, kidx = knn_point(self.knn, xyzs[t], xyzs[j])
+                    src = upsample(f[j], kidx, n_out=n_t)
+                return getattr(self, "conv%d%d" % (j, t))(src)
+            return run
+
+        # the four source states are independent of each other: transition / gather + projection side by side;
+        # the sum keeps the reference's order f_t + f_0t + f_1t + ... (ascending source state)
+        parts = ops.parallel(*[source(j) for j in range(5) if j != t])
         acc = f[t]
-        for j in range(5):
-            if j == t:
-                continue
-            if j < t:  # finer state -> target through the composed FPS indices (:617-632)
-                comp = fps[t - 1]
-                for m in range(t - 2, j - 1, -1):
-                    comp = index_points(fps[m].unsqueeze(-1), comp).squeeze(-1)
-                src = index_points(f[j], comp)
-            elif j == t + 1:  # adjacent coarser state: reuse the encoder's kNN (:650,663,678,693)
-                src = upsample(f[j], knn_enc[j], n_out=n_t)
-            else:  # non-adjacent coarser state: fresh coordinate kNN (:667,681,685,696,700,704)
-                _, kidx = knn_point(self.knn, xyzs[t], xyzs[j])
-                src = upsample(f[j], kidx, n_out=n_t)
-            acc = acc + getattr(self, "conv%d%d" % (j, t))(src)
+        for part in parts:
+            acc = acc + part
         f[t] = getattr(self, "conv%d" % t)(acc) + f[t]
         return tuple(f)
 

@@ -720,7 +720,8 @@ def parallel(*thunks):
     if not _STREAMS_ENABLED or len(thunks) < 2 or not torch.cuda.is_available():
         return [t() for t in thunks]
     cur = torch.cuda.current_stream()
-    streams = _side_streams(cur.device, len(thunks) - 1, cur)
+    streams = [st for st in _side_streams(cur.device, 8, cur)[:-1]
+               if _geo is None or st != _geo.stream][:len(thunks) - 1]
     if len(streams) < len(thunks) - 1:
         return [t() for t in thunks]
     results = [None] * len(thunks)
@@ -737,6 +738,56 @@ def parallel(*thunks):
             if t.is_cuda:
                 t.record_stream(cur)  # produced on a side stream, consumed (and later freed) on this one
     return results
+
+
+class _GeoScope:
+    """Coordinate-only work (FPS, coordinate-space kNN, coordinate gathers) depends on nothing but the input
+    cloud, so it runs on its own stream, in program order, ahead of the feature pipeline that consumes it."""
+
+    def __init__(self):
+        cur = torch.cuda.current_stream()
+        self.stream = _side_streams(cur.device, 8, cur)[-1]  # the last pool stream: never handed to parallel()
+        self.stream.wait_stream(cur)  # fork: everything issued so far (the input cloud) is visible
+
+    def call(self, fn):
+        with torch.cuda.stream(self.stream):
+            out = fn()
+        return out
+
+    def join(self, outputs=None):
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.stream)
+        for t in _tensors_of(outputs):
+            if t.is_cuda:
+                t.record_stream(cur)
+
+
+_geo = None
+
+
+@contextlib.contextmanager
+def geometry_scope():
+    """Inside this scope geo_call() runs its thunk on the geometry stream; geo_join() makes the current stream
+    wait for everything issued there so far.  Outside a scope (or with MPC_STREAMS=0) both are no-ops."""
+    global _geo
+    old = _geo
+    _geo = _GeoScope() if (_STREAMS_ENABLED and torch.cuda.is_available()) else None
+    try:
+        yield
+    finally:
+        if _geo is not None:
+            torch.cuda.current_stream().wait_stream(_geo.stream)
+        _geo = old
+
+
+def geo_call(fn):
+    return _geo.call(fn) if _geo is not None else fn()
+
+
+def geo_join(outputs=None):
+    if _geo is not None:
+        _geo.join(outputs)
+    return outputs
 
 
 def launches():

@@ -113,7 +113,8 @@ class LocalMerge(nn.Module):
         self.feature_Trans2 = LocalTrans(in_channels, out_channels, knn, usetanh=self.usetanh, residual=self.residual)
 
     def forward(self, xyz, base_xyz, normal=None, feature=None, FPS_idx=None, xyz_flag=True):
-        dist, idx = knn_point(self.knn, base_xyz, xyz)
+        # coordinate-space neighbour search: geometry stream (it only depends on the cloud), joined here
+        dist, idx = ops.geo_join(ops.geo_call(lambda: knn_point(self.knn, base_xyz, xyz)))
         if feature is None:
             merge_features = self.xyz_Trans(features=xyz, idx=idx, pos=base_xyz, FPS_idx=FPS_idx, xyz=True)
         else:
@@ -175,7 +176,7 @@ class Fuse(nn.Module):
                 elif j == t + 1:  # adjacent coarser state: reuse the encoder's kNN (:650,663,678,693)
                     src = upsample(f[j], knn_enc[j], n_out=n_t)
                 else:  # non-adjacent coarser state: fresh coordinate kNN (:667,681,685,696,700,704)
-                    _, kidx = knn_point(self.knn, xyzs[t], xyzs[j])
+                    _, kidx = ops.geo_join(ops.geo_call(lambda: knn_point(self.knn, xyzs[t], xyzs[j])))
                     src = upsample(f[j], kidx, n_out=n_t)
                 return getattr(self, "conv%d%d" % (j, t))(src)
             return run
@@ -227,21 +228,30 @@ class KeepHighResolutionModulePartSeg(nn.Module):
     def forward(self, xyz, normal, label):
         xyz = xyz.permute(0, 2, 1).contiguous()
         normal = normal.permute(0, 2, 1).contiguous()
+        with ops.geometry_scope():
+            return self._forward(xyz, normal, label)
+
+    @staticmethod
+    def _sample(points, npoint):
+        """FPS + gather of the sampled coordinates, issued on the geometry stream (joined by the consumer's
+        coordinate kNN, which follows it on that stream)."""
+        def run():
+            idx = farthest_point_sample(points, npoint)
+            return idx, index_points(points, idx)
+        return ops.geo_call(run)
+
+    def _forward(self, xyz, normal, label):
         N = xyz.shape[1]
         n = [N, N // 2, N // 4, N // 8, N // 16]
         # encoder (:765-791)
         e0, nrm0, knn0, dist0 = self.la0(xyz=xyz, base_xyz=xyz, normal=normal, xyz_flag=True)
-        F0 = farthest_point_sample(xyz, n[1])
-        x1 = index_points(xyz, F0)
+        F0, x1 = self._sample(xyz, n[1])
         e1, nrm1, knn1, dist1 = self.la1(xyz=x1, base_xyz=xyz, normal=nrm0, feature=e0, FPS_idx=F0, xyz_flag=True)
-        F1 = farthest_point_sample(x1, n[2])
-        x2 = index_points(x1, F1)
+        F1, x2 = self._sample(x1, n[2])
         e2, nrm2, knn2, dist2 = self.la2(xyz=x2, base_xyz=x1, normal=nrm1, feature=e1, FPS_idx=F1, xyz_flag=False)
-        F2 = farthest_point_sample(x2, n[3])
-        x3 = index_points(x2, F2)
+        F2, x3 = self._sample(x2, n[3])
         e3, nrm3, knn3, dist3 = self.la3(xyz=x3, base_xyz=x2, normal=nrm2, feature=e2, FPS_idx=F2, xyz_flag=True)
-        F3 = farthest_point_sample(x3, n[4])
-        x4 = index_points(x3, F3)
+        F3, x4 = self._sample(x3, n[4])
         e4, nrm4, knn4, dist4 = self.la4(xyz=x4, base_xyz=x3, normal=nrm3, feature=e3, FPS_idx=F3, xyz_flag=False)
         kw = dict(FPS_0=F0, FPS_1=F1, FPS_2=F2, FPS_3=F3, knn_0=knn0, knn_1=knn1, knn_2=knn2, knn_3=knn3,
                   knn_4=knn4, xyz0=xyz, xyz1=x1, xyz2=x2, xyz3=x3, xyz4=x4)

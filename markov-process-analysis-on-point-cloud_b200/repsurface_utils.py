@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .ops import farthest_point_sample, index_points, knn_point, query_knn_point, square_distance  # noqa: F401
 from .pointnet2_utils import Linear, LocalTrans
 
@@ -29,14 +30,19 @@ class LocalMerge(nn.Module):
         self.feature_Trans2 = LocalTrans(in_channels, out_channels, knn, usetanh=self.usetanh, residual=self.residual)
 
     def forward(self, xyz, base_xyz, normal=None, feature=None, FPS_idx=None, xyz_flag=True):
-        dist, idx = knn_point(self.knn, base_xyz, xyz)
+        dist, idx = ops.geo_join(ops.geo_call(lambda: knn_point(self.knn, base_xyz, xyz)))
         if feature is None:
             merge_features = self.xyz_Trans(features=xyz, idx=idx, pos=base_xyz, FPS_idx=FPS_idx, xyz=True)
         else:
-            fs = index_points(feature, FPS_idx) if FPS_idx is not None else feature
-            _, idx_feature = knn_point(self.knn, feature, fs)
-            a = self.feature_Trans(features=feature, idx=idx, pos=base_xyz, FPS_idx=FPS_idx)
-            b = self.feature_Trans2(features=feature, idx=idx_feature, pos=base_xyz, FPS_idx=FPS_idx)
+            def branch_a():
+                return self.feature_Trans(features=feature, idx=idx, pos=base_xyz, FPS_idx=FPS_idx)
+
+            def branch_b():
+                fs = index_points(feature, FPS_idx) if FPS_idx is not None else feature
+                _, idx_feature = knn_point(self.knn, feature, fs)
+                return self.feature_Trans2(features=feature, idx=idx_feature, pos=base_xyz, FPS_idx=FPS_idx)
+
+            b, a = ops.parallel(branch_b, branch_a)  # two independent branches side by side
             merge_features = self.fc2(torch.cat((a, b), dim=2))
         return merge_features, normal, idx, dist
 
@@ -69,14 +75,17 @@ class KeepHighResolutionModule(nn.Module):
     def forward(self, xyz, normal):
         xyz = xyz.permute(0, 2, 1).contiguous()
         normal = normal.permute(0, 2, 1).contiguous()
-        feat, normal, _, _ = self.la0(xyz=xyz, base_xyz=xyz, normal=normal, xyz_flag=True)
-        base = xyz
-        for name, npoint in self.STAGES:
-            fps_idx = farthest_point_sample(base, npoint)
-            sub = index_points(base, fps_idx)
-            feat, normal, _, _ = getattr(self, name)(xyz=sub, base_xyz=base, normal=normal, feature=feat,
-                                                    FPS_idx=fps_idx)
-            base = sub
+        with ops.geometry_scope():  # FPS / coordinate kNN run ahead on the geometry stream
+            feat, normal, _, _ = self.la0(xyz=xyz, base_xyz=xyz, normal=normal, xyz_flag=True)
+            base = xyz
+            for name, npoint in self.STAGES:
+                def sample(points=base, npoint=npoint):
+                    idx = farthest_point_sample(points, npoint)
+                    return idx, index_points(points, idx)
+                fps_idx, sub = ops.geo_call(sample)
+                feat, normal, _, _ = getattr(self, name)(xyz=sub, base_xyz=base, normal=normal, feature=feat,
+                                                        FPS_idx=fps_idx)
+                base = sub
         final = self.conv4(self.conv3(feat))  # [B,32,1024]
         pooled = torch.cat((final.max(dim=1)[0], final.mean(dim=1)), 1)  # adaptive max / avg pool (:632-634)
         return self.lrelu(self.bn(self.final_class(pooled)))

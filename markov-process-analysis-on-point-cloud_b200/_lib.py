@@ -60,6 +60,8 @@ _lib = None
 launch_count = 0   # C-ABI calls that enqueued GPU work
 kernel_count = 0   # kernels of ours those calls launched (bench.py reports it as gpu_launches)
 # Optional per-op device timing for bench.py: {"names": set or None (= all), "records": {name: [(ev0, ev1, bytes)]}}
+# With "calls": [] instead of "records", the matching calls are only logged as (name, args, bytes) so that bench.py
+# can re-issue exactly the same launches back to back inside a CUDA graph (pure device time, no host gaps).
 profiler = None
 
 
@@ -98,6 +100,9 @@ def call(name, *args, algo_bytes=0):
     lib = load()
     prof = profiler
     timed = prof is not None and (prof["names"] is None or name in prof["names"])
+    if timed and "calls" in prof:
+        prof["calls"].append((name, args, algo_bytes))
+        timed = False
     if timed:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -110,6 +115,15 @@ def call(name, *args, algo_bytes=0):
         prof["records"].setdefault(name, []).append((ev0, ev1, algo_bytes))
     launch_count += 1
     kernel_count += KERNELS_PER_CALL[name]
+
+
+def replay(calls):
+    """Re-issue logged calls on the current stream (used under CUDA-graph capture by bench.py)."""
+    lib = load()
+    for name, args, _ in calls:
+        rc = getattr(lib, name)(*args, stream_ptr())
+        if rc != 0:
+            raise MpcError("%s failed on replay: %d" % (name, rc))
 
 
 def require_cuda(*tensors):

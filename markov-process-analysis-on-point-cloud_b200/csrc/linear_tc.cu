@@ -21,6 +21,8 @@
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mpc {
@@ -480,10 +482,42 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D fp32 row-major [rows, cols] (row stride ld floats), box = 32 columns x box_rows rows, 128B swizzle, zero fill
+// 2D fp32 row-major [rows, cols] (row stride ld floats), box = 32 columns x box_rows rows, 128B swizzle, zero fill.
+// Encoding a tensor map costs a few microseconds of host time; layers are called with the same buffers step after
+// step (the caching allocator hands the same addresses back), so encoded maps are kept in a small direct-mapped
+// cache keyed by everything that goes into the encoding.
+struct MapKey {
+    const void* base;
+    int64_t rows, cols, ld;
+    int box_rows, mn;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && mn == o.mn;
+    }
+};
+struct MapSlot {
+    MapKey key;
+    CUtensorMap map;
+    bool valid;
+};
+constexpr int MAP_CACHE_SLOTS = 1024;
+static MapSlot g_map_cache[MAP_CACHE_SLOTS];
+static std::mutex g_map_mutex;
+
 static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                     bool mn_major = false) {
     if (((uintptr_t)base & 15u) || (ld & 3)) return MPC_ERR_UNSUPPORTED;
+    const MapKey key{base, rows, cols, ld, box_rows, mn_major ? 1 : 0};
+    uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+    h ^= (uint64_t)rows * 0xC2B2AE3D27D4EB4Full + (uint64_t)cols * 0x165667B19E3779F9ull + (uint64_t)ld * 31 +
+         (uint64_t)box_rows * 7 + (uint64_t)key.mn;
+    MapSlot& slot = g_map_cache[(h >> 20) % MAP_CACHE_SLOTS];
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        if (slot.valid && slot.key == key) {
+            *map = slot.map;
+            return MPC_OK;
+        }
+    }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return MPC_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -493,9 +527,13 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? MPC_OK : MPC_ERR_INVALID;
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    slot.key = key;
+    slot.map = *map;
+    slot.valid = true;
+    return MPC_OK;
 }
 
 static long long* g_trace = nullptr;  // debug only, see mpc_debug_trace_buffer

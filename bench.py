@@ -251,6 +251,45 @@ def kernel_table(rows):
     return out
 
 
+def rebind_gemm_calls(mpc, calls, device):
+    """The logged launches point at activations that die with their step; give every logged GEMM launch fresh
+    buffers of the same shapes (random contents) so that the launch mix can be replayed on its own."""
+    import ctypes
+
+    def val(a):
+        return a.value if a.value is not None else 0
+
+    def buf(rows, ld):
+        return torch.randn(max(int(rows), 1), int(ld), dtype=torch.float32, device=device)
+
+    out, keep = [], []
+    for name, a, by in calls:
+        if name == "mpc_linear_fwd_f32":
+            ldx, ldw, ldy, M, K, N = (val(a[i]) for i in (1, 3, 6, 8, 9, 10))
+            x, w, y = buf(M, ldx), buf(N, ldw), buf(M, ldy)
+            bias = torch.randn(N, device=device) if val(a[4]) else None
+            sc = torch.zeros(2 * N + 1, dtype=torch.float64, device=device) if val(a[7]) else None
+            keep += [x, w, y, bias, sc]
+            P = mpc._lib.ptr
+            na = (P(x), a[1], P(w), a[3], P(bias), P(y), a[6], P(sc), a[8], a[9], a[10])
+        elif name == "mpc_linear_dgrad_f32":
+            ldg, ldw, ldx, M, K, N = (val(a[i]) for i in (1, 3, 5, 6, 7, 8))
+            g, w, x = buf(M, ldg), buf(N, ldw), buf(M, ldx)
+            keep += [g, w, x]
+            P = mpc._lib.ptr
+            na = (P(g), a[1], P(w), a[3], P(x), a[5], a[6], a[7], a[8])
+        elif name == "mpc_linear_wgrad_f32":
+            ldg, ldx, ldw, M, K, N = (val(a[i]) for i in (1, 3, 5, 6, 7, 8))
+            g, x, w = buf(M, ldg), buf(M, ldx), buf(N, ldw)
+            keep += [g, x, w]
+            P = mpc._lib.ptr
+            na = (P(g), a[1], P(x), a[3], P(w), a[5], a[6], a[7], a[8])
+        else:
+            return None, None  # not a GEMM entry point: cannot rebuild its buffers generically
+        out.append((name, na, by))
+    return out, keep
+
+
 def op_table(records):
     rows = []
     for name, recs in records.items():
@@ -319,10 +358,13 @@ def run_own(args):
     if rank == 0:
         sampler.start()
     mpc._lib.profiler = {"names": set(dominant_entries), "calls": []}
-    keep = step(xyz, label, target, device_starts())  # keeps the autograd graph (activations) of this step alive
+    step(xyz, label, target, device_starts())
     torch.cuda.synchronize()
     calls = mpc._lib.profiler["calls"]
     mpc._lib.profiler = None
+    calls, keep = rebind_gemm_calls(mpc, calls, device)
+    if calls is None:
+        raise SystemExit("bench.py: dominant kernel %s is not a GEMM entry point; extend rebind_gemm_calls" % dominant_kernel)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):

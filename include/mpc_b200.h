@@ -179,6 +179,13 @@ int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t
 int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float momentum, double* scratch, int64_t M, int64_t C,
                      mpc_stream_t stream);
+/* Training-mode forward in one launch from the column sums the GEMM epilogue left in `sums` (sum, then sum of
+ * squares, C doubles each): mean / variance are derived on the fly, out = lrelu(BN(y)), stats[0:C] / stats[C:2C]
+ * receive mean / biased variance for the backward pass, running statistics are updated like nn.BatchNorm1d.
+ * Requires C % 4 == 0, 1024 % C == 0; otherwise MPC_ERR_UNSUPPORTED (use mpc_bn_finalize_f32 + mpc_bn_act_fwd_f32). */
+int mpc_bn_act_fwd_sums_f32(const float* y, const double* sums, const float* gamma, const float* beta, float eps,
+                            float slope, float* out, float* stats, float* running_mean, float* running_var,
+                            int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C, mpc_stream_t stream);
 /* out[c] = sum over the M rows of y[:,c] (fp64 accumulation; scratch: 2*C+1 doubles).  The bias gradient of a
  * projection that is not followed by BatchNorm (q / k / v of LocalTrans).  C/4 must be a power of two <= 256. */
 int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t M, int64_t C, mpc_stream_t stream);

@@ -369,19 +369,59 @@ attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ fe
                 }
             }
     }
-    // one reduction per thread into the [C,cin] / [C] accumulators
+    // reduce the per-thread partials over the CTA's row slots in shared memory first (threads tid, tid + Cb, ...
+    // own the same channel), then one red.global per (CTA, channel, quantity): 4x-8x fewer same-address atomics
+    if constexpr (CIN == 0) {  // generic input width (not on a live model path): direct reductions
 #pragma unroll
-    for (int i = 0; i < CM; ++i)
-        if (i < cin) {
-            red_add_f32(gwq + c * cin + i, GWq[i]);
-            red_add_f32(gwk + c * cin + i, GWk[i]);
-            red_add_f32(gwv + c * cin + i, GWv[i]);
-            if (gres) red_add_f32(gwr + c * cin + i, GWr[i]);
+        for (int i = 0; i < CM; ++i)
+            if (i < cin) {
+                red_add_f32(gwq + c * cin + i, GWq[i]);
+                red_add_f32(gwk + c * cin + i, GWk[i]);
+                red_add_f32(gwv + c * cin + i, GWv[i]);
+                if (gres) red_add_f32(gwr + c * cin + i, GWr[i]);
+            }
+        red_add_f32(gbq + c, GBq);
+        red_add_f32(gbk + c, GBk);
+        red_add_f32(gbv + c, GBv);
+        if (gres) red_add_f32(gbr + c, GBr);
+        return;
+    }
+    constexpr int RQ = CIN > 0 ? 4 * (CIN + 1) : 1;
+    __shared__ float red[RQ][256];
+    {
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < CM; ++i) {
+            red[q++][threadIdx.x] = GWq[i];
+            red[q++][threadIdx.x] = GWk[i];
+            red[q++][threadIdx.x] = GWv[i];
+            red[q++][threadIdx.x] = GWr[i];
         }
-    if (gres) red_add_f32(gbr + c, GBr);
-    red_add_f32(gbq + c, GBq);
-    red_add_f32(gbk + c, GBk);
-    red_add_f32(gbv + c, GBv);
+        red[q++][threadIdx.x] = GBq;
+        red[q++][threadIdx.x] = GBk;
+        red[q++][threadIdx.x] = GBv;
+        red[q++][threadIdx.x] = GBr;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < Cb) {
+        auto total = [&](int q) {
+            float a = 0.f;
+            for (int t = threadIdx.x; t < (int)blockDim.x; t += Cb) a += red[q][t];
+            return a;
+        };
+#pragma unroll
+        for (int i = 0; i < CM; ++i)
+            if (i < cin) {
+                red_add_f32(gwq + c * cin + i, total(4 * i + 0));
+                red_add_f32(gwk + c * cin + i, total(4 * i + 1));
+                red_add_f32(gwv + c * cin + i, total(4 * i + 2));
+                if (gres) red_add_f32(gwr + c * cin + i, total(4 * i + 3));
+            }
+        red_add_f32(gbq + c, total(4 * CM + 0));
+        red_add_f32(gbk + c, total(4 * CM + 1));
+        red_add_f32(gbv + c, total(4 * CM + 2));
+        if (gres) red_add_f32(gbr + c, total(4 * CM + 3));
+    }
 }
 
 static inline int xyz_threads(int C) {  // C <= 256: several rows per CTA; else 256 channels per CTA

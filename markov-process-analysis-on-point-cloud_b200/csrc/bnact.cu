@@ -353,6 +353,53 @@ bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restri
     for (; t < total; t += stride) gy[t] = apply(__ldg(y + t), __ldg(gout + t));
 }
 
+// Training forward straight from the GEMM epilogue's column sums: every thread derives mean / variance of its 4
+// channels from the fp64 sums (so the separate finalise launch disappears); CTA 0 also publishes mean / biased
+// variance for the backward pass and applies nn.BatchNorm1d's running-statistics update.
+__global__ void __launch_bounds__(256)
+bn_act_fwd_sums_kernel(const float4* __restrict__ y, const double* __restrict__ s1, const double* __restrict__ s2,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
+                       float4* __restrict__ out, float* __restrict__ stats, float* __restrict__ running_mean,
+                       float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked, float momentum,
+                       int64_t M, int C, int64_t total) {
+    if (blockIdx.x == 0) {
+        StatsFinal fin{stats, running_mean, running_var, num_batches_tracked, momentum};
+        for (int i = threadIdx.x; i < C; i += 256) finalize_channel(s1, s2, fin, M, C, i);
+        if (threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    }
+    const int c = (threadIdx.x * 4) % C;
+    float mu[4], sc[4], be[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double mean = s1[c + i] / (double)M;
+        double var = s2[c + i] / (double)M - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        mu[i] = (float)mean;
+        sc[i] = gamma[c + i] * (1.0f / sqrtf((float)var + eps));
+        be[i] = beta[c + i];
+    }
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    auto apply = [&](const float4& v) {
+        float4 o;
+        float z;
+        z = fmaf(v.x - mu[0], sc[0], be[0]); o.x = z > 0.f ? z : z * slope;
+        z = fmaf(v.y - mu[1], sc[1], be[1]); o.y = z > 0.f ? z : z * slope;
+        z = fmaf(v.z - mu[2], sc[2], be[2]); o.z = z > 0.f ? z : z * slope;
+        z = fmaf(v.w - mu[3], sc[3], be[3]); o.w = z > 0.f ? z : z * slope;
+        return o;
+    };
+    for (; t + 3 * stride < total; t += 4 * stride) {
+        const float4 v0 = __ldg(y + t), v1 = __ldg(y + t + stride), v2 = __ldg(y + t + 2 * stride),
+                     v3 = __ldg(y + t + 3 * stride);
+        out[t] = apply(v0);
+        out[t + stride] = apply(v1);
+        out[t + 2 * stride] = apply(v2);
+        out[t + 3 * stride] = apply(v3);
+    }
+    for (; t < total; t += stride) out[t] = apply(__ldg(y + t));
+}
+
 static inline bool fast_ew(int64_t C) { return C % 4 == 0 && C <= 1024 && 1024 % C == 0; }
 
 // backward pass A: per channel sum(dz) and sum(dz * xhat)
@@ -556,6 +603,20 @@ MPC_API int mpc_bn_finalize_f32(const double* sums, float* stats, float* running
     if (!sums || !stats || M <= 0 || C <= 0) return MPC_ERR_INVALID;
     bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
         sums, sums + C, stats, running_mean, running_var, num_batches_tracked, momentum, M, (int)C);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_bn_act_fwd_sums_f32(const float* y, const double* sums, const float* gamma, const float* beta, float eps,
+                                    float slope, float* out, float* stats, float* running_mean, float* running_var,
+                                    int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C,
+                                    mpc_stream_t stream) {
+    if (!y || !sums || !gamma || !beta || !out || !stats || M <= 0 || C <= 0) return MPC_ERR_INVALID;
+    if (!fast_ew(C) || !al16(y) || !al16(out)) return MPC_ERR_UNSUPPORTED;
+    const int64_t total = M * (C / 4);
+    bn_act_fwd_sums_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(y), sums, sums + C, gamma, beta, eps, slope, reinterpret_cast<float4*>(out), stats,
+        running_mean, running_var, num_batches_tracked, momentum, M, (int)C, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

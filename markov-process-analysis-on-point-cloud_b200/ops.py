@@ -106,6 +106,17 @@ def farthest_point_sample(xyz, npoint, cuda=False, start=None):
     return out
 
 
+def sample(nsample, feature, cuda=False):
+    """Data-side FPS of the reference's training scripts (`sample(args.num_point, points, cuda=...)`,
+    R/tool/train_cls_scanobjectnn.py:244 -- called there, defined nowhere in the shipped tree; upstream RepSurf
+    semantics): feature [B, C, N] with xyz in channels 0..2 -> [B, C, nsample], the columns picked by farthest
+    point sampling on the coordinates."""
+    require_cuda(feature)
+    xyz = feature[:, :3, :].permute(0, 2, 1).contiguous()
+    idx = farthest_point_sample(xyz, nsample)
+    return index_points(feature.permute(0, 2, 1).contiguous(), idx).permute(0, 2, 1).contiguous()
+
+
 def _list_length(k):
     for L in _KNN_LIST_LENGTHS:
         if k <= L:
@@ -613,15 +624,25 @@ class LinearBNAct(torch.autograd.Function):
             scratch = torch.empty(2 * N + 1, dtype=torch.float64, device=dev)
             stats = torch.empty(2 * N, dtype=torch.float32, device=dev)
             _tc_gemm(x2d, w, bias, y, stat_scratch=scratch)
-            call("mpc_bn_finalize_f32", ptr(scratch), ptr(stats), ptr(running_mean), ptr(running_var),
-                 ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M), _i64(N))
             mean, var = stats[:N], stats[N:]
+            out = torch.empty_like(y)
+            if N % 4 == 0 and N <= 1024 and 1024 % N == 0:
+                # finalise + normalise + activation + running-statistics update in one launch
+                call("mpc_bn_act_fwd_sums_f32", ptr(y), ptr(scratch), ptr(gamma), ptr(beta), ctypes.c_float(eps),
+                     ctypes.c_float(slope), ptr(out), ptr(stats), ptr(running_mean), ptr(running_var),
+                     ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M), _i64(N),
+                     algo_bytes=2 * M * N * 4)
+            else:
+                call("mpc_bn_finalize_f32", ptr(scratch), ptr(stats), ptr(running_mean), ptr(running_var),
+                     ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M), _i64(N))
+                call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
+                     ctypes.c_float(slope), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
         else:
             _tc_gemm(x2d, w, bias, y)
             mean, var = running_mean, running_var
-        out = torch.empty_like(y)
-        call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
-             ctypes.c_float(slope), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
+            out = torch.empty_like(y)
+            call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
+                 ctypes.c_float(slope), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
         ctx.save_for_backward(x2d, w, y, mean, var, gamma, beta)
         ctx.cfg = (training, eps, slope, bias is not None)
         return out

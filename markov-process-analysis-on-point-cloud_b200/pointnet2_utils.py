@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .ops import (farthest_point_sample, index_points, knn_point, query_ball_point, query_knn_point,  # noqa: F401
-                  square_distance, three_interpolate, three_nn, upsample)
+                  sample, square_distance, three_interpolate, three_nn, upsample)
 
 
 class Linear(nn.Module):

@@ -265,3 +265,16 @@ def test_linear_3xtf32_strided_operands(mpc):
     out = torch.empty(2000, 96, device="cuda")
     mpc.ops._tc_gemm(x, w, None, out)
     torch.testing.assert_close(out, (x.double() @ w.double().t()).float(), rtol=1e-5, atol=1e-5)
+
+
+def test_sample_data_side_fps(mpc, orc):
+    """sample(nsample, feature[B,C,N]) of the training scripts: FPS on the xyz channels, gather of all channels."""
+    g = torch.Generator().manual_seed(11)
+    feat = torch.rand(3, 6, 500, generator=g) * 2 - 1
+    torch.manual_seed(5)
+    out = mpc.ops.sample(64, feat.cuda())
+    torch.manual_seed(5)
+    start = torch.randint(0, 500, (3,), dtype=torch.long)
+    idx = orc.farthest_point_sample(feat[:, :3].permute(0, 2, 1).contiguous(), 64, start)
+    ref = torch.gather(feat, 2, idx.unsqueeze(1).expand(-1, 6, -1))
+    assert out.shape == (3, 6, 64) and torch.equal(out.cpu(), ref)

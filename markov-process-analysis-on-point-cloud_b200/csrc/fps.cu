@@ -270,8 +270,9 @@ static int launch_cluster(const float* xyz, const int64_t* start, int64_t* out, 
 MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, int64_t B, int64_t N, int64_t C,
                         int64_t npoint, mpc_stream_t stream) {
     using namespace mpc;
-    if (!xyz || !start || !out || B < 0 || N <= 0 || C <= 0 || npoint < 0) return MPC_ERR_INVALID;
-    if (B == 0 || npoint == 0) return MPC_OK;
+    if (B < 0 || N <= 0 || C <= 0 || npoint < 0) return MPC_ERR_INVALID;
+    if (B == 0 || npoint == 0) return MPC_OK;  // nothing to do: empty tensors carry null pointers
+    if (!xyz || !start || !out) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     if (C != 3) {
         size_t smem = (size_t)(N + C) * sizeof(float);

@@ -241,8 +241,9 @@ using namespace mpc;
 
 MPC_API int mpc_gather_f32(const float* points, const int64_t* idx, float* out, int64_t B, int64_t N, int64_t M,
                            int64_t C, mpc_stream_t stream) {
-    if (!points || !idx || !out || B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (B == 0 || M == 0) return MPC_OK;
+    if (!points || !idx || !out) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
         const int CV = (int)(C / 4);
@@ -259,8 +260,9 @@ MPC_API int mpc_gather_f32(const float* points, const int64_t* idx, float* out, 
 
 MPC_API int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* out, int64_t B, int64_t N,
                            int64_t M, mpc_stream_t stream) {
-    if (!values || !idx || !out || B < 0 || N <= 0 || M < 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (B < 0 || N <= 0 || M < 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (B == 0 || M == 0) return MPC_OK;
+    if (!values || !idx || !out) return MPC_ERR_INVALID;
     const int64_t total = B * M;
     gather_kernel<long long><<<grid_for(total), GT, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const long long*>(values), idx, reinterpret_cast<long long*>(out), (int)N, M, 1, total);
@@ -270,11 +272,13 @@ MPC_API int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* o
 
 MPC_API int mpc_gather_bwd_f32(const float* grad_out, const int64_t* idx, float* grad_points, int64_t B,
                                int64_t N, int64_t M, int64_t C, mpc_stream_t stream) {
-    if (!grad_out || !idx || !grad_points || B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (B == 0) return MPC_OK;
+    if (!grad_points) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     MPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * N * C * sizeof(float), st));
     if (M == 0) return MPC_OK;
+    if (!grad_out || !idx) return MPC_ERR_INVALID;
     if (C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points)) {
         const int CV = (int)(C / 4);
         const int64_t total = B * M * CV;
@@ -290,10 +294,10 @@ MPC_API int mpc_gather_bwd_f32(const float* grad_out, const int64_t* idx, float*
 
 MPC_API int mpc_transition_fwd_f32(const float* points, const int64_t* idx, float* out, float* cnt, int64_t B,
                                    int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream) {
-    if (!points || !idx || !out || !cnt || B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX)
-        return MPC_ERR_INVALID;
+    if (B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (K > 32) return MPC_ERR_UNSUPPORTED;
     if (B == 0) return MPC_OK;
+    if (!out || !cnt || (S > 0 && (!points || !idx))) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     MPC_CUDA(cudaMemsetAsync(out, 0, (size_t)B * N * C * sizeof(float), st));
     MPC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)B * N * sizeof(float), st));
@@ -323,10 +327,10 @@ MPC_API int mpc_transition_fwd_f32(const float* points, const int64_t* idx, floa
 MPC_API int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, const float* cnt,
                                    float* grad_points, int64_t B, int64_t S, int64_t K, int64_t C, int64_t N,
                                    mpc_stream_t stream) {
-    if (!grad_out || !idx || !cnt || !grad_points || B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX)
-        return MPC_ERR_INVALID;
+    if (B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (K > 32) return MPC_ERR_UNSUPPORTED;
     if (B == 0 || S == 0) return MPC_OK;
+    if (!grad_out || !idx || !cnt || !grad_points) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points);
     const int CV = (int)(v4 ? C / 4 : C);
@@ -344,9 +348,9 @@ MPC_API int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, co
 MPC_API int mpc_three_interpolate_fwd_f32(const float* points2, const float* dist, const int64_t* idx,
                                           float* weight_out, float* out, int64_t B, int64_t N, int64_t S,
                                           int64_t C, mpc_stream_t stream) {
-    if (!points2 || !dist || !idx || !weight_out || !out || B < 0 || N < 0 || S <= 0 || C <= 0 || S > INT32_MAX)
-        return MPC_ERR_INVALID;
+    if (B < 0 || N < 0 || S <= 0 || C <= 0 || S > INT32_MAX) return MPC_ERR_INVALID;
     if (B == 0 || N == 0) return MPC_OK;
+    if (!points2 || !dist || !idx || !weight_out || !out) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     three_weights_kernel<<<grid_for(B * N), GT, 0, st>>>(dist, weight_out, B * N);
     MPC_LAUNCH_CHECK();
@@ -365,12 +369,13 @@ MPC_API int mpc_three_interpolate_fwd_f32(const float* points2, const float* dis
 MPC_API int mpc_three_interpolate_bwd_f32(const float* grad_out, const float* weight, const int64_t* idx,
                                           float* grad_points2, int64_t B, int64_t N, int64_t S, int64_t C,
                                           mpc_stream_t stream) {
-    if (!grad_out || !weight || !idx || !grad_points2 || B < 0 || N < 0 || S <= 0 || C <= 0 || S > INT32_MAX)
-        return MPC_ERR_INVALID;
+    if (B < 0 || N < 0 || S <= 0 || C <= 0 || S > INT32_MAX) return MPC_ERR_INVALID;
     if (B == 0) return MPC_OK;
+    if (!grad_points2) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     MPC_CUDA(cudaMemsetAsync(grad_points2, 0, (size_t)B * S * C * sizeof(float), st));
     if (N == 0) return MPC_OK;
+    if (!grad_out || !weight || !idx) return MPC_ERR_INVALID;
     const bool v4 = C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points2);
     const int64_t total = B * N * (v4 ? C / 4 : C);
     if (v4)

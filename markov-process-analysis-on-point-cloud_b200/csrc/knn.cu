@@ -681,9 +681,10 @@ ball_query_generic_kernel(const float* __restrict__ xyz, const float* __restrict
 MPC_API int mpc_knn_f32(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, int64_t B,
                         int64_t N, int64_t S, int64_t C, int64_t K, mpc_stream_t stream) {
     using namespace mpc;
-    if (!ref || !qry || !idx_out || B < 0 || N <= 0 || S < 0 || C <= 0 || K <= 0 || K > N) return MPC_ERR_INVALID;
+    if (B < 0 || N <= 0 || S < 0 || C <= 0 || K <= 0 || K > N) return MPC_ERR_INVALID;
+    if (B == 0 || S == 0) return MPC_OK;  // nothing to do: empty tensors carry null pointers
+    if (!ref || !qry || !idx_out) return MPC_ERR_INVALID;
     if (K > 32 || C > 1024 || N > INT32_MAX || S > INT32_MAX || B > 65535) return MPC_ERR_UNSUPPORTED;
-    if (B == 0 || S == 0) return MPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int b = (int)B, n = (int)N, s = (int)S, c = (int)C;
     if (K <= 3) {
@@ -700,9 +701,10 @@ MPC_API int mpc_knn_f32(const float* ref, const float* qry, float* dist_out, int
 MPC_API int mpc_ball_query_f32(const float* xyz, const float* new_xyz, int64_t* idx_out, float r2, int64_t B,
                                int64_t N, int64_t S, int64_t C, int64_t nsample, mpc_stream_t stream) {
     using namespace mpc;
-    if (!xyz || !new_xyz || !idx_out || B < 0 || N <= 0 || S < 0 || C <= 0 || nsample <= 0) return MPC_ERR_INVALID;
-    if (N > INT32_MAX || S > INT32_MAX || B > 65535 || nsample > INT32_MAX) return MPC_ERR_UNSUPPORTED;
+    if (B < 0 || N <= 0 || S < 0 || C <= 0 || nsample <= 0) return MPC_ERR_INVALID;
     if (B == 0 || S == 0) return MPC_OK;
+    if (!xyz || !new_xyz || !idx_out) return MPC_ERR_INVALID;
+    if (N > INT32_MAX || S > INT32_MAX || B > 65535 || nsample > INT32_MAX) return MPC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)ceil_div(S, BQ_THREADS), (unsigned)B);
     if (C == 3)

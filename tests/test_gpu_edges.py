@@ -1,0 +1,133 @@
+"""Edge cases of the point-set ops on the GPU: empty and ragged shapes, non-contiguous inputs, wrong dtypes,
+large single clouds, degenerate clouds (all points identical), and the classifier at BASELINE config-1 size."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def cloud(B, N, C=3, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, N, C, generator=g) * 2 - 1
+
+
+def test_empty_batches_and_query_sets(mpc):
+    ops = mpc.ops
+    xyz = cloud(2, 64).cuda()
+    empty_q = torch.empty(2, 0, 3, device="cuda")
+    d, i = ops.knn_point(8, xyz, empty_q)
+    assert d.shape == (2, 0, 8) and i.shape == (2, 0, 8)
+    assert ops.farthest_point_sample(xyz, 0).shape == (2, 0)
+    assert ops.query_ball_point(0.3, 4, xyz, empty_q).shape == (2, 0, 4)
+    feats = torch.randn(2, 64, 16, device="cuda", requires_grad=True)
+    out = ops.index_points(feats, torch.empty(2, 0, dtype=torch.long, device="cuda"))
+    assert out.shape == (2, 0, 16)
+    out.sum().backward()
+    assert torch.count_nonzero(feats.grad) == 0
+    b0 = torch.empty(0, 64, 3, device="cuda")
+    assert ops.farthest_point_sample(b0, 8).shape == (0, 8)
+    assert ops.knn_point(8, b0, b0)[1].shape == (0, 64, 8)
+
+
+def test_non_contiguous_and_wrong_dtype(mpc, orc):
+    ops = mpc.ops
+    base = cloud(2, 128, 3, seed=4)
+    view = base.cuda().permute(0, 2, 1).permute(0, 2, 1)[:, ::2]  # strided view, 64 points
+    ref = base[:, ::2].contiguous()
+    d0, i0 = orc.knn_point(8, ref, ref)
+    d1, i1 = ops.knn_point(8, view, view)
+    assert torch.equal(i1.cpu(), i0) and torch.equal(d1.cpu(), d0)
+    with pytest.raises(TypeError):
+        ops.knn_point(8, view.double(), view.double())
+    with pytest.raises(TypeError):
+        ops.index_points(torch.zeros(1, 4, 2, dtype=torch.float16, device="cuda"),
+                         torch.zeros(1, 2, dtype=torch.long, device="cuda"))
+
+
+def test_degenerate_cloud_all_points_identical(mpc, orc):
+    """Every distance is an exact tie: FPS falls back to index 0 after the start, kNN returns indices 0..K-1."""
+    xyz = torch.full((2, 50, 3), 0.25)
+    start = torch.tensor([7, 0])
+    ref = orc.farthest_point_sample(xyz, 10, start)
+    out = mpc.ops.farthest_point_sample(xyz.cuda(), 10, start=start.cuda())
+    assert torch.equal(out.cpu(), ref) and (ref[:, 1:] == 0).all()
+    d, i = mpc.ops.knn_point(8, xyz.cuda(), xyz.cuda())
+    assert torch.equal(i.cpu(), torch.arange(8).expand(2, 50, 8))
+    d0, i0 = orc.knn_point(8, xyz, xyz)
+    assert torch.equal(d.cpu(), d0) and torch.equal(i.cpu(), i0)
+
+
+def test_knn_large_reference_set(mpc, orc):
+    ref, qry = cloud(1, 100000, seed=1), cloud(1, 300, seed=2)
+    d0, i0 = orc.knn_point(16, ref, qry)
+    d1, i1 = mpc.ops.knn_point(16, ref.cuda(), qry.cuda())
+    assert torch.equal(i1.cpu(), i0) and torch.equal(d1.cpu(), d0)
+
+
+def test_ragged_sizes_every_op(mpc, orc):
+    """Sizes that are not multiples of any tile: N=1031 points, S=257 queries, C=20 channels, K=5."""
+    ops = mpc.ops
+    g = torch.Generator().manual_seed(9)
+    xyz, sub = cloud(3, 1031, seed=5), cloud(3, 257, seed=6)
+    d0, i0 = orc.knn_point(5, xyz, sub)
+    d1, i1 = ops.knn_point(5, xyz.cuda(), sub.cuda())
+    assert torch.equal(i1.cpu(), i0) and torch.equal(d1.cpu(), d0)
+    feats = torch.randn(3, 257, 20, generator=g)
+    up0 = orc.upsample(feats, i0, n_out=1031)
+    up1 = ops.upsample(feats.cuda(), i1, n_out=1031)
+    torch.testing.assert_close(up1.cpu(), up0, rtol=1e-5, atol=1e-6)
+    x = torch.randn(3 * 257, 20, generator=g).cuda()
+    lin = mpc.pointnet2_utils.Linear(20, 28, bn=False).cuda().train()  # K % 32 != 0 -> library GEMM path
+    ref_lin = torch.nn.Sequential()
+    y = lin(x.view(3, 257, 20))
+    z = torch.nn.functional.linear(x, lin.linear.weight, lin.linear.bias)
+    z = torch.nn.functional.leaky_relu(torch.nn.functional.batch_norm(z, None, None, lin.norm2.weight, lin.norm2.bias,
+                                                                       training=True), 0.2)
+    torch.testing.assert_close(y.reshape(-1, 28), z, rtol=1e-4, atol=1e-5)
+
+
+def test_tensor_core_linear_block_matches_library_path(mpc):
+    """Linear(64, 128): the tcgen05 path (GEMM + epilogue statistics + fused BatchNorm) against the library ops."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 1000, 64, generator=g).cuda().requires_grad_(True)
+    lin = mpc.pointnet2_utils.Linear(64, 128, bn=False).cuda().train()
+    w = torch.randn(4, 1000, 128, generator=g).cuda()
+    y = lin(x)
+    (y * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    z = torch.nn.functional.linear(xr.double(), lin.linear.weight.double(), lin.linear.bias.double())
+    z = torch.nn.functional.batch_norm(z.reshape(-1, 128), None, None, lin.norm2.weight.double(),
+                                       lin.norm2.bias.double(), training=True).reshape(4, 1000, 128)
+    z = torch.nn.functional.leaky_relu(z, 0.2)
+    (z * w.double()).sum().backward()
+    torch.testing.assert_close(y, z.float(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(x.grad, xr.grad.float(), rtol=1e-3, atol=1e-5)
+    rm = lin.norm2.running_mean
+    ref_mean = torch.nn.functional.linear(x.detach(), lin.linear.weight, lin.linear.bias).reshape(-1, 128).mean(0)
+    torch.testing.assert_close(rm, 0.1 * ref_mean, rtol=1e-4, atol=1e-6)
+    assert int(lin.norm2.num_batches_tracked) == 1
+
+
+def test_classifier_config1_shape(mpc):
+    """BASELINE config 1: classifier forward, batch 16 x 1024 points, eval: finite log-probabilities that sum to one;
+    streams on/off agree bit for bit (same kernels, same order of arithmetic)."""
+    torch.manual_seed(0)
+    m = mpc.task_models.Model(argparse.Namespace(num_point=1024, return_dist=True, cuda_ops=True, num_class=40))
+    m = m.cuda().eval()
+    pts = (torch.rand(16, 3, 1024, generator=torch.Generator().manual_seed(1)) * 2 - 1).cuda()
+    starts = [torch.randint(0, n, (16,), generator=torch.Generator().manual_seed(n)) for n in (1024, 512, 256, 128, 64)]
+    with torch.no_grad(), mpc.ops.index_tape(fps_starts=starts):
+        a = m(pts)
+    assert a.shape == (16, 40) and torch.isfinite(a).all()
+    torch.testing.assert_close(a.exp().sum(1), torch.ones(16, device="cuda"), rtol=1e-4, atol=1e-4)
+    old = mpc.ops._STREAMS_ENABLED
+    try:
+        mpc.ops._STREAMS_ENABLED = False
+        with torch.no_grad(), mpc.ops.index_tape(fps_starts=starts):
+            b = m(pts)
+    finally:
+        mpc.ops._STREAMS_ENABLED = old
+    assert torch.equal(a, b)

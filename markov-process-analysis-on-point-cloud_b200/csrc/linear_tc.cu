@@ -108,11 +108,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 constexpr int STAGING_BYTES = BLOCK_M * 128;  // one 32-column slab of a tile: 128 rows x 128 B
-constexpr int EPI_SMEM_BYTES = STAGING_BYTES + 1024;  // + bias for up to 256 columns
+constexpr int EPI_BIAS_BYTES = 1024;  // bias for up to 256 columns
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1, layout SWIZZLE_128B (2).
@@ -144,6 +145,7 @@ struct Params {
     int k_chunks;     // ceil(reduction length / 32)
     long long* trace; // debug: per-role clock64() timeline of CTA 0 (null in production)
     int tma_out;      // 1: results leave through a swizzled staging slab + TMA store / TMA reduce-add
+    int epi_bufs;     // staging slabs (1 or 2): with 2 the TMA store of slab i overlaps the fill of slab i+1
     double* stat_sum; // optional [2][N]: per-column sum and sum of squares of y (BatchNorm batch statistics),
                       // accumulated from the staged tile while it is still in shared memory
 };
@@ -168,8 +170,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int b_tile_bytes = p.block_n * BLOCK_K * 4;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
-    uint8_t* staging = smem + (size_t)p.stages * stage_bytes;                 // 16 KB, 1024-aligned
-    float* bias_s = reinterpret_cast<float*>(staging + STAGING_BYTES);        // 256 floats
+    uint8_t* staging0 = smem + (size_t)p.stages * stage_bytes;                // epi_bufs x 16 KB, 1024-aligned
+    float* bias_s = reinterpret_cast<float*>(staging0 + p.epi_bufs * STAGING_BYTES);  // 256 floats
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int chunks_per_split = (p.k_chunks + p.splits - 1) / p.splits;
@@ -195,15 +197,24 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x == 32) {  // descriptor fetches (~1 DRAM round trip each) off the critical path
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    }
+    __syncthreads();  // barriers initialised: the TMA producer and the splitters start right away
+    uint32_t tmem_base = 0;
     if (warp == 9) {  // TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                      "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
+    if (warp == 9 || warp < 4) {  // only the MMA issuer and the epilogue warps need the TMEM address
+        tc_fence_before();
+        asm volatile("bar.sync 2, 160;" ::: "memory");
+        tc_fence_after();
+        tmem_base = tmem_base_slot;
+    }
 
     if (warp == 8) {
         // ===== TMA producer =====
@@ -340,33 +351,42 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows 32w..32w+31 of the tile =====
-        int tile_it = 0, tn_ = 0;
+        int tile_it = 0, tn_ = 0, slab_it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             int mt, nt, kc0, kc1;
             decode(tile, mt, nt, kc0, kc1);
             const int as = tile_it & 1;
             const uint32_t aph = (tile_it >> 1) & 1;
-            mbar_wait(&bar_tmem_full[as], aph);
-            if (threadIdx.x == 0) MPC_TRACE(3, tn_);
-            tc_fence_after();
             const int row = mt * BLOCK_M + warp * 32 + lane;
             const int n0 = nt * p.block_n;
-            const uint32_t taddr = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(warp * 32) << 16);
             if (p.tma_out) {
-                // bias of this tile's columns -> shared (broadcast reads below); also orders reuse of bias_s
+                // bias of this tile's columns -> shared (broadcast reads below), fetched while the main loop of
+                // this tile is still running; the first barrier orders the reuse of bias_s across tiles
                 epi_barrier();
                 for (int i = threadIdx.x; i < p.block_n; i += 128)
                     bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+            }
+            mbar_wait(&bar_tmem_full[as], aph);
+            if (threadIdx.x == 0) MPC_TRACE(3, tn_);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(warp * 32) << 16);
+            if (p.tma_out) {
                 epi_barrier();
                 const int r_in = warp * 32 + lane;  // row inside the tile = TMEM lane
-                uint4* srow = reinterpret_cast<uint4*>(staging + r_in * 128);
-                for (int c = 0; c < p.block_n; c += 32) {
+                for (int c = 0; c < p.block_n; c += 32, ++slab_it) {
+                    uint8_t* staging = staging0 + (p.epi_bufs == 2 ? (slab_it & 1) * STAGING_BYTES : 0);
+                    uint4* srow = reinterpret_cast<uint4*>(staging + r_in * 128);
                     uint32_t r0[16], r1[16];
                     tmem_ld16(taddr + c, r0);
                     tmem_ld16(taddr + c + 16, r1);
                     tmem_ld_wait();
-                    // the previous slab's TMA store must have finished READING the staging buffer
-                    if (threadIdx.x == 0) bulk_wait_read0();
+                    // the TMA store that last used this staging slab must have finished READING it
+                    if (threadIdx.x == 0) {
+                        if (p.epi_bufs == 2)
+                            bulk_wait_read1();
+                        else
+                            bulk_wait_read0();
+                    }
                     epi_barrier();
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {  // 8 x 16 B of this row, 128B-swizzled like the TMA box expects
@@ -538,6 +558,21 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 
 static long long* g_trace = nullptr;  // debug only, see mpc_debug_trace_buffer
 
+// Shared-memory budget (224 KB opt-in, 1 KB alignment slack): as many operand stages as fit; a second epilogue
+// staging slab only if at least 3 operand stages remain (TMA latency ~1.3 us needs >= 3 stages in flight).
+static void pick_pipeline(int stage_bytes, int* stages, int* epi_bufs) {
+    const int budget = 222 * 1024 - EPI_BIAS_BYTES;
+    int s2 = (budget - 2 * STAGING_BYTES) / stage_bytes;
+    int s1 = (budget - STAGING_BYTES) / stage_bytes;
+    if (s2 >= 3) {
+        *stages = s2 > MAX_STAGES ? MAX_STAGES : s2;
+        *epi_bufs = 2;
+    } else {
+        *stages = s1 > MAX_STAGES ? MAX_STAGES : s1;
+        *epi_bufs = 1;
+    }
+}
+
 static cudaError_t ensure_smem_optin() {
     static bool done = false;  // idempotent attribute; a benign race at worst sets it twice
     if (done) return cudaSuccess;
@@ -576,8 +611,8 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
         MPC_CUDA(cudaMemsetAsync(stat_scratch, 0, sizeof(double) * (2 * (size_t)N + 1), (cudaStream_t)stream));
     }
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
-    int stages = (222 * 1024 - EPI_SMEM_BYTES) / stage_bytes;  // opt-in is 224 KB; 1 KB alignment slack
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    int stages;
+    pick_pipeline(stage_bytes, &stages, &p.epi_bufs);
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
     p.bias = bias;
@@ -598,7 +633,7 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
         rc = make_map(&map_y, y, M, N, ldy, BLOCK_M);  // box 32 columns x 128 rows, 128B swizzle
         if (rc) return rc;
     }
-    const size_t smem = (size_t)stages * stage_bytes + EPI_SMEM_BYTES + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + p.epi_bufs * STAGING_BYTES + EPI_BIAS_BYTES + 1024;
     MPC_CUDA(ensure_smem_optin());
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
@@ -635,8 +670,8 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     while (splits > 1 && (int)ceil_div(p.k_chunks, splits) * (splits - 1) >= p.k_chunks) --splits;
     p.splits = splits;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
-    int stages = (222 * 1024 - EPI_SMEM_BYTES) / stage_bytes;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    int stages;
+    pick_pipeline(stage_bytes, &stages, &p.epi_bufs);
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
     p.bias = nullptr;
@@ -664,7 +699,7 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
         rc = make_map(&map_y, gw, N, K, ldw, BLOCK_M);  // TMA reduce-add (or store) of 32 x 128 slabs
         if (rc) return rc;
     }
-    const size_t smem = (size_t)stages * stage_bytes + EPI_SMEM_BYTES + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + p.epi_bufs * STAGING_BYTES + EPI_BIAS_BYTES + 1024;
     MPC_CUDA(ensure_smem_optin());
     const int items = tiles * splits;
     const int grid = items < kNumSMs ? items : kNumSMs;
@@ -700,8 +735,8 @@ MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, i
     p.splits = 1;
     p.tma_out = ((ldx & 3) == 0 && ((uintptr_t)gx & 15u) == 0) ? 1 : 0;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
-    int stages = (222 * 1024 - EPI_SMEM_BYTES) / stage_bytes;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    int stages;
+    pick_pipeline(stage_bytes, &stages, &p.epi_bufs);
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
     p.bias = nullptr;
@@ -721,7 +756,7 @@ MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, i
         rc = make_map(&map_y, gx, M, K, ldx, BLOCK_M);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)stages * stage_bytes + EPI_SMEM_BYTES + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + p.epi_bufs * STAGING_BYTES + EPI_BIAS_BYTES + 1024;
     MPC_CUDA(ensure_smem_optin());
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;

@@ -80,8 +80,8 @@ def test_ragged_sizes_every_op(mpc, orc):
     up1 = ops.upsample(feats.cuda(), i1, n_out=1031)
     torch.testing.assert_close(up1.cpu(), up0, rtol=1e-5, atol=1e-6)
     x = torch.randn(3 * 257, 20, generator=g).cuda()
+    torch.manual_seed(9)
     lin = mpc.pointnet2_utils.Linear(20, 28, bn=False).cuda().train()  # K % 32 != 0 -> library GEMM path
-    ref_lin = torch.nn.Sequential()
     y = lin(x.view(3, 257, 20))
     z = torch.nn.functional.linear(x, lin.linear.weight, lin.linear.bias)
     z = torch.nn.functional.leaky_relu(torch.nn.functional.batch_norm(z, None, None, lin.norm2.weight, lin.norm2.bias,
@@ -92,6 +92,7 @@ def test_ragged_sizes_every_op(mpc, orc):
 def test_tensor_core_linear_block_matches_library_path(mpc):
     """Linear(64, 128): the tcgen05 path (GEMM + epilogue statistics + fused BatchNorm) against the library ops."""
     g = torch.Generator().manual_seed(3)
+    torch.manual_seed(3)  # the layer's random init comes from the global generator
     x = torch.randn(4, 1000, 64, generator=g).cuda().requires_grad_(True)
     lin = mpc.pointnet2_utils.Linear(64, 128, bn=False).cuda().train()
     w = torch.randn(4, 1000, 128, generator=g).cuda()
@@ -104,7 +105,8 @@ def test_tensor_core_linear_block_matches_library_path(mpc):
     z = torch.nn.functional.leaky_relu(z, 0.2)
     (z * w.double()).sum().backward()
     torch.testing.assert_close(y, z.float(), rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(x.grad, xr.grad.float(), rtol=1e-3, atol=1e-5)
+    gscale = float(xr.grad.abs().max())
+    torch.testing.assert_close(x.grad, xr.grad.float(), rtol=1e-3, atol=1e-4 * gscale)
     rm = lin.norm2.running_mean
     ref_mean = torch.nn.functional.linear(x.detach(), lin.linear.weight, lin.linear.bias).reshape(-1, 128).mean(0)
     torch.testing.assert_close(rm, 0.1 * ref_mean, rtol=1e-4, atol=1e-6)

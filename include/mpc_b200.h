@@ -103,6 +103,11 @@ int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* out, int6
  * ------------------------------------------------------------------------------------------------- */
 int mpc_transition_fwd_f32(const float* points, const int64_t* idx, float* out, float* cnt, int64_t B,
                            int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
+/* Same result through the gather form: per-cloud reverse-neighbour lists (CSR) are built from idx with S*K integer
+ * atomics + a scan, then every output row is written once from its sorted source list: no float atomics, no
+ * zero-fill / normalise passes, deterministic summation order (ascending s).  workspace: B*(2N+1) + B*S*K int32. */
+int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, float* out, float* cnt, int32_t* workspace,
+                               int64_t B, int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
 int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, const float* cnt, float* grad_points,
                            int64_t B, int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
 

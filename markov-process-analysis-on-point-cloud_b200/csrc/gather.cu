@@ -119,6 +119,195 @@ __global__ void __launch_bounds__(GT) transition_fix_cnt_kernel(float* __restric
         if (cnt[t] == 0.0f) cnt[t] = 1.0f;
 }
 
+// ---- Markov transition, gather form -----------------------------------------------------------------------------
+// out = D^-1 A^T X is a gather once A^T (for every fine point n, the coarse points s whose neighbour list contains
+// n) is available as per-cloud CSR lists.  Building them costs S*K integer atomics and a scan -- 16x fewer atomics
+// than reducing S*K*C floats into out -- and the product itself then streams every source row exactly once per
+// incidence and writes every output row exactly once (no zero-fill, no normalise pass).  Lists are sorted, so the
+// fp32 summation order is fixed (ascending s, as in the oracle): the op is deterministic.
+__device__ __forceinline__ bool dup_before(const int64_t* irow, int k, int64_t raw) {
+    bool dup = false;
+    for (int j = 0; j < k; ++j) dup |= (__ldg(irow + j) == raw);
+    return dup;
+}
+
+__global__ void __launch_bounds__(GT)
+csr_count_kernel(const int64_t* __restrict__ idx, int* __restrict__ deg, int S, int K, int N, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / K;
+        const int k = (int)(t - row * K);
+        const int64_t b = row / S;
+        const int64_t raw = __ldg(idx + t);
+        if (raw < 0 || raw >= N || dup_before(idx + row * K, k, raw)) continue;
+        atomicAdd(deg + b * (int64_t)(N + 1) + raw, 1);
+    }
+}
+
+// exclusive scan of deg[b, 0..N] in place (one CTA per cloud); cursor[b, n] = start of list n.  Every thread owns
+// one contiguous chunk: local sum, one block-wide scan of the 1024 chunk sums, local rewrite (two barriers in all).
+__global__ void __launch_bounds__(1024)
+csr_scan_kernel(int* __restrict__ deg, int* __restrict__ cursor, int N) {
+    __shared__ int warp_sums[32];
+    int* d = deg + (int64_t)blockIdx.x * (N + 1);
+    int* cur = cursor + (int64_t)blockIdx.x * N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = (N + 1 + 1023) / 1024;
+    const int lo = min(N + 1, (int)threadIdx.x * chunk), hi = min(N + 1, lo + chunk);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += d[i];
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    int run = (warp > 0 ? warp_sums[warp - 1] : 0) + x - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = d[i];
+        d[i] = run;
+        if (i < N) cur[i] = run;
+        run += v;
+    }
+}
+
+// Large clouds: three-phase scan over 1024-element blocks (grid = blocks x clouds) so that no thread walks a long
+// dependent chain: (1) block sums, (2) scan of the block sums (one CTA per cloud), (3) block rescans + offset.
+__device__ __forceinline__ int block_inclusive_scan_1024(int v, int* warp_sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    return x + (warp > 0 ? warp_sums[warp - 1] : 0);
+}
+
+__global__ void __launch_bounds__(1024)
+csr_block_sums_kernel(const int* __restrict__ deg, int* __restrict__ bsum, int N, int nblk) {
+    __shared__ int warp_sums[32];
+    const int* d = deg + (int64_t)blockIdx.y * (N + 1);
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const int incl = block_inclusive_scan_1024(i <= N ? d[i] : 0, warp_sums);
+    if (threadIdx.x == 1023) bsum[(int64_t)blockIdx.y * nblk + blockIdx.x] = incl;
+}
+
+__global__ void __launch_bounds__(1024)
+csr_scan_block_sums_kernel(int* __restrict__ bsum, int nblk) {  // nblk <= 1024*... handled by chunks, carry in smem
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    int* bs = bsum + (int64_t)blockIdx.x * nblk;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblk ? bs[i] : 0;
+        const int incl = block_inclusive_scan_1024(v, warp_sums);
+        const int c = carry;
+        __syncthreads();
+        if (i < nblk) bs[i] = c + incl - v;  // exclusive
+        if (threadIdx.x == 1023) carry = c + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+csr_block_rescan_kernel(int* __restrict__ deg, int* __restrict__ cursor, const int* __restrict__ bsum, int N,
+                        int nblk) {
+    __shared__ int warp_sums[32];
+    int* d = deg + (int64_t)blockIdx.y * (N + 1);
+    int* cur = cursor + (int64_t)blockIdx.y * N;
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const int v = i <= N ? d[i] : 0;
+    const int incl = block_inclusive_scan_1024(v, warp_sums);
+    const int excl = bsum[(int64_t)blockIdx.y * nblk + blockIdx.x] + incl - v;
+    if (i <= N) d[i] = excl;
+    if (i < N) cur[i] = excl;
+}
+
+__global__ void __launch_bounds__(GT)
+csr_fill_kernel(const int64_t* __restrict__ idx, int* __restrict__ cursor, int* __restrict__ list, int S, int K, int N,
+                int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / K;
+        const int k = (int)(t - row * K);
+        const int64_t b = row / S;
+        const int64_t raw = __ldg(idx + t);
+        if (raw < 0 || raw >= N || dup_before(idx + row * K, k, raw)) continue;
+        const int pos = atomicAdd(cursor + b * (int64_t)N + raw, 1);
+        list[b * (int64_t)S * K + pos] = (int)(row - b * S);
+    }
+}
+
+// one thread per (fine point, 4 channels): sorted walk over the reverse-neighbour list
+template <bool VEC4>
+__global__ void __launch_bounds__(GT)
+transition_gather_kernel(const float* __restrict__ points, const int* __restrict__ offs, const int* __restrict__ list,
+                         float* __restrict__ out, float* __restrict__ cnt, int S, int K, int C, int N, int64_t total) {
+    const int CV = VEC4 ? C / 4 : C;
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / CV;  // (b, n)
+        const int v = (int)(t - row * CV);
+        const int64_t b = row / N;
+        const int n = (int)(row - b * N);
+        const int* o = offs + b * (int64_t)(N + 1) + n;
+        const int lo = __ldg(o), hi = __ldg(o + 1);
+        const int* lst = list + b * (int64_t)S * K;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float nz = 0.f;
+        int prev = -1;
+        for (int e = lo; e < hi; ++e) {
+            // next source in ascending order (lists are short: K*S/N entries on average): selection walk
+            int s = 0x7fffffff;
+            for (int f = lo; f < hi; ++f) {
+                const int c = __ldg(lst + f);
+                if (c > prev && c < s) s = c;
+            }
+            prev = s;
+            const float* src = points + ((size_t)b * S + s) * C;
+            if (__ldg(src) != 0.0f) nz += 1.0f;  // count_nonzero of channel 0 (reference :44)
+            if (VEC4) {
+                const float4 p = __ldg(reinterpret_cast<const float4*>(src) + v);
+                acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+            } else {
+                acc.x += __ldg(src + v);
+            }
+        }
+        const float dv = nz == 0.0f ? 1.0f : nz;
+        if (VEC4) {
+            reinterpret_cast<float4*>(out)[t] = make_float4(__fdiv_rn(acc.x, dv), __fdiv_rn(acc.y, dv),
+                                                            __fdiv_rn(acc.z, dv), __fdiv_rn(acc.w, dv));
+        } else {
+            out[t] = __fdiv_rn(acc.x, dv);
+        }
+        if (v == 0) cnt[row] = dv;
+    }
+}
+
 // backward: a pure gather (no atomics): grad_points[row,:] = sum_k grad_out[b, idx[row,k], :] / cnt[b, idx[row,k]]
 template <bool VEC4>
 __global__ void __launch_bounds__(GT)
@@ -320,6 +509,55 @@ MPC_API int mpc_transition_fwd_f32(const float* points, const int64_t* idx, floa
         transition_normalise_kernel<false><<<grid_for(total), GT, 0, st>>>(out, cnt, (int)C, total);
     MPC_LAUNCH_CHECK();
     transition_fix_cnt_kernel<<<grid_for(B * N), GT, 0, st>>>(cnt, B * N);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, float* out, float* cnt,
+                                       int32_t* workspace, int64_t B, int64_t S, int64_t K, int64_t C, int64_t N,
+                                       mpc_stream_t stream) {
+    if (B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (K > 32 || S * K > INT32_MAX) return MPC_ERR_UNSUPPORTED;
+    if (B == 0) return MPC_OK;
+    if (!out || !cnt || !workspace || (S > 0 && (!points || !idx))) return MPC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    // workspace: offsets [B, N+1] | cursor [B, N] | lists [B, S*K]
+    int* offs = workspace;
+    int* cursor = offs + B * (N + 1);
+    int* list = cursor + B * N;
+    MPC_CUDA(cudaMemsetAsync(offs, 0, sizeof(int) * (size_t)B * (N + 1), st));
+    if (S > 0) {
+        const int64_t total = B * S * K;
+        csr_count_kernel<<<grid_for(total), GT, 0, st>>>(idx, offs, (int)S, (int)K, (int)N, total);
+        MPC_LAUNCH_CHECK();
+    }
+    if (N + 1 <= 8192) {
+        csr_scan_kernel<<<(unsigned)B, 1024, 0, st>>>(offs, cursor, (int)N);
+        MPC_LAUNCH_CHECK();
+    } else {  // the block sums live at the head of the (not yet filled) list area
+        const int nblk = (int)ceil_div(N + 1, 1024);
+        if ((int64_t)nblk > S * K) return MPC_ERR_UNSUPPORTED;
+        int* bsum = list;
+        csr_block_sums_kernel<<<dim3((unsigned)nblk, (unsigned)B), 1024, 0, st>>>(offs, bsum, (int)N, nblk);
+        MPC_LAUNCH_CHECK();
+        csr_scan_block_sums_kernel<<<(unsigned)B, 1024, 0, st>>>(bsum, nblk);
+        MPC_LAUNCH_CHECK();
+        csr_block_rescan_kernel<<<dim3((unsigned)nblk, (unsigned)B), 1024, 0, st>>>(offs, cursor, bsum, (int)N, nblk);
+        MPC_LAUNCH_CHECK();
+    }
+    if (S > 0) {
+        const int64_t total = B * S * K;
+        csr_fill_kernel<<<grid_for(total), GT, 0, st>>>(idx, cursor, list, (int)S, (int)K, (int)N, total);
+        MPC_LAUNCH_CHECK();
+    }
+    const bool v4 = C % 4 == 0 && aligned16(points) && aligned16(out);
+    const int64_t total = B * N * (v4 ? C / 4 : C);
+    if (v4)
+        transition_gather_kernel<true><<<grid_for(total), GT, 0, st>>>(points, offs, list, out, cnt, (int)S, (int)K, (int)C,
+                                                                      (int)N, total);
+    else
+        transition_gather_kernel<false><<<grid_for(total), GT, 0, st>>>(points, offs, list, out, cnt, (int)S, (int)K,
+                                                                       (int)C, (int)N, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

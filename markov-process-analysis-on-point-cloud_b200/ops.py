@@ -21,6 +21,7 @@ from ._lib import call, ptr, require_cuda
 _i64 = ctypes.c_int64
 _CHECK_INDEX = os.environ.get("MPC_CHECK_INDEX", "0") == "1"
 _KNN_LIST_LENGTHS = (1, 3, 8, 9, 16, 32)
+_TRANSITION_IMPL = os.environ.get("MPC_TRANSITION", "csr")  # "atomic": red.global scatter form
 
 
 def _f32c(t):
@@ -250,8 +251,13 @@ class _Transition(torch.autograd.Function):
         K = idx.shape[2]
         out = torch.empty(B, n_out, C, dtype=torch.float32, device=points.device)
         cnt = torch.empty(B, n_out, dtype=torch.float32, device=points.device)
-        call("mpc_transition_fwd_f32", ptr(points), ptr(idx), ptr(out), ptr(cnt), _i64(B), _i64(S), _i64(K),
-             _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8))
+        if _TRANSITION_IMPL == "csr":  # gather form over reverse-neighbour lists (deterministic, no float atomics)
+            ws = torch.empty(B * (2 * n_out + 1) + B * S * K, dtype=torch.int32, device=points.device)
+            call("mpc_transition_fwd_csr_f32", ptr(points), ptr(idx), ptr(out), ptr(cnt), ptr(ws), _i64(B), _i64(S),
+                 _i64(K), _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8))
+        else:
+            call("mpc_transition_fwd_f32", ptr(points), ptr(idx), ptr(out), ptr(cnt), _i64(B), _i64(S), _i64(K),
+                 _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8))
         ctx.save_for_backward(idx, cnt)
         ctx.dims = (B, S, K, C, n_out)
         return out

@@ -268,3 +268,24 @@ def test_full_size_properties(mpc, orc, golden_specs):
     torch.testing.assert_close(up(a + 2 * b, knn), up(a, knn) + 2 * up(b, knn), rtol=1e-4, atol=1e-4)
     ones = up(torch.ones(32, 1024, 64, device="cuda"), knn)
     assert ((ones - 1).abs() < 1e-6).logical_or(ones == 0).all()
+
+
+def test_seg_24k_point_block_fwd_bwd(mpc, orc, golden_specs):
+    """BASELINE config 3 shape: one 24 000-point block through the generalised part-seg module (states 24000 /
+    12000 / 6000 / 3000 / 1500; FPS on a thread-block cluster), train mode, forward + backward: finite outputs and
+    gradients, FPS picks distinct points, every state keeps its size."""
+    m = _seg(mpc, orc, golden_specs).train()
+    gen = torch.Generator().manual_seed(24)
+    xyz = (torch.rand(2, 3, 24000, generator=gen) * 2 - 1).cuda()
+    lab = torch.eye(16)[torch.randint(0, 16, (2,), generator=gen)].unsqueeze(1).cuda()
+    rec = []
+    with mpc.ops.index_tape(record=rec):
+        y, _ = m(xyz, lab)
+    assert y.shape == (2, 24000, 50) and torch.isfinite(y).all()
+    y.square().mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    fps = [i for k, i in rec if k == "fps"]
+    assert [f.shape[1] for f in fps] == [12000, 6000, 3000, 1500]
+    for f in fps:
+        s = f.sort(dim=1)[0]
+        assert (s[:, 1:] != s[:, :-1]).all()

@@ -309,6 +309,9 @@ def run_own(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.distributed.init_process_group("nccl", device_id=device)
     mpc = importlib.import_module(PKG)
     mpc._lib.load()

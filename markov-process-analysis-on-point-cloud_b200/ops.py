@@ -136,6 +136,16 @@ def knn_point(nsample, xyz, new_xyz):
     if nsample > N:
         raise RuntimeError("selected index k out of range")  # what torch.topk raises in the reference
     taped = _taped("knn", xyz.device)
+    # inside one forward the same coordinate search can be asked for twice (la0 and la1_up both search the full
+    # cloud in itself): the geometry scope remembers coordinate-space results by operand identity
+    cache = _geo.cache if (_geo is not None and C == 3) else None
+    key = (xyz.data_ptr(), new_xyz.data_ptr(), tuple(xyz.shape), tuple(new_xyz.shape), nsample)
+    if cache is not None and key in cache:
+        dist, idx = cache[key]
+        if taped is not None:
+            idx = taped
+        _record("knn", idx)
+        return dist, idx
     xyz, new_xyz = _f32c(xyz.detach()), _f32c(new_xyz.detach())
     L = _list_length(nsample)  # the kernels keep sorted lists of these lengths; a longer list is sliced
     if L > N:
@@ -146,6 +156,8 @@ def knn_point(nsample, xyz, new_xyz):
          algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
     if L != nsample:
         dist, idx = dist[:, :, :nsample].contiguous(), idx[:, :, :nsample].contiguous()
+    if cache is not None:
+        cache[key] = (dist, idx)
     if taped is not None:
         idx = taped
     _record("knn" if C == 3 else "knnf", idx)  # "knnf": feature-space search (tie-prone, see tests)
@@ -775,6 +787,7 @@ class _GeoScope:
         cur = torch.cuda.current_stream()
         self.stream = _side_streams(cur.device, 8, cur)[-1]  # the last pool stream: never handed to parallel()
         self.stream.wait_stream(cur)  # fork: everything issued so far (the input cloud) is visible
+        self.cache = {}  # coordinate-space kNN results of this forward, by operand identity
 
     def call(self, fn):
         with torch.cuda.stream(self.stream):

@@ -176,7 +176,9 @@ int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t
  *     in `scratch`, 2*C+1 doubles, zero-filled by the call).  If non-NULL, running_mean / running_var [C] get
  *     nn.BatchNorm1d's update (x = (1-momentum)*x + momentum*stat, unbiased variance) and
  *     *num_batches_tracked (device int64) is incremented.
- *   mpc_bn_act_fwd_f32: out = lrelu(gamma * (y - mean) * rsqrt(var + eps) + beta, slope); slope = 1 => no act.
+ *   mpc_bn_act_fwd_f32: out = lrelu(gamma * (y - mean) * rsqrt(var + eps) + beta, slope) [+ residual]; slope = 1 =>
+ *     no act.  residual (optional, [M,C]) folds LocalTrans's `residual + ffn(context)` (:572) into the same pass
+ *     (needs C % 4 == 0 and 1024 % C == 0).
  *   mpc_bn_act_bwd_f32: given grad_out and the saved pre-norm y, writes grad_y [M,C] and grad_gamma/beta [C]
  *     (train = 1: batch statistics take part in the gradient; train = 0: running statistics are constants).
  *     scratch: 2*C doubles.
@@ -189,14 +191,15 @@ int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* r
  * receive mean / biased variance for the backward pass, running statistics are updated like nn.BatchNorm1d.
  * Requires C % 4 == 0, 1024 % C == 0; otherwise MPC_ERR_UNSUPPORTED (use mpc_bn_finalize_f32 + mpc_bn_act_fwd_f32). */
 int mpc_bn_act_fwd_sums_f32(const float* y, const double* sums, const float* gamma, const float* beta, float eps,
-                            float slope, float* out, float* stats, float* running_mean, float* running_var,
-                            int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C, mpc_stream_t stream);
+                            float slope, const float* residual, float* out, float* stats, float* running_mean,
+                            float* running_var, int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C,
+                            mpc_stream_t stream);
 /* out[c] = sum over the M rows of y[:,c] (fp64 accumulation; scratch: 2*C+1 doubles).  The bias gradient of a
  * projection that is not followed by BatchNorm (q / k / v of LocalTrans).  C/4 must be a power of two <= 256. */
 int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t M, int64_t C, mpc_stream_t stream);
 int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, const float* gamma,
-                       const float* beta, float eps, float slope, float* out, int64_t M, int64_t C,
-                       mpc_stream_t stream);
+                       const float* beta, float eps, float slope, const float* residual, float* out, int64_t M,
+                       int64_t C, mpc_stream_t stream);
 int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean, const float* var,
                        const float* gamma, const float* beta, float eps, float slope, int train,
                        float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, int64_t M,

@@ -35,9 +35,9 @@ SIGNATURES = {
     "mpc_attn_xyz_bwd_f32": [_ptr] * 21 + [_i64] * 6 + [_ptr],
     "mpc_bn_stats_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _ptr, _i64, _i64, _ptr],
     "mpc_col_sum_f32": [_ptr, _ptr, _ptr, _i64, _i64, _ptr],
-    "mpc_bn_act_fwd_sums_f32": [_ptr, _ptr, _ptr, _ptr, _f32, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i64, _i64,
-                                _ptr],
-    "mpc_bn_act_fwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _ptr, _i64, _i64, _ptr],
+    "mpc_bn_act_fwd_sums_f32": [_ptr, _ptr, _ptr, _ptr, _f32, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i64,
+                                _i64, _ptr],
+    "mpc_bn_act_fwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _ptr, _ptr, _i64, _i64, _ptr],
     "mpc_bn_act_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _int, _ptr, _ptr, _ptr, _ptr,
                            _i64, _i64, _ptr],
     "mpc_linear_fwd_f32": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr],

@@ -277,7 +277,7 @@ bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, c
 __global__ void __launch_bounds__(256)
 bn_act_fwd_fast_kernel(const float4* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ var,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
-                       float4* __restrict__ out, int C, int64_t total) {
+                       const float4* __restrict__ residual, float4* __restrict__ out, int C, int64_t total) {
     const int c = (threadIdx.x * 4) % C;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
     const float4 vr = __ldg(reinterpret_cast<const float4*>(var + c));
@@ -296,6 +296,15 @@ bn_act_fwd_fast_kernel(const float4* __restrict__ y, const float* __restrict__ m
         z = fmaf(v.w - mu.w, sc.w, be.w); o.w = z > 0.f ? z : z * slope;
         return o;
     };
+    if (residual) {  // out = act(BN(y)) + residual: the `residual + ffn(context)` of LocalTrans in the same pass
+        for (; t < total; t += stride) {
+            float4 o = apply(__ldg(y + t));
+            const float4 r = __ldg(residual + t);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            out[t] = o;
+        }
+        return;
+    }
     for (; t + 3 * stride < total; t += 4 * stride) {  // 4 independent 128-bit loads in flight
         const float4 v0 = __ldg(y + t), v1 = __ldg(y + t + stride), v2 = __ldg(y + t + 2 * stride),
                      v3 = __ldg(y + t + 3 * stride);
@@ -359,7 +368,8 @@ bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restri
 __global__ void __launch_bounds__(256)
 bn_act_fwd_sums_kernel(const float4* __restrict__ y, const double* __restrict__ s1, const double* __restrict__ s2,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
-                       float4* __restrict__ out, float* __restrict__ stats, float* __restrict__ running_mean,
+                       const float4* __restrict__ residual, float4* __restrict__ out, float* __restrict__ stats,
+                       float* __restrict__ running_mean,
                        float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked, float momentum,
                        int64_t M, int C, int64_t total) {
     if (blockIdx.x == 0) {
@@ -389,6 +399,15 @@ bn_act_fwd_sums_kernel(const float4* __restrict__ y, const double* __restrict__ 
         z = fmaf(v.w - mu[3], sc[3], be[3]); o.w = z > 0.f ? z : z * slope;
         return o;
     };
+    if (residual) {
+        for (; t < total; t += stride) {
+            float4 o = apply(__ldg(y + t));
+            const float4 r = __ldg(residual + t);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            out[t] = o;
+        }
+        return;
+    }
     for (; t + 3 * stride < total; t += 4 * stride) {
         const float4 v0 = __ldg(y + t), v1 = __ldg(y + t + stride), v2 = __ldg(y + t + 2 * stride),
                      v3 = __ldg(y + t + 3 * stride);
@@ -535,16 +554,18 @@ MPC_API int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, 
 }
 
 MPC_API int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, const float* gamma,
-                               const float* beta, float eps, float slope, float* out, int64_t M, int64_t C,
-                               mpc_stream_t stream) {
+                               const float* beta, float eps, float slope, const float* residual, float* out, int64_t M,
+                               int64_t C, mpc_stream_t stream) {
     if (!y || !mean || !var || !gamma || !beta || !out || M < 0 || C <= 0) return MPC_ERR_INVALID;
+    if (residual && !(C % 4 == 0 && fast_ew(C) && al16(residual))) return MPC_ERR_UNSUPPORTED;
     if (M == 0) return MPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = C % 4 == 0 && al16(y) && al16(out) && al16(mean) && al16(var) && al16(gamma) && al16(beta);
     const int64_t total = M * (v4 ? C / 4 : C);
     if (v4 && fast_ew(C))
         bn_act_fwd_fast_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float4*>(y), mean, var, gamma, beta,
-                                                              eps, slope, reinterpret_cast<float4*>(out), (int)C, total);
+                                                              eps, slope, reinterpret_cast<const float4*>(residual),
+                                                              reinterpret_cast<float4*>(out), (int)C, total);
     else if (v4)
         bn_act_fwd_kernel<true><<<ew_grid(total), 256, 0, st>>>(y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
     else
@@ -608,15 +629,16 @@ MPC_API int mpc_bn_finalize_f32(const double* sums, float* stats, float* running
 }
 
 MPC_API int mpc_bn_act_fwd_sums_f32(const float* y, const double* sums, const float* gamma, const float* beta, float eps,
-                                    float slope, float* out, float* stats, float* running_mean, float* running_var,
-                                    int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C,
-                                    mpc_stream_t stream) {
+                                    float slope, const float* residual, float* out, float* stats, float* running_mean,
+                                    float* running_var, int64_t* num_batches_tracked, float momentum, int64_t M,
+                                    int64_t C, mpc_stream_t stream) {
     if (!y || !sums || !gamma || !beta || !out || !stats || M <= 0 || C <= 0) return MPC_ERR_INVALID;
-    if (!fast_ew(C) || !al16(y) || !al16(out)) return MPC_ERR_UNSUPPORTED;
+    if (!fast_ew(C) || !al16(y) || !al16(out) || (residual && !al16(residual))) return MPC_ERR_UNSUPPORTED;
     const int64_t total = M * (C / 4);
     bn_act_fwd_sums_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(y), sums, sums + C, gamma, beta, eps, slope, reinterpret_cast<float4*>(out), stats,
-        running_mean, running_var, num_batches_tracked, momentum, M, (int)C, total);
+        reinterpret_cast<const float4*>(y), sums, sums + C, gamma, beta, eps, slope,
+        reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), stats, running_mean, running_var,
+        num_batches_tracked, momentum, M, (int)C, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

@@ -513,7 +513,7 @@ class BNAct(torch.autograd.Function):
             mean, var = running_mean, running_var
         out = torch.empty_like(y)
         call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
-             ctypes.c_float(slope), ptr(out), _i64(M), _i64(C), algo_bytes=2 * M * C * 4)
+             ctypes.c_float(slope), ptr(None), ptr(out), _i64(M), _i64(C), algo_bytes=2 * M * C * 4)
         ctx.save_for_backward(y, mean, var, gamma, beta)
         ctx.cfg = (training, eps, slope)
         return out
@@ -629,10 +629,11 @@ class LinearBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2d, w, bias, gamma, beta, running_mean, running_var, num_batches_tracked, training, momentum,
-                eps, slope):
+                eps, slope, residual):
         M, K = x2d.shape
         N = w.shape[0]
         dev = x2d.device
+        fuse_res = residual is not None and N % 4 == 0 and N <= 1024 and 1024 % N == 0
         y = torch.empty(M, N, dtype=torch.float32, device=dev)
         if training:
             if M <= 1:
@@ -647,22 +648,26 @@ class LinearBNAct(torch.autograd.Function):
             if N % 4 == 0 and N <= 1024 and 1024 % N == 0:
                 # finalise + normalise + activation + running-statistics update in one launch
                 call("mpc_bn_act_fwd_sums_f32", ptr(y), ptr(scratch), ptr(gamma), ptr(beta), ctypes.c_float(eps),
-                     ctypes.c_float(slope), ptr(out), ptr(stats), ptr(running_mean), ptr(running_var),
-                     ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M), _i64(N),
-                     algo_bytes=2 * M * N * 4)
+                     ctypes.c_float(slope), ptr(residual if fuse_res else None), ptr(out), ptr(stats),
+                     ptr(running_mean), ptr(running_var), ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M),
+                     _i64(N), algo_bytes=(3 if fuse_res else 2) * M * N * 4)
             else:
                 call("mpc_bn_finalize_f32", ptr(scratch), ptr(stats), ptr(running_mean), ptr(running_var),
                      ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M), _i64(N))
                 call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
-                     ctypes.c_float(slope), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
+                     ctypes.c_float(slope), ptr(None), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
         else:
             _tc_gemm(x2d, w, bias, y)
             mean, var = running_mean, running_var
             out = torch.empty_like(y)
             call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
-                 ctypes.c_float(slope), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
+                 ctypes.c_float(slope), ptr(residual if fuse_res else None), ptr(out), _i64(M), _i64(N),
+                 algo_bytes=(3 if fuse_res else 2) * M * N * 4)
+        if residual is not None and not fuse_res:
+            out = out + residual
         ctx.save_for_backward(x2d, w, y, mean, var, gamma, beta)
         ctx.cfg = (training, eps, slope, bias is not None)
+        ctx.has_residual = residual is not None
         return out
 
     @staticmethod
@@ -692,24 +697,31 @@ class LinearBNAct(torch.autograd.Function):
                 gw = gy.t().mm(x2d)
         if has_bias and ctx.needs_input_grad[2]:
             gbias = torch.zeros_like(gb) if training else gamma * torch.rsqrt(var + eps) * gb
-        return gx, gw, gbias, gg, gb, None, None, None, None, None, None, None
+        # out = act(BN(y)) + residual: the residual's gradient is the incoming gradient itself
+        gres = grad_out if ctx.has_residual else None
+        return gx, gw, gbias, gg, gb, None, None, None, None, None, None, None, gres
 
 
-def linear_bn_act(x, weight, bias, bn, training, slope):
-    """Linear -> BatchNorm1d(channels) -> LeakyReLU(slope) on any [..., K] input (slope = 1: no activation).
-    `bn` is the nn.BatchNorm1d holding gamma / beta / running statistics."""
+def linear_bn_act(x, weight, bias, bn, training, slope, residual=None):
+    """Linear -> BatchNorm1d(channels) -> LeakyReLU(slope) [+ residual] on any [..., K] input (slope = 1: no
+    activation).  `bn` is the nn.BatchNorm1d holding gamma / beta / running statistics.  `residual` ([..., N]) is
+    added to the result inside the normalise kernel (LocalTrans's `residual + ffn(context)`, Fuse's `conv(acc) + f`)."""
     require_cuda(x)
     shape = x.shape
     x2d = x.reshape(-1, shape[-1])
+    N = weight.shape[0]
     if _tc_ok(x2d, weight):
+        res2d = _f32c(residual.reshape(-1, N)) if residual is not None else None
         out = LinearBNAct.apply(_f32c(x2d), weight.contiguous(), bias, bn.weight, bn.bias, bn.running_mean,
                                 bn.running_var, bn.num_batches_tracked, bool(training), float(bn.momentum),
-                                float(bn.eps), float(slope))
+                                float(bn.eps), float(slope), res2d)
     else:
         y = torch.nn.functional.linear(x2d, weight, bias)
         out = bn_act(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, training,
                      momentum=bn.momentum, eps=bn.eps, slope=slope)
-    return out.view(*shape[:-1], weight.shape[0])
+        if residual is not None:
+            out = out + residual.reshape(-1, N)
+    return out.view(*shape[:-1], N)
 
 
 def linear(x, weight, bias=None):

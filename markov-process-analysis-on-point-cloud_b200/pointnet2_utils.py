@@ -35,12 +35,15 @@ class Linear(nn.Module):
         self.norm2 = nn.BatchNorm1d(out_channels)
         self.act = nn.LeakyReLU(negative_slope=0.2)
 
-    def forward(self, input):
+    def forward(self, input, residual=None):
+        """`residual` (extension, same shape as the output) is added to the result inside the normalise kernel;
+        Linear(x) + r with one pass less.  The reference signature is forward(input)."""
         if self.bn_flag is True:  # LayerNorm branch: never taken by a shipped model
             y = self.norm1(ops.linear(input, self.linear.weight, self.linear.bias))
-            return self.act(y) if self.act_flag is True else y
+            y = self.act(y) if self.act_flag is True else y
+            return y if residual is None else y + residual
         return ops.linear_bn_act(input, self.linear.weight, self.linear.bias, self.norm2, self.training,
-                                 0.2 if self.act_flag is True else 1.0)
+                                 0.2 if self.act_flag is True else 1.0, residual=residual)
 
 
 class LocalTrans(nn.Module):
@@ -83,7 +86,7 @@ class LocalTrans(nn.Module):
             else:
                 center = index_points(features, FPS_idx) if FPS_idx is not None else features
                 residual = self.conv_res(center) if self.residual is True else center
-            return residual + self.ffn(context)
+            return self.ffn(context, residual=residual)
         center = index_points(features, FPS_idx) if FPS_idx is not None else features
         residual = self.conv_res(center) if self.residual is True else center
         if ops.feat_attention_fusable(center, self.q.weight):
@@ -95,7 +98,7 @@ class LocalTrans(nn.Module):
             kv = ops.linear(features, torch.cat((self.k.weight, self.v.weight), 0),
                             torch.cat((self.k.bias, self.v.bias), 0))
             context = ops.AttnFeat.apply(q.contiguous(), kv.contiguous(), idx.contiguous())
-        return residual + self.ffn(context)
+        return self.ffn(context, residual=residual)
 
 
 class LocalMerge(nn.Module):
@@ -187,7 +190,7 @@ class Fuse(nn.Module):
         acc = f[t]
         for part in parts:
             acc = acc + part
-        f[t] = getattr(self, "conv%d" % t)(acc) + f[t]
+        f[t] = getattr(self, "conv%d" % t)(acc, residual=f[t])
         return tuple(f)
 
 

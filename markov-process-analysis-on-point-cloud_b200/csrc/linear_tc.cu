@@ -165,6 +165,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __shared__ uint32_t tmem_base_slot;
     __shared__ float stat_red[2][4][32];
 
+    // programmatic dependent launch: let the next kernel in the stream start its own prologue now ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // dynamic smem is requested with 1024 B of slack and aligned here (swizzle-128B atoms need 1024 B alignment)
     // (pointer arithmetic on the __shared__ array, not an integer round-trip, so accesses stay LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -202,6 +204,9 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
     }
+    // ... and wait here, after the part of our prologue that touches no global data (barrier init, descriptor
+    // prefetch), until the kernel before us has completed and its writes are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();  // barriers initialised: the TMA producer and the splitters start right away
     uint32_t tmem_base = 0;
     if (warp == 9) {  // TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns
@@ -558,6 +563,11 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 
 static long long* g_trace = nullptr;  // debug only, see mpc_debug_trace_buffer
 
+// Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream
+// is still draining (it blocks in griddepcontrol.wait before reading anything the predecessor wrote).
+static cudaError_t launch_pdl(int grid, size_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
+                              const CUtensorMap& y, const Params& p);
+
 // Shared-memory budget (224 KB opt-in, 1 KB alignment slack): as many operand stages as fit; a second epilogue
 // staging slab only if at least 3 operand stages remain (TMA latency ~1.3 us needs >= 3 stages in flight).
 static void pick_pipeline(int stage_bytes, int* stages, int* epi_bufs) {
@@ -579,6 +589,21 @@ static cudaError_t ensure_smem_optin() {
     cudaError_t e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     done = e == cudaSuccess;
     return e;
+}
+
+static cudaError_t launch_pdl(int grid, size_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
+                              const CUtensorMap& y, const Params& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, linear_3xtf32_kernel, a, b, y, p);
 }
 
 }  // namespace tc
@@ -637,8 +662,7 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     MPC_CUDA(ensure_smem_optin());
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
-    linear_3xtf32_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, p);
-    MPC_LAUNCH_CHECK();
+    MPC_CUDA(launch_pdl(grid, smem, (cudaStream_t)stream, map_a, map_b, map_y, p));
     return MPC_OK;
 }
 
@@ -703,8 +727,7 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     MPC_CUDA(ensure_smem_optin());
     const int items = tiles * splits;
     const int grid = items < kNumSMs ? items : kNumSMs;
-    linear_3xtf32_kernel<<<grid, THREADS, smem, st>>>(map_a, map_b, map_y, p);
-    MPC_LAUNCH_CHECK();
+    MPC_CUDA(launch_pdl(grid, smem, st, map_a, map_b, map_y, p));
     return MPC_OK;
 }
 
@@ -760,7 +783,6 @@ MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, i
     MPC_CUDA(ensure_smem_optin());
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
-    linear_3xtf32_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, p);
-    MPC_LAUNCH_CHECK();
+    MPC_CUDA(launch_pdl(grid, smem, (cudaStream_t)stream, map_a, map_b, map_y, p));
     return MPC_OK;
 }

@@ -292,10 +292,12 @@ MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, in
     if (n <= 2048) return launch_cta<8, 256>(xyz, start, out, b, n, np, st);
     if (n <= 4096) return launch_cta<8, 512>(xyz, start, out, b, n, np, st);
     if (n <= 8192) return launch_cta<8, 1024>(xyz, start, out, b, n, np, st);
-    // cluster: CS CTAs x 1024 threads x 8 points
-    if (n <= 2 * 8192) return launch_cluster<8, 1024>(xyz, start, out, b, n, np, 2, st);
-    if (n <= 4 * 8192) return launch_cluster<8, 1024>(xyz, start, out, b, n, np, 4, st);
-    if (n <= 8 * 8192) return launch_cluster<8, 1024>(xyz, start, out, b, n, np, 8, st);
+    // cluster: a round costs (points per thread) x ~12 instructions per warp plus one cluster barrier, so mid-sized
+    // clouds are spread thinly (512 threads x 8 points per CTA) over up to 16 CTAs; larger ones use fatter CTAs
+    if (n <= 2 * 4096) return launch_cluster<8, 512>(xyz, start, out, b, n, np, 2, st);
+    if (n <= 4 * 4096) return launch_cluster<8, 512>(xyz, start, out, b, n, np, 4, st);
+    if (n <= 8 * 4096) return launch_cluster<8, 512>(xyz, start, out, b, n, np, 8, st);
+    if (n <= 16 * 4096) return launch_cluster<8, 512>(xyz, start, out, b, n, np, 16, st);
     if (n <= 16 * 8192) return launch_cluster<8, 1024>(xyz, start, out, b, n, np, 16, st);
     if (n <= 16 * 16384) return launch_cluster<16, 1024>(xyz, start, out, b, n, np, 16, st);
     return MPC_ERR_UNSUPPORTED;

@@ -268,7 +268,7 @@ def rebind_gemm_calls(mpc, calls, device):
             ldx, ldw, ldy, M, K, N = (val(a[i]) for i in (1, 3, 6, 8, 9, 10))
             x, w, y = buf(M, ldx), buf(N, ldw), buf(M, ldy)
             bias = torch.randn(N, device=device) if val(a[4]) else None
-            sc = torch.zeros(2 * N + 1, dtype=torch.float64, device=device) if val(a[7]) else None
+            sc = torch.zeros(2 * N + 2, dtype=torch.float64, device=device) if val(a[7]) else None
             keep += [x, w, y, bias, sc]
             P = mpc._lib.ptr
             na = (P(x), a[1], P(w), a[3], P(bias), P(y), a[6], P(sc), a[8], a[9], a[10])
@@ -277,13 +277,15 @@ def rebind_gemm_calls(mpc, calls, device):
             g, w, x = buf(M, ldg), buf(N, ldw), buf(M, ldx)
             keep += [g, w, x]
             P = mpc._lib.ptr
-            na = (P(g), a[1], P(w), a[3], P(x), a[5], a[6], a[7], a[8])
+            zb = torch.empty(max(val(a[10]), 4), dtype=torch.float32, device=device) if val(a[9]) else None
+            keep.append(zb)
+            na = (P(g), a[1], P(w), a[3], P(x), a[5], a[6], a[7], a[8], P(zb), a[10])
         elif name == "mpc_linear_wgrad_f32":
             ldg, ldx, ldw, M, K, N = (val(a[i]) for i in (1, 3, 5, 6, 7, 8))
             g, x, w = buf(M, ldg), buf(M, ldx), buf(N, ldw)
             keep += [g, x, w]
             P = mpc._lib.ptr
-            na = (P(g), a[1], P(x), a[3], P(w), a[5], a[6], a[7], a[8])
+            na = (P(g), a[1], P(x), a[3], P(w), a[5], a[6], a[7], a[8], a[9])
         else:
             return None, None  # not a GEMM entry point: cannot rebuild its buffers generically
         out.append((name, na, by))

@@ -172,8 +172,11 @@ int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t
  * Shared-MLP block tail.  Replaces the BatchNorm1d-over-channels + LeakyReLU(0.2) of `Linear.forward`,
  * R/modules/pointnet2_utils.py:413-425, on the [M,C] view (M = all leading axes), without the two
  * permute().contiguous() copies of :420.
+ * SCRATCH CONTRACT (all `scratch` / `sums` / `stat_scratch` arguments below): a caller-owned buffer of 2*C+2
+ *   doubles that is ZERO ON ENTRY and is left ZERO ON EXIT by the call that consumes it (the last CTA to finish
+ *   clears it), so a persistent per-layer buffer allocated zeroed once never needs a memset launch again.
  *   mpc_bn_stats_f32: stats[0:C] = mean, stats[C:2C] = biased variance of y over M rows (fp64 accumulation
- *     in `scratch`, 2*C+1 doubles, zero-filled by the call).  If non-NULL, running_mean / running_var [C] get
+ *     in `scratch`).  If non-NULL, running_mean / running_var [C] get
  *     nn.BatchNorm1d's update (x = (1-momentum)*x + momentum*stat, unbiased variance) and
  *     *num_batches_tracked (device int64) is incremented.
  *   mpc_bn_act_fwd_f32: out = lrelu(gamma * (y - mean) * rsqrt(var + eps) + beta, slope) [+ residual]; slope = 1 =>
@@ -181,7 +184,8 @@ int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t
  *     (needs C % 4 == 0 and 1024 % C == 0).
  *   mpc_bn_act_bwd_f32: given grad_out and the saved pre-norm y, writes grad_y [M,C] and grad_gamma/beta [C]
  *     (train = 1: batch statistics take part in the gradient; train = 0: running statistics are constants).
- *     scratch: 2*C doubles.
+ *     zero_buf (optional, zero_count floats, 16-byte aligned, count % 4 == 0) is cleared by the same launches on
+ *     behalf of a later call in the stream (the split-reduction target of mpc_linear_wgrad_f32).
  * ------------------------------------------------------------------------------------------------- */
 int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float momentum, double* scratch, int64_t M, int64_t C,
@@ -189,12 +193,13 @@ int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* r
 /* Training-mode forward in one launch from the column sums the GEMM epilogue left in `sums` (sum, then sum of
  * squares, C doubles each): mean / variance are derived on the fly, out = lrelu(BN(y)), stats[0:C] / stats[C:2C]
  * receive mean / biased variance for the backward pass, running statistics are updated like nn.BatchNorm1d.
- * Requires C % 4 == 0, 1024 % C == 0; otherwise MPC_ERR_UNSUPPORTED (use mpc_bn_finalize_f32 + mpc_bn_act_fwd_f32). */
-int mpc_bn_act_fwd_sums_f32(const float* y, const double* sums, const float* gamma, const float* beta, float eps,
+ * Requires C % 4 == 0, 1024 % C == 0; otherwise MPC_ERR_UNSUPPORTED (use mpc_bn_finalize_f32 + mpc_bn_act_fwd_f32).
+ * Consumes `sums` (clears it, see the scratch contract). */
+int mpc_bn_act_fwd_sums_f32(const float* y, double* sums, const float* gamma, const float* beta, float eps,
                             float slope, const float* residual, float* out, float* stats, float* running_mean,
                             float* running_var, int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C,
                             mpc_stream_t stream);
-/* out[c] = sum over the M rows of y[:,c] (fp64 accumulation; scratch: 2*C+1 doubles).  The bias gradient of a
+/* out[c] = sum over the M rows of y[:,c] (fp64 accumulation; scratch contract above).  The bias gradient of a
  * projection that is not followed by BatchNorm (q / k / v of LocalTrans).  C/4 must be a power of two <= 256. */
 int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t M, int64_t C, mpc_stream_t stream);
 int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, const float* gamma,
@@ -202,8 +207,8 @@ int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, cons
                        int64_t C, mpc_stream_t stream);
 int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean, const float* var,
                        const float* gamma, const float* beta, float eps, float slope, int train,
-                       float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, int64_t M,
-                       int64_t C, mpc_stream_t stream);
+                       float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, float* zero_buf,
+                       int64_t zero_count, int64_t M, int64_t C, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Shared-MLP projection on the tensor cores.  Replaces the nn.Linear inside `Linear` and the q/k/v projections
@@ -212,25 +217,29 @@ int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean,
  * tcgen05.mma kind::tf32 with the 3xTF32 operand split (hi/lo), fp32 accumulation in TMEM, TMA-fed: fp32-level
  * accuracy (the parity tolerance is rtol 1e-4).  Requires K % 32 == 0, ldx % 4 == ldw % 4 == 0, 16-byte aligned
  * x and w; other shapes return MPC_ERR_UNSUPPORTED and the host falls back to the library GEMM.
- * stat_scratch (optional, 2*N+1 doubles, zero-filled by the call): the epilogue also accumulates the per-column sum
- * and sum of squares of y over the M rows -- the BatchNorm batch statistics of the `Linear` block -- from the tile
- * while it is still in shared memory; mpc_bn_finalize_f32 turns them into mean / variance / running statistics.
+ * stat_scratch (optional, scratch contract above: zero on entry; this call only accumulates): the epilogue adds the
+ * per-column sum and sum of squares of y over the M rows -- the BatchNorm batch statistics of the `Linear` block --
+ * from the tile while it is still in shared memory, one atomic per column per CTA; mpc_bn_act_fwd_sums_f32 or
+ * mpc_bn_finalize_f32 consume (and clear) them.
  * ------------------------------------------------------------------------------------------------- */
 int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
                        int64_t ldy, double* stat_scratch, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
 /* stats[0:C] = mean, stats[C:2C] = biased variance from sums[0:C] = sum(y), sums[C:2C] = sum(y*y) over M rows;
- * running statistics / num_batches_tracked updated like nn.BatchNorm1d when non-NULL. */
-int mpc_bn_finalize_f32(const double* sums, float* stats, float* running_mean, float* running_var,
+ * running statistics / num_batches_tracked updated like nn.BatchNorm1d when non-NULL.  Consumes (clears) `sums`. */
+int mpc_bn_finalize_f32(double* sums, float* stats, float* running_mean, float* running_var,
                         int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C, mpc_stream_t stream);
 /* Input gradient of the same layer:  gx[M,K] = gy[M,N] w[N,K].  The weight matrix is consumed as stored (MN-major
- * tensor-core operand), no transposed copy.  K % 32 == 0, ldg % 4 == 0. */
+ * tensor-core operand), no transposed copy.  K % 32 == 0, ldg % 4 == 0.  zero_buf (optional, zero_count floats,
+ * 16-byte aligned, count % 4 == 0) is cleared by the same launch on behalf of the mpc_linear_wgrad_f32 that follows. */
 int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t ldw, float* gx, int64_t ldx,
-                         int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+                         int64_t M, int64_t K, int64_t N, float* zero_buf, int64_t zero_count, mpc_stream_t stream);
 /* Weight gradient of the same layer (what autograd derives for nn.Linear):  gw[N,K] = gy[M,N]^T x[M,K].
  * Same 3xTF32 tcgen05 pipeline with MN-major operand descriptors (no transposed copies), the reduction over the M
- * points split across the SMs and combined with red.global.add into gw (zero-filled by the call).  K % 32 == 0. */
+ * points split across the SMs and combined with TMA reduce-add into gw.  gw_is_zero = 1: an earlier call in the
+ * stream already cleared gw (zero_buf of mpc_bn_act_bwd_f32 / mpc_linear_dgrad_f32); 0: this call clears it with a
+ * memset first.  K % 32 == 0. */
 int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t ldx, float* gw, int64_t ldw,
-                         int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+                         int64_t M, int64_t K, int64_t N, int64_t gw_is_zero, mpc_stream_t stream);
 
 /* Debug facility (not part of the data path): when set to a device buffer of 1024 int64, CTA 0 of the tensor-core
  * kernels records a clock64() timeline per warp role (producer / splitter / MMA / epilogue: 256 slots each).

@@ -32,6 +32,28 @@ __device__ __forceinline__ float4 ld4(const float* p, bool vec) {
     return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Scratch contract (include/mpc_b200.h): the fp64 scratch [2C sums | ticket A | ticket B] is zero on entry and the
+// kernel that consumes the sums leaves it zero again -- its last CTA to finish (ticket B) clears it -- so no memset
+// launch is needed between uses.  Must be reached by every thread of every CTA (1-D blocks).
+__device__ __forceinline__ void clear_scratch_when_last(double* scratch, int C) {
+    __shared__ bool last_cta;
+    __threadfence();  // this CTA's reads of the sums are done before its ticket is drawn
+    __syncthreads();
+    if (threadIdx.x == 0)
+        last_cta = atomicAdd(reinterpret_cast<unsigned*>(scratch + 2 * C + 1), 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (last_cta)
+        for (int i = threadIdx.x; i < 2 * C + 2; i += blockDim.x) scratch[i] = 0.0;
+}
+// Clears a buffer on behalf of a LATER launch in the stream (the weight-gradient GEMM's split-reduction target).
+__device__ __forceinline__ void zero_service(float* buf, int64_t count) {
+    if (!buf) return;
+    float4* b4 = reinterpret_cast<float4*>(buf);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count / 4; i += (int64_t)gridDim.x * blockDim.x)
+        b4[i] = z;
+}
+
 // Reduce 4 channel partials (a: 4 values, b: 4 values) over the BN_TY row slots and add to the fp64 scratch.
 __device__ __forceinline__ void block_reduce_to_scratch(float4 a, float4 b, double* __restrict__ sa,
                                                         double* __restrict__ sb, int cbase, int C) {
@@ -203,6 +225,9 @@ col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, c
             } else {
                 for (int c = threadIdx.x; c < C; c += RT) fin.stats[c] = (float)__ldcg(s1 + c);
             }
+            // scratch contract: every other CTA has drawn its ticket, so nothing touches the sums any more
+            for (int c = threadIdx.x; c < C; c += RT) s1[c] = s2[c] = 0.0;
+            if (threadIdx.x == 0) *ticket = 0u;
         }
     }
 }
@@ -220,7 +245,7 @@ static inline unsigned col_reduce_grid(int64_t M, int CV) {
 }
 
 // mean / biased variance, plus nn.BatchNorm1d's running-statistics update (unbiased variance, momentum)
-__global__ void bn_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2,
+__global__ void bn_finalize_kernel(double* __restrict__ s1, double* __restrict__ s2,
                                    float* __restrict__ stats, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked,
                                    float momentum, int64_t M, int C) {
@@ -232,6 +257,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ s1, const double* 
     var = var < 0.0 ? 0.0 : var;
     stats[c] = (float)mean;
     stats[C + c] = (float)var;
+    s1[c] = 0.0;  // scratch contract: each thread clears the channel it consumed
+    s2[c] = 0.0;
     if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
     if (running_var) {
         const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
@@ -320,9 +347,10 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restrict__ y,
                          const float* __restrict__ mean, const float* __restrict__ var,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
-                         int train, const double* __restrict__ s1, const double* __restrict__ s2,
-                         float4* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta, int64_t M,
-                         int C, int64_t total) {
+                         int train, double* __restrict__ s1, double* __restrict__ s2,
+                         float4* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                         float* __restrict__ zero_buf, int64_t zero_count, int64_t M, int C, int64_t total) {
+    zero_service(zero_buf, zero_count);
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < C; i += 256) {
             gbeta[i] = (float)s1[i];
@@ -360,13 +388,14 @@ bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restri
         gy[t + stride] = apply(y1, g1);
     }
     for (; t < total; t += stride) gy[t] = apply(__ldg(y + t), __ldg(gout + t));
+    clear_scratch_when_last(s1, C);
 }
 
 // Training forward straight from the GEMM epilogue's column sums: every thread derives mean / variance of its 4
 // channels from the fp64 sums (so the separate finalise launch disappears); CTA 0 also publishes mean / biased
 // variance for the backward pass and applies nn.BatchNorm1d's running-statistics update.
 __global__ void __launch_bounds__(256)
-bn_act_fwd_sums_kernel(const float4* __restrict__ y, const double* __restrict__ s1, const double* __restrict__ s2,
+bn_act_fwd_sums_kernel(const float4* __restrict__ y, double* __restrict__ s1, double* __restrict__ s2,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
                        const float4* __restrict__ residual, float4* __restrict__ out, float* __restrict__ stats,
                        float* __restrict__ running_mean,
@@ -406,17 +435,18 @@ bn_act_fwd_sums_kernel(const float4* __restrict__ y, const double* __restrict__ 
             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
             out[t] = o;
         }
-        return;
+    } else {
+        for (; t + 3 * stride < total; t += 4 * stride) {
+            const float4 v0 = __ldg(y + t), v1 = __ldg(y + t + stride), v2 = __ldg(y + t + 2 * stride),
+                         v3 = __ldg(y + t + 3 * stride);
+            out[t] = apply(v0);
+            out[t + stride] = apply(v1);
+            out[t + 2 * stride] = apply(v2);
+            out[t + 3 * stride] = apply(v3);
+        }
+        for (; t < total; t += stride) out[t] = apply(__ldg(y + t));
     }
-    for (; t + 3 * stride < total; t += 4 * stride) {
-        const float4 v0 = __ldg(y + t), v1 = __ldg(y + t + stride), v2 = __ldg(y + t + 2 * stride),
-                     v3 = __ldg(y + t + 3 * stride);
-        out[t] = apply(v0);
-        out[t + stride] = apply(v1);
-        out[t + 2 * stride] = apply(v2);
-        out[t + 3 * stride] = apply(v3);
-    }
-    for (; t < total; t += stride) out[t] = apply(__ldg(y + t));
+    clear_scratch_when_last(s1, C);
 }
 
 static inline bool fast_ew(int64_t C) { return C % 4 == 0 && C <= 1024 && 1024 % C == 0; }
@@ -473,9 +503,10 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float eps, float slope, int train, const double* __restrict__ s1, const double* __restrict__ s2,
-                    float* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta, int64_t M, int C,
-                    int64_t total) {
+                    float eps, float slope, int train, double* __restrict__ s1, double* __restrict__ s2,
+                    float* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                    float* __restrict__ zero_buf, int64_t zero_count, int64_t M, int C, int64_t total) {
+    zero_service(zero_buf, zero_count);
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < C; c += 256) {
             gbeta[c] = (float)s1[c];
@@ -512,6 +543,7 @@ bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ y,
         else
             gy[t] = o[0];
     }
+    clear_scratch_when_last(s1, C);
 }
 
 static inline unsigned ew_grid(int64_t total) {
@@ -530,7 +562,6 @@ MPC_API int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, 
                              mpc_stream_t stream) {
     if (!y || !stats || !scratch || M <= 0 || C <= 0 || C > INT32_MAX / 4) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * (size_t)C + 1), st));
     if (fast_cv(C) && al16(y)) {
         const int CV = (int)(C / 4);
         StatsFinal fin{stats, running_mean, running_var, num_batches_tracked, momentum};
@@ -576,13 +607,13 @@ MPC_API int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* v
 
 MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean, const float* var,
                                const float* gamma, const float* beta, float eps, float slope, int train,
-                               float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, int64_t M,
-                               int64_t C, mpc_stream_t stream) {
+                               float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, float* zero_buf,
+                               int64_t zero_count, int64_t M, int64_t C, mpc_stream_t stream) {
     if (!grad_out || !y || !mean || !var || !gamma || !beta || !grad_y || !grad_gamma || !grad_beta || !scratch)
         return MPC_ERR_INVALID;
     if (M <= 0 || C <= 0) return MPC_ERR_INVALID;
+    if (zero_buf && (!al16(zero_buf) || (zero_count & 3) || zero_count < 0)) return MPC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)C, st));
     const bool v4 = C % 4 == 0 && al16(y) && al16(grad_out) && al16(grad_y);
     const Dims d = bn_dims(M, (int)(v4 ? C / 4 : C));
     const int64_t total = M * (v4 ? C / 4 : C);
@@ -600,25 +631,25 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
         if (fast_ew(C))
             bn_bwd_apply_fast_kernel<<<ew_grid(total), 256, 0, st>>>(
                 reinterpret_cast<const float4*>(grad_out), reinterpret_cast<const float4*>(y), mean, var, gamma, beta, eps,
-                slope, train, scratch, scratch + C, reinterpret_cast<float4*>(grad_y), grad_gamma, grad_beta, M, (int)C,
-                total);
+                slope, train, scratch, scratch + C, reinterpret_cast<float4*>(grad_y), grad_gamma, grad_beta, zero_buf,
+                zero_count, M, (int)C, total);
         else
             bn_bwd_apply_kernel<true><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
                                                                      train, scratch, scratch + C, grad_y, grad_gamma,
-                                                                     grad_beta, M, (int)C, total);
+                                                                     grad_beta, zero_buf, zero_count, M, (int)C, total);
     } else {
         bn_bwd_sums_kernel<false><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, scratch,
                                                              scratch + C, M, (int)C);
         MPC_LAUNCH_CHECK();
         bn_bwd_apply_kernel<false><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
                                                                   train, scratch, scratch + C, grad_y, grad_gamma,
-                                                                  grad_beta, M, (int)C, total);
+                                                                  grad_beta, zero_buf, zero_count, M, (int)C, total);
     }
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }
 
-MPC_API int mpc_bn_finalize_f32(const double* sums, float* stats, float* running_mean, float* running_var,
+MPC_API int mpc_bn_finalize_f32(double* sums, float* stats, float* running_mean, float* running_var,
                                 int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C,
                                 mpc_stream_t stream) {
     if (!sums || !stats || M <= 0 || C <= 0) return MPC_ERR_INVALID;
@@ -628,7 +659,7 @@ MPC_API int mpc_bn_finalize_f32(const double* sums, float* stats, float* running
     return MPC_OK;
 }
 
-MPC_API int mpc_bn_act_fwd_sums_f32(const float* y, const double* sums, const float* gamma, const float* beta, float eps,
+MPC_API int mpc_bn_act_fwd_sums_f32(const float* y, double* sums, const float* gamma, const float* beta, float eps,
                                     float slope, const float* residual, float* out, float* stats, float* running_mean,
                                     float* running_var, int64_t* num_batches_tracked, float momentum, int64_t M,
                                     int64_t C, mpc_stream_t stream) {
@@ -647,7 +678,6 @@ MPC_API int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t
     if (!y || !out || !scratch || M <= 0 || C <= 0) return MPC_ERR_INVALID;
     if (!fast_cv(C) || !al16(y)) return MPC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    MPC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * (size_t)C + 1), st));
     const int CV = (int)(C / 4);
     StatsFinal fin{out, nullptr, nullptr, nullptr, 0.f};
     col_reduce_kernel<2><<<col_reduce_grid(M, CV), RT, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,

@@ -230,10 +230,21 @@ fps_generic_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ st
     }
 }
 
+// FPS is a latency chain: every CTA wants an SM's issue slots to itself.  Small CTAs (128-512 threads) launched
+// while other kernels hold most SMs get STACKED several to an SM by the block scheduler (measured: 3.3x slower
+// rounds inside the multi-stream training step).  Asking for enough dynamic shared memory that only
+// ceil(ctas / SMs) of them fit on one SM spreads the clouds over distinct SMs.
+static size_t spread_smem(size_t needed, int ctas) {
+    const int per_sm = (ctas + kNumSMs - 1) / kNumSMs;
+    if (per_sm >= 8) return needed;
+    const size_t want = (size_t)(226 * 1024) / (per_sm + 1) + 1024;
+    return needed > want ? needed : want;
+}
+
 template <int PPT, int THREADS>
 static int launch_cta(const float* xyz, const int64_t* start, int64_t* out, int B, int N, int npoint,
                       cudaStream_t st) {
-    size_t smem = (size_t)N * 3 * sizeof(float);
+    size_t smem = spread_smem((size_t)N * 3 * sizeof(float), B);
     auto kern = fps_cta_kernel<PPT, THREADS>;
     if (smem > 40 * 1024)  // static shared memory (warp slots) counts against the default 48 KB too
         MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -245,7 +256,7 @@ static int launch_cta(const float* xyz, const int64_t* start, int64_t* out, int 
 template <int PPT, int THREADS>
 static int launch_cluster(const float* xyz, const int64_t* start, int64_t* out, int B, int N, int npoint,
                           int CS, cudaStream_t st) {
-    size_t smem = (size_t)PPT * THREADS * 3 * sizeof(float);
+    size_t smem = spread_smem((size_t)PPT * THREADS * 3 * sizeof(float), B * CS);
     auto kern = fps_cluster_kernel<PPT, THREADS>;
     MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CS > 8) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

@@ -147,7 +147,9 @@ struct Params {
     int tma_out;      // 1: results leave through a swizzled staging slab + TMA store / TMA reduce-add
     int epi_bufs;     // staging slabs (1 or 2): with 2 the TMA store of slab i overlaps the fill of slab i+1
     double* stat_sum; // optional [2][N]: per-column sum and sum of squares of y (BatchNorm batch statistics),
-                      // accumulated from the staged tile while it is still in shared memory
+                      // accumulated from the staged tile while it is still in shared memory (must be zero on entry)
+    float4* zero_ptr; // optional: buffer this launch clears on behalf of a LATER launch in the same stream (the
+    long long zero_n4;//   split-reduction target of the weight-gradient GEMM that follows a dgrad), in float4 units
 };
 
 // debug timeline: role r in [0,4) records up to 255 timestamps
@@ -164,6 +166,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __shared__ uint64_t bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ float stat_red[2][4][32];
+    __shared__ double stat_acc[2][256];  // per-CTA column sums over all of this CTA's tiles (one atomic per column)
 
     // programmatic dependent launch: let the next kernel in the stream start its own prologue now ...
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -209,6 +212,11 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();  // barriers initialised: the TMA producer and the splitters start right away
     uint32_t tmem_base = 0;
+    if (p.zero_ptr && warp < 8) {  // epilogue + splitter warps are idle until the first TMA round trip completes
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.zero_n4; i += (long long)gridDim.x * 256)
+            p.zero_ptr[i] = z;
+    }
     if (warp == 9) {  // TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                      "r"(512));
@@ -255,7 +263,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
         }
     } else if (warp >= 4 && warp < 8) {
-        // ===== splitters: x -> (hi, lo) in place, 16 bytes per thread per step, conflict-free =====
+        // ===== splitters: lo = x - trunc_tf32(x) next to the raw tile, 16 bytes per thread per step =====
         const int t = threadIdx.x - 128;
         int it = 0, tn_ = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -271,12 +279,13 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 uint4* a_lo = reinterpret_cast<uint4*>(st + A_TILE_BYTES);
                 uint4* b_hi = reinterpret_cast<uint4*>(st + 2 * A_TILE_BYTES);
                 uint4* b_lo = reinterpret_cast<uint4*>(st + 2 * A_TILE_BYTES + b_tile_bytes);
-                auto split = [](uint4 v, uint4& hi, uint4& lo) {
-                    hi.x = v.x & TF32_MASK; hi.y = v.y & TF32_MASK; hi.z = v.z & TF32_MASK; hi.w = v.w & TF32_MASK;
-                    lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x)) & TF32_MASK;
-                    lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y)) & TF32_MASK;
-                    lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z)) & TF32_MASK;
-                    lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w)) & TF32_MASK;
+                // kind::tf32 reads the top 19 bits of each 32-bit container and ignores the rest, so the tile as
+                // TMA delivered it already IS the hi term; only lo = x - trunc(x) has to be materialised
+                auto split = [](uint4 v, uint4& lo) {
+                    lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & TF32_MASK));
+                    lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & TF32_MASK));
+                    lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & TF32_MASK));
+                    lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & TF32_MASK));
                 };
                 {   // all loads first (independent), then split + store: one shared-memory latency, not eight
                     uint4 v[A_TILE_BYTES / 16 / 128];
@@ -284,9 +293,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) v[i] = a_hi[t + i * 128];
 #pragma unroll
                     for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
-                        uint4 hi, lo;
-                        split(v[i], hi, lo);
-                        a_hi[t + i * 128] = hi;
+                        uint4 lo;
+                        split(v[i], lo);
                         a_lo[t + i * 128] = lo;
                     }
                 }
@@ -298,9 +306,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (i0 + u * 128 < b_tile_bytes / 16) {
-                            uint4 hi, lo;
-                            split(v[u], hi, lo);
-                            b_hi[i0 + u * 128] = hi;
+                            uint4 lo;
+                            split(v[u], lo);
                             b_lo[i0 + u * 128] = lo;
                         }
                 }
@@ -357,9 +364,23 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows 32w..32w+31 of the tile =====
         int tile_it = 0, tn_ = 0, slab_it = 0;
+        int stat_n0 = -1;  // column offset the per-CTA statistics accumulators currently belong to
+        auto stat_flush = [&]() {  // warp 0 only: lane owns columns lane, lane + 32, ...
+            if (stat_n0 < 0) return;
+            for (int i = lane; i < p.block_n; i += 32)
+                if (stat_n0 + i < p.N) {
+                    atomicAdd(p.stat_sum + stat_n0 + i, stat_acc[0][i]);
+                    atomicAdd(p.stat_sum + p.N + stat_n0 + i, stat_acc[1][i]);
+                }
+        };
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             int mt, nt, kc0, kc1;
             decode(tile, mt, nt, kc0, kc1);
+            if (p.stat_sum && warp == 0 && nt * p.block_n != stat_n0) {
+                stat_flush();
+                stat_n0 = nt * p.block_n;
+                for (int i = lane; i < p.block_n; i += 32) stat_acc[0][i] = stat_acc[1][i] = 0.0;
+            }
             const int as = tile_it & 1;
             const uint32_t aph = (tile_it >> 1) & 1;
             const int row = mt * BLOCK_M + warp * 32 + lane;
@@ -430,13 +451,13 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         stat_red[0][warp][lane] = su;
                         stat_red[1][warp][lane] = sq2;
                         epi_barrier();
-                        if (warp == 0 && n0 + c + lane < p.N) {
+                        if (warp == 0) {
                             const double a = (double)stat_red[0][0][lane] + (double)stat_red[0][1][lane] +
                                              (double)stat_red[0][2][lane] + (double)stat_red[0][3][lane];
                             const double b = (double)stat_red[1][0][lane] + (double)stat_red[1][1][lane] +
                                              (double)stat_red[1][2][lane] + (double)stat_red[1][3][lane];
-                            atomicAdd(p.stat_sum + n0 + c + lane, a);
-                            atomicAdd(p.stat_sum + p.N + n0 + c + lane, b);
+                            stat_acc[0][c + lane] += a;
+                            stat_acc[1][c + lane] += b;
                         }
                     }
                 }
@@ -479,6 +500,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             mbar_arrive(&bar_tmem_empty[as]);
             if (threadIdx.x == 0) MPC_TRACE(3, tn_);
         }
+        if (p.stat_sum && warp == 0) stat_flush();
     }
 
     if (threadIdx.x == 0 && p.tma_out) bulk_wait0();  // staged results have left shared memory
@@ -571,7 +593,7 @@ static cudaError_t launch_pdl(int grid, size_t smem, cudaStream_t st, const CUte
 // Shared-memory budget (224 KB opt-in, 1 KB alignment slack): as many operand stages as fit; a second epilogue
 // staging slab only if at least 3 operand stages remain (TMA latency ~1.3 us needs >= 3 stages in flight).
 static void pick_pipeline(int stage_bytes, int* stages, int* epi_bufs) {
-    const int budget = 222 * 1024 - EPI_BIAS_BYTES;
+    const int budget = 217 * 1024 - EPI_BIAS_BYTES;  // 227 KB per CTA minus static shared memory and alignment slack
     int s2 = (budget - 2 * STAGING_BYTES) / stage_bytes;
     int s1 = (budget - STAGING_BYTES) / stage_bytes;
     if (s2 >= 3) {
@@ -586,7 +608,7 @@ static void pick_pipeline(int stage_bytes, int* stages, int* epi_bufs) {
 static cudaError_t ensure_smem_optin() {
     static bool done = false;  // idempotent attribute; a benign race at worst sets it twice
     if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024);  // + 7 KB static <= 227 KB
     done = e == cudaSuccess;
     return e;
 }
@@ -626,15 +648,17 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     const int tma_out = ((ldy & 3) == 0 && ((uintptr_t)y & 15u) == 0) ? 1 : 0;
     int bn = (int)(N < 256 ? N : 256);
     bn = tma_out ? ((bn + 31) & ~31) : ((bn + 15) & ~15);
+    // few rows: narrower column tiles until the tile count reaches the SM count (each CTA then loads and splits a
+    // proportionally smaller slice of the weight matrix instead of 32 CTAs each chewing through all of it)
+    while (bn > 64 && ceil_div(M, BLOCK_M) * ceil_div(N, bn) < kNumSMs) bn = (bn / 2 + 31) & ~31;
     p.block_n = bn;
     p.n_tiles = (int)ceil_div(N, bn);
     p.m_tiles = (int)ceil_div(M, BLOCK_M);
     p.tma_out = tma_out;
     p.stat_sum = stat_scratch;
-    if (stat_scratch) {
-        if (!tma_out) return MPC_ERR_UNSUPPORTED;
-        MPC_CUDA(cudaMemsetAsync(stat_scratch, 0, sizeof(double) * (2 * (size_t)N + 1), (cudaStream_t)stream));
-    }
+    if (stat_scratch && !tma_out) return MPC_ERR_UNSUPPORTED;  // zero on entry is the caller's contract
+    p.zero_ptr = nullptr;
+    p.zero_n4 = 0;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
     int stages;
     pick_pipeline(stage_bytes, &stages, &p.epi_bufs);
@@ -669,7 +693,7 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
 // grad_w[N,K] = gy[M,N]^T x[M,K]: both operands are contiguous along the OUTPUT dimensions (MN-major for the
 // tensor core), the reduction runs over all M points and is split across the SMs.
 MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t ldx, float* gw, int64_t ldw,
-                                 int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+                                 int64_t M, int64_t K, int64_t N, int64_t gw_is_zero, mpc_stream_t stream) {
     using namespace mpc;
     using namespace mpc::tc;
     if (!gy || !x || !gw || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
@@ -704,6 +728,8 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     p.a_mn = 1;
     p.b_mn = 1;
     p.stat_sum = nullptr;
+    p.zero_ptr = nullptr;
+    p.zero_n4 = 0;
     p.tma_out = ((ldw & 3) == 0 && ((uintptr_t)gw & 15u) == 0) ? 1 : 0;
     p.trace = g_trace;
     CUtensorMap map_a, map_b;
@@ -711,7 +737,7 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     if (rc) return rc;
     rc = make_map(&map_b, x, M, K, ldx, 32, true);
     if (rc) return rc;
-    if (splits > 1) {
+    if (splits > 1 && !gw_is_zero) {
         if (ldw == K) {
             MPC_CUDA(cudaMemsetAsync(gw, 0, (size_t)N * K * sizeof(float), st));
         } else {
@@ -739,18 +765,23 @@ MPC_API int mpc_debug_trace_buffer(void* device_buffer) {
 // grad_x[M,K] = gy[M,N] w[N,K]: A = gy is K-major (the reduction index n is contiguous), B = w is MN-major (the
 // output index k is contiguous), so the weight matrix is consumed as stored -- no transposed copy.
 MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t ldw, float* gx, int64_t ldx,
-                                 int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+                                 int64_t M, int64_t K, int64_t N, float* zero_buf, int64_t zero_count,
+                                 mpc_stream_t stream) {
     using namespace mpc;
     using namespace mpc::tc;
     if (!gy || !w || !gx || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
     if (K % 32 || ldg < N || ldw < K || ldx < K || (ldg & 3) || (ldw & 3)) return MPC_ERR_UNSUPPORTED;
     if (((uintptr_t)gy | (uintptr_t)w) & 15u) return MPC_ERR_UNSUPPORTED;
     if (M > INT32_MAX || N > 65536 || K > 65536) return MPC_ERR_UNSUPPORTED;
+    if (zero_buf && (((uintptr_t)zero_buf & 15u) || (zero_count & 3) || zero_count < 0)) return MPC_ERR_UNSUPPORTED;
     Params p;
+    p.zero_ptr = reinterpret_cast<float4*>(zero_buf);
+    p.zero_n4 = zero_buf ? zero_count / 4 : 0;
     p.M = (int)M;  // output rows
     p.N = (int)K;  // output cols = layer input width
     p.K = (int)N;  // reduction   = layer output width
-    const int bn = (int)(K < 256 ? K : 256);  // multiple of 32
+    int bn = (int)(K < 256 ? K : 256);  // multiple of 32
+    while (bn > 64 && ceil_div(M, BLOCK_M) * ceil_div(K, bn) < kNumSMs) bn = (bn / 2 + 31) & ~31;  // see fwd
     p.block_n = bn;
     p.n_tiles = (int)ceil_div(K, bn);
     p.m_tiles = (int)ceil_div(M, BLOCK_M);

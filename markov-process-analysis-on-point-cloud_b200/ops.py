@@ -98,13 +98,25 @@ def farthest_point_sample(xyz, npoint, cuda=False, start=None):
     if taped is not None:
         _record("fps", taped)
         return taped
+    out = _fps_launch(xyz, npoint, start)
+    _record("fps", out)
+    return out
+
+
+def _fps_launch(xyz, npoint, start):
+    B, N, C = xyz.shape
     xyz = _f32c(xyz.detach())
     start = _i64c(start.to(xyz.device))
     out = torch.empty(B, npoint, dtype=torch.int64, device=xyz.device)
     call("mpc_fps_f32", ptr(xyz), ptr(start), ptr(out), _i64(B), _i64(N), _i64(C), _i64(npoint),
          algo_bytes=B * (N * C * 4 + npoint * 8))
-    _record("fps", out)
     return out
+
+
+def _fps_compute(xyz, npoint):
+    """Prefetch path: draws the start index like farthest_point_sample, no tape bookkeeping."""
+    B, N, _ = xyz.shape
+    return _fps_launch(xyz, npoint, draw_fps_start(B, N, xyz.device))
 
 
 def sample(nsample, feature, cuda=False):
@@ -137,15 +149,23 @@ def knn_point(nsample, xyz, new_xyz):
         raise RuntimeError("selected index k out of range")  # what torch.topk raises in the reference
     taped = _taped("knn", xyz.device)
     # inside one forward the same coordinate search can be asked for twice (la0 and la1_up both search the full
-    # cloud in itself): the geometry scope remembers coordinate-space results by operand identity
+    # cloud in itself) or be prefetched: the geometry scope remembers coordinate-space results by operand identity
+    dist, idx = _knn_compute(nsample, xyz, new_xyz)
+    if taped is not None:
+        idx = taped
+    _record("knn" if C == 3 else "knnf", idx)  # "knnf": feature-space search (tie-prone, see tests)
+    return dist, idx
+
+
+@torch.no_grad()
+def _knn_compute(nsample, xyz, new_xyz):
+    """The search itself (no tape bookkeeping); coordinate-space results are remembered by the geometry scope."""
+    B, N, C = xyz.shape
+    S = new_xyz.shape[1]
     cache = _geo.cache if (_geo is not None and C == 3) else None
     key = (xyz.data_ptr(), new_xyz.data_ptr(), tuple(xyz.shape), tuple(new_xyz.shape), nsample)
     if cache is not None and key in cache:
-        dist, idx = cache[key]
-        if taped is not None:
-            idx = taped
-        _record("knn", idx)
-        return dist, idx
+        return cache[key]
     xyz, new_xyz = _f32c(xyz.detach()), _f32c(new_xyz.detach())
     L = _list_length(nsample)  # the kernels keep sorted lists of these lengths; a longer list is sliced
     if L > N:
@@ -158,9 +178,6 @@ def knn_point(nsample, xyz, new_xyz):
         dist, idx = dist[:, :, :nsample].contiguous(), idx[:, :, :nsample].contiguous()
     if cache is not None:
         cache[key] = (dist, idx)
-    if taped is not None:
-        idx = taped
-    _record("knn" if C == 3 else "knnf", idx)  # "knnf": feature-space search (tie-prone, see tests)
     return dist, idx
 
 
@@ -426,15 +443,17 @@ class FeatAttention(torch.autograd.Function):
              ctypes.c_void_p(gkv.data_ptr() + 4 * C), _i64(2 * C), ptr(gbias), _i64(B), _i64(S), _i64(N), _i64(K),
              _i64(C), algo_bytes=B * ((4 * N * C + 3 * S * C) * 4 + S * K * 8))
         g_center = g_feat = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            g_center = _tc_dgrad(gq, wq, c2d).view(B, S, Cin)
-            g_feat = _tc_dgrad(gkv, wkv, f2d).view(B, N, Cin)
         gwq = torch.empty(C, Cin, dtype=torch.float32, device=dev)
         gwkv = torch.empty(2 * C, Cin, dtype=torch.float32, device=dev)
+        zeroed = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if zeroed:  # each dgrad launch also clears the split-reduction target of the wgrad GEMM that follows
+            g_center = _tc_dgrad(gq, wq, c2d, zero=gwq).view(B, S, Cin)
+            g_feat = _tc_dgrad(gkv, wkv, f2d, zero=gwkv).view(B, N, Cin)
         call("mpc_linear_wgrad_f32", ptr(gq), _i64(C), ptr(c2d), _i64(Cin), ptr(gwq), _i64(Cin), _i64(B * S),
-             _i64(Cin), _i64(C), algo_bytes=(B * S * (Cin + C) + C * Cin) * 4)
+             _i64(Cin), _i64(C), _i64(1 if zeroed else 0), algo_bytes=(B * S * (Cin + C) + C * Cin) * 4)
         call("mpc_linear_wgrad_f32", ptr(gkv), _i64(2 * C), ptr(f2d), _i64(Cin), ptr(gwkv), _i64(Cin), _i64(B * N),
-             _i64(Cin), _i64(2 * C), algo_bytes=(B * N * (Cin + 2 * C) + 2 * C * Cin) * 4)
+             _i64(Cin), _i64(2 * C), _i64(1 if zeroed else 0),
+             algo_bytes=(B * N * (Cin + 2 * C) + 2 * C * Cin) * 4)
         return (g_center, g_feat, None, gwq, gbias[:C], gwkv[:C], gbias[C:2 * C], gwkv[C:], gbias[2 * C:])
 
 
@@ -489,6 +508,27 @@ class AttnXyz(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------
 # BatchNorm1d-over-channels + LeakyReLU on the [M,C] view
 # ------------------------------------------------------------------------------------------------------
+_scratch_pool = {}
+
+
+def _scratch(owner, role, C):
+    """Persistent fp64 reduction scratch of one layer (2C+2 doubles), allocated zeroed once.  The C ABI's scratch
+    contract (include/mpc_b200.h): zero on entry, and the kernel that consumes the sums leaves it zero again, so no
+    memset launch sits between the producer and its predecessor in the stream.  Keyed by the layer's parameter
+    storage and the role (a layer never runs concurrently with itself)."""
+    key = (owner.device, owner.data_ptr(), role, C)
+    buf = _scratch_pool.get(key)
+    if buf is None:
+        buf = _scratch_pool[key] = torch.zeros(2 * C + 2, dtype=torch.float64, device=owner.device)
+    return buf
+
+
+def reset_scratch():
+    """Re-zero every pooled scratch buffer (only needed after a CUDA error interrupted a producer/consumer pair)."""
+    for buf in _scratch_pool.values():
+        buf.zero_()
+
+
 class BNAct(torch.autograd.Function):
     """Tail of the reference's `Linear` block (R/modules/pointnet2_utils.py:417-423) with bn=False (=> BatchNorm1d)
     on the [M,C] view.  Running statistics are updated in place exactly like nn.BatchNorm1d (momentum 0.1,
@@ -503,7 +543,7 @@ class BNAct(torch.autograd.Function):
             if M <= 1:
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s"
                                  % (tuple(y.shape),))
-            scratch = torch.empty(2 * C + 1, dtype=torch.float64, device=dev)
+            scratch = _scratch(gamma, "bn_stats", C)
             stats = torch.empty(2 * C, dtype=torch.float32, device=dev)
             call("mpc_bn_stats_f32", ptr(y), ptr(stats), ptr(running_mean), ptr(running_var),
                  ptr(num_batches_tracked), ctypes.c_float(momentum), ptr(scratch), _i64(M), _i64(C),
@@ -527,10 +567,10 @@ class BNAct(torch.autograd.Function):
         gy = torch.empty_like(y)
         gg = torch.empty(C, dtype=torch.float32, device=y.device)
         gb = torch.empty(C, dtype=torch.float32, device=y.device)
-        scratch = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+        scratch = _scratch(gamma, "bn_bwd", C)
         call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
-             ptr(gb), ptr(scratch), _i64(M), _i64(C), algo_bytes=3 * M * C * 4)
+             ptr(gb), ptr(scratch), ptr(None), _i64(0), _i64(M), _i64(C), algo_bytes=3 * M * C * 4)
         return gy, gg, gb, None, None, None, None, None, None, None
 
 
@@ -564,28 +604,36 @@ def _tc_gemm(x2d, w, bias, out, stat_scratch=None):
          algo_bytes=(M * K + M * N + N * K) * 4)
 
 
-def _tc_dgrad(gy, w, x_like):
+def _tc_dgrad(gy, w, x_like, zero=None):
     """grad_x[M,K] = gy[M,N] @ w[N,K] on the tensor cores (weights consumed as stored); library GEMM when the
-    shape is outside the kernel's reach."""
+    shape is outside the kernel's reach.  `zero` (optional tensor) is cleared by the same launch for the
+    weight-gradient GEMM that follows."""
     M, N = gy.shape
     K = w.shape[1]
-    if _GEMM_IMPL == "tcgen05" and K % 32 == 0 and N % 4 == 0 and M > 0:
+    if _GEMM_IMPL == "tcgen05" and K % 32 == 0 and gy.stride(0) % 4 == 0 and M > 0:
         gx = torch.empty(M, K, dtype=torch.float32, device=gy.device)
         call("mpc_linear_dgrad_f32", ptr(gy), _i64(gy.stride(0)), ptr(w), _i64(w.stride(0)), ptr(gx), _i64(K),
-             _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+             _i64(M), _i64(K), _i64(N), ptr(zero), _i64(zero.numel() if zero is not None else 0),
+             algo_bytes=(M * K + M * N + N * K) * 4)
         return gx
+    if zero is not None:
+        zero.zero_()
     return gy.mm(w)
 
 
 class LinearTC(torch.autograd.Function):
-    """y = x W^T + b.  Forward and grad-input run on the tcgen05 kernel (the two GEMMs whose large operand is
-    the activation stream); grad-weight (a [N,M]x[M,K] reduction over all points) uses the library GEMM."""
+    """y = x W^T + b with forward, grad-input and grad-weight all on the tcgen05 kernel.  An output width that is
+    not a multiple of 4 (the 50-class head) is computed into / read from a buffer whose rows are padded to 16 bytes,
+    which is all TMA needs; the pad columns are never read."""
 
     @staticmethod
     def forward(ctx, x2d, w, bias):
         M, K = x2d.shape
         N = w.shape[0]
-        y = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
+        Np = (N + 3) & ~3
+        y = torch.empty(M, Np, dtype=torch.float32, device=x2d.device)
+        if Np != N:
+            y = y[:, :N]
         _tc_gemm(x2d, w, bias, y)
         ctx.save_for_backward(x2d, w)
         ctx.has_bias = bias is not None
@@ -594,25 +642,32 @@ class LinearTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x2d, w = ctx.saved_tensors
-        gy = _f32c(gy)
+        M, K = x2d.shape
+        N = w.shape[0]
+        if N % 4:
+            gp = torch.empty(M, (N + 3) & ~3, dtype=torch.float32, device=gy.device)[:, :N]
+            gp.copy_(gy)
+            gy = gp
+        else:
+            gy = _f32c(gy)
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = _tc_dgrad(gy, w, x2d)
+        tc_wgrad = ctx.needs_input_grad[1] and _GEMM_IMPL == "tcgen05" and K % 32 == 0
+        if tc_wgrad:
+            gw = torch.empty(N, K, dtype=torch.float32, device=gy.device)
+        if ctx.needs_input_grad[0]:  # the dgrad launch also clears gw (split-reduction target of the wgrad GEMM)
+            gx = _tc_dgrad(gy, w, x2d, zero=gw)
         if ctx.needs_input_grad[1]:
-            M, K = x2d.shape
-            N = w.shape[0]
-            if _GEMM_IMPL == "tcgen05" and K % 32 == 0 and N % 4 == 0:
-                gw = torch.empty(N, K, dtype=torch.float32, device=gy.device)
+            if tc_wgrad:
                 call("mpc_linear_wgrad_f32", ptr(gy), _i64(gy.stride(0)), ptr(x2d), _i64(x2d.stride(0)), ptr(gw),
-                     _i64(K), _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+                     _i64(K), _i64(M), _i64(K), _i64(N), _i64(1 if ctx.needs_input_grad[0] else 0),
+                     algo_bytes=(M * K + M * N + N * K) * 4)
             else:
                 gw = gy.t().mm(x2d)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            M, N = gy.shape
             cv = N // 4
             if N % 4 == 0 and 1 <= cv <= 256 and (cv & (cv - 1)) == 0:
                 gb = torch.empty(N, dtype=torch.float32, device=gy.device)
-                scratch = torch.empty(2 * N + 1, dtype=torch.float64, device=gy.device)
+                scratch = _scratch(w, "col_sum", N)
                 call("mpc_col_sum_f32", ptr(gy), ptr(gb), ptr(scratch), _i64(M), _i64(N), algo_bytes=M * N * 4)
             else:
                 gb = gy.sum(0)
@@ -640,7 +695,7 @@ class LinearBNAct(torch.autograd.Function):
                 raise ValueError("Expected more than 1 value per channel when training, got input size %s"
                                  % ((M, N),))
             # batch statistics come out of the GEMM epilogue (the tile is summed while still in shared memory)
-            scratch = torch.empty(2 * N + 1, dtype=torch.float64, device=dev)
+            scratch = _scratch(w, "fwd_stats", N)
             stats = torch.empty(2 * N, dtype=torch.float32, device=dev)
             _tc_gemm(x2d, w, bias, y, stat_scratch=scratch)
             mean, var = stats[:N], stats[N:]
@@ -681,18 +736,21 @@ class LinearBNAct(torch.autograd.Function):
         gy = torch.empty_like(y)
         gg = torch.empty(N, dtype=torch.float32, device=dev)
         gb = torch.empty(N, dtype=torch.float32, device=dev)
-        scratch = torch.empty(2 * N, dtype=torch.float64, device=dev)
+        scratch = _scratch(w, "bn_bwd", N)
+        gx = gw = gbias = None
+        tc_wgrad = ctx.needs_input_grad[1] and K % 32 == 0 and N % 4 == 0
+        if tc_wgrad:  # cleared by the BatchNorm-backward launch: no memset node in front of the wgrad GEMM
+            gw = torch.empty(N, K, dtype=torch.float32, device=dev)
         call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
-             ptr(gb), ptr(scratch), _i64(M), _i64(N), algo_bytes=3 * M * N * 4)
-        gx = gw = gbias = None
+             ptr(gb), ptr(scratch), ptr(gw), _i64(N * K if tc_wgrad else 0), _i64(M), _i64(N),
+             algo_bytes=3 * M * N * 4)
         if ctx.needs_input_grad[0]:
             gx = _tc_dgrad(gy, w, x2d)
         if ctx.needs_input_grad[1]:
-            if K % 32 == 0 and N % 4 == 0:
-                gw = torch.empty(N, K, dtype=torch.float32, device=dev)
+            if tc_wgrad:
                 call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(K), ptr(gw), _i64(K), _i64(M), _i64(K),
-                     _i64(N), algo_bytes=(M * K + M * N + N * K) * 4)
+                     _i64(N), _i64(1), algo_bytes=(M * K + M * N + N * K) * 4)
             else:
                 gw = gy.t().mm(x2d)
         if has_bias and ctx.needs_input_grad[2]:
@@ -793,34 +851,67 @@ def parallel(*thunks):
 
 class _GeoScope:
     """Coordinate-only work (FPS, coordinate-space kNN, coordinate gathers) depends on nothing but the input
-    cloud, so it runs on its own stream, in program order, ahead of the feature pipeline that consumes it."""
+    cloud, so it runs ahead of the feature pipeline that consumes it, on two lanes: the sampling chain
+    (FPS -> gather -> FPS -> ...; strictly sequential, one CTA per cloud) on a high-priority stream of its own, and
+    the neighbour searches on the geometry stream.  Every result carries the event recorded right after it was
+    produced; a consumer waits for exactly that event, not for everything queued on the lane."""
 
     def __init__(self):
         cur = torch.cuda.current_stream()
         self.stream = _side_streams(cur.device, 8, cur)[-1]  # the last pool stream: never handed to parallel()
+        self.fps_stream = _fps_streams.get(cur.device)
+        if self.fps_stream is None:
+            self.fps_stream = _fps_streams[cur.device] = torch.cuda.Stream(device=cur.device, priority=-1)
         self.stream.wait_stream(cur)  # fork: everything issued so far (the input cloud) is visible
-        self.cache = {}  # coordinate-space kNN results of this forward, by operand identity
+        self.fps_stream.wait_stream(cur)
+        self.cache = {}      # coordinate-space kNN results of this forward, by operand identity
+        self.fps_cache = {}  # prefetched (FPS indices, sampled coordinates), by operand identity
+        self.events = {}     # tensor storage address -> event recorded after its producer
+        self.keep = []       # keeps those tensors (hence their addresses) alive for the scope
+        self.used_fps_lane = False
 
-    def call(self, fn):
-        with torch.cuda.stream(self.stream):
+    def call(self, fn, lane="knn", deps=()):
+        st = self.fps_stream if lane == "fps" else self.stream
+        if lane == "fps":
+            self.used_fps_lane = True
+        for d in deps:  # operands produced on the other lane
+            ev = self.events.get(d.data_ptr())
+            if ev is not None:
+                st.wait_event(ev)
+        with torch.cuda.stream(st):
             out = fn()
+        ev = torch.cuda.Event()
+        ev.record(st)
+        for t in _tensors_of(out):
+            if t.is_cuda and t.data_ptr() not in self.events:  # a cached result keeps its producer's event
+                self.events[t.data_ptr()] = ev
+                self.keep.append(t)
+                t.record_stream(self.stream)
+                t.record_stream(self.fps_stream)
         return out
 
     def join(self, outputs=None):
         cur = torch.cuda.current_stream()
-        cur.wait_stream(self.stream)
-        for t in _tensors_of(outputs):
-            if t.is_cuda:
-                t.record_stream(cur)
+        tensors = [t for t in _tensors_of(outputs) if t.is_cuda]
+        evs = [self.events.get(t.data_ptr()) for t in tensors]
+        if not tensors or any(e is None for e in evs):
+            cur.wait_stream(self.stream)
+            cur.wait_stream(self.fps_stream)
+        else:
+            for e in set(evs):
+                cur.wait_event(e)
+        for t in tensors:
+            t.record_stream(cur)
 
 
 _geo = None
+_fps_streams = {}
 
 
 @contextlib.contextmanager
 def geometry_scope():
-    """Inside this scope geo_call() runs its thunk on the geometry stream; geo_join() makes the current stream
-    wait for everything issued there so far.  Outside a scope (or with MPC_STREAMS=0) both are no-ops."""
+    """Inside this scope geo_call() runs its thunk on a geometry lane; geo_join() makes the current stream wait
+    for the producers of the given results.  Outside a scope (or with MPC_STREAMS=0) both are no-ops."""
     global _geo
     old = _geo
     _geo = _GeoScope() if (_STREAMS_ENABLED and torch.cuda.is_available()) else None
@@ -829,17 +920,72 @@ def geometry_scope():
     finally:
         if _geo is not None:
             torch.cuda.current_stream().wait_stream(_geo.stream)
+            torch.cuda.current_stream().wait_stream(_geo.fps_stream)
         _geo = old
 
 
-def geo_call(fn):
-    return _geo.call(fn) if _geo is not None else fn()
+def geo_call(fn, lane="knn", deps=()):
+    return _geo.call(fn, lane, deps) if _geo is not None else fn()
 
 
 def geo_join(outputs=None):
     if _geo is not None:
         _geo.join(outputs)
     return outputs
+
+
+@torch.no_grad()
+def fps_and_gather(points, npoint):
+    """One sampling step of the encoders (R/modules/pointnet2_utils.py:771-772 and the like): FPS indices and the
+    sampled coordinates.  Inside a geometry scope a prefetched result (geo_prefetch_pyramid) is returned."""
+    if _geo is not None:
+        hit = _geo.fps_cache.get((points.data_ptr(), tuple(points.shape), npoint))
+        if hit is not None:
+            _record("fps", hit[0])
+            return hit
+    idx = farthest_point_sample(points, npoint)
+    return idx, index_points(points, idx)
+
+
+def geo_prefetch_pyramid(xyz, npoints, k, self_levels=(0,), cross=()):
+    """Issue the whole coordinate pyramid of one forward up front: the sampling chain xyz -> npoints[0] -> npoints[1]
+    ... on the sampling lane, and on the neighbour-search lane the k-NN of every sampled state in its parent state
+    (LocalMerge encoder stages), of the states in `self_levels` in themselves (level-0 stage, decoder stages) and of
+    the (target, source) state pairs in `cross` (Fuse's non-adjacent transitions).  The consumers then find their
+    results in the scope's caches (knn_point / fps_and_gather) in their own call order, so index recording and the
+    CPU-generator draws for the FPS start indices keep the reference's order.  Returns the list of states' coordinates.
+    No-op (returns None) outside a geometry scope or while indices are being injected."""
+    if _geo is None or _tape.inject is not None:
+        return None
+    geo = _geo
+    levels = [xyz]
+    done = set()
+
+    def knn(ref, qry):
+        key = (ref.data_ptr(), qry.data_ptr())
+        if key not in done:
+            done.add(key)
+            geo.call(lambda: _knn_compute(k, ref, qry), "knn", deps=(ref, qry))
+
+    if 0 in self_levels:
+        knn(xyz, xyz)
+    for npoint in npoints:
+        base = levels[-1]
+
+        def sample(base=base, npoint=npoint):
+            idx = _fps_compute(base, npoint)
+            sub = index_points(base, idx)
+            geo.fps_cache[(base.data_ptr(), tuple(base.shape), npoint)] = (idx, sub)
+            return idx, sub
+
+        _, sub = geo.call(sample, "fps", deps=(base,))
+        levels.append(sub)
+        knn(base, sub)
+    for lv in self_levels:
+        knn(levels[lv], levels[lv])
+    for t, j in cross:
+        knn(levels[t], levels[j])
+    return levels
 
 
 def launches():

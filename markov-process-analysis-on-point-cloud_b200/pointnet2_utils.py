@@ -238,14 +238,15 @@ class KeepHighResolutionModulePartSeg(nn.Module):
     def _sample(points, npoint):
         """FPS + gather of the sampled coordinates, issued on the geometry stream (joined by the consumer's
         coordinate kNN, which follows it on that stream)."""
-        def run():
-            idx = farthest_point_sample(points, npoint)
-            return idx, index_points(points, idx)
-        return ops.geo_call(run)
+        return ops.geo_call(lambda: ops.fps_and_gather(points, npoint))
 
     def _forward(self, xyz, normal, label):
         N = xyz.shape[1]
         n = [N, N // 2, N // 4, N // 8, N // 16]
+        # the whole coordinate pyramid (4 sampling steps, 5 + 4 + 6 neighbour searches) only depends on xyz: issue
+        # it now on the geometry lanes; the stages below pick their results up in the reference's call order
+        ops.geo_prefetch_pyramid(xyz, n[1:], 8, self_levels=(0, 3, 2, 1),
+                                 cross=((2, 4), (1, 3), (1, 4), (0, 2), (0, 3), (0, 4)))
         # encoder (:765-791)
         e0, nrm0, knn0, dist0 = self.la0(xyz=xyz, base_xyz=xyz, normal=normal, xyz_flag=True)
         F0, x1 = self._sample(xyz, n[1])

@@ -75,14 +75,12 @@ class KeepHighResolutionModule(nn.Module):
     def forward(self, xyz, normal):
         xyz = xyz.permute(0, 2, 1).contiguous()
         normal = normal.permute(0, 2, 1).contiguous()
-        with ops.geometry_scope():  # FPS / coordinate kNN run ahead on the geometry stream
+        with ops.geometry_scope():  # FPS / coordinate kNN run ahead on the geometry lanes
+            ops.geo_prefetch_pyramid(xyz, [npoint for _, npoint in self.STAGES], 8)
             feat, normal, _, _ = self.la0(xyz=xyz, base_xyz=xyz, normal=normal, xyz_flag=True)
             base = xyz
             for name, npoint in self.STAGES:
-                def sample(points=base, npoint=npoint):
-                    idx = farthest_point_sample(points, npoint)
-                    return idx, index_points(points, idx)
-                fps_idx, sub = ops.geo_call(sample)
+                fps_idx, sub = ops.geo_call(lambda points=base, npoint=npoint: ops.fps_and_gather(points, npoint))
                 feat, normal, _, _ = getattr(self, name)(xyz=sub, base_xyz=base, normal=normal, feature=feat,
                                                         FPS_idx=fps_idx)
                 base = sub

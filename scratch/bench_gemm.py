@@ -23,6 +23,6 @@ for (M,K,N) in shapes:
         t2 = timeit(lambda: torch.nn.functional.linear(x,w,b))
         print("fwd   M=%6d K=%4d N=%4d  %8.1f us  %7.1f GB/s  %6.1f TF/s   (cublas fp32 %8.1f us)" % (M,K,N,t,by/t/1e3,fl/t/1e6,t2))
     if which in ("all","wgrad"):
-        t = timeit(lambda: mpc._lib.call("mpc_linear_wgrad_f32", mpc._lib.ptr(gy), ctypes.c_int64(N), mpc._lib.ptr(x), ctypes.c_int64(K), mpc._lib.ptr(gw), ctypes.c_int64(K), ctypes.c_int64(M), ctypes.c_int64(K), ctypes.c_int64(N)))
+        t = timeit(lambda: mpc._lib.call("mpc_linear_wgrad_f32", mpc._lib.ptr(gy), ctypes.c_int64(N), mpc._lib.ptr(x), ctypes.c_int64(K), mpc._lib.ptr(gw), ctypes.c_int64(K), ctypes.c_int64(M), ctypes.c_int64(K), ctypes.c_int64(N), ctypes.c_int64(0)))
         t2 = timeit(lambda: gy.t().mm(x))
         print("wgrad M=%6d K=%4d N=%4d  %8.1f us  %7.1f GB/s  %6.1f TF/s   (cublas fp32 %8.1f us)" % (M,K,N,t,by/t/1e3,fl/t/1e6,t2))

@@ -13,7 +13,7 @@ def run(M, K, N, pattern):
         x[:, :] = torch.arange(K, device="cuda").float()[None, :] + 1
     gw = torch.full((N, K), -7.0, device="cuda")
     mpc._lib.call("mpc_linear_wgrad_f32", mpc._lib.ptr(gy), ctypes.c_int64(N), mpc._lib.ptr(x), ctypes.c_int64(K), mpc._lib.ptr(gw),
-                  ctypes.c_int64(K), ctypes.c_int64(M), ctypes.c_int64(K), ctypes.c_int64(N))
+                  ctypes.c_int64(K), ctypes.c_int64(M), ctypes.c_int64(K), ctypes.c_int64(N), ctypes.c_int64(0))
     torch.cuda.synchronize()
     ref = gy.double().t() @ x.double()
     print("M,K,N", M, K, N, pattern, "maxerr", (gw.double() - ref).abs().max().item(), "ref max", ref.abs().max().item())

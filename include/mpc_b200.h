@@ -245,6 +245,10 @@ int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t l
  * kernels records a clock64() timeline per warp role (producer / splitter / MMA / epilogue: 256 slots each).
  * Pass NULL to switch it off (the default).  Process-global. */
 int mpc_debug_trace_buffer(void* device_buffer);
+/* Debug facility: launch-geometry knobs of the streaming BatchNorm kernels (0 restores the built-in default).
+ * id 0: elementwise CTAs per SM, 1: column-reduction CTAs per SM, 2: float4 per thread the elementwise grid is sized
+ * for.  Process-global; used by scratch/bench_bn.py to pick the defaults. */
+int mpc_debug_set_knob(int id, int64_t value);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mpc_linear_wgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr],
     "mpc_linear_dgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
     "mpc_debug_trace_buffer": [_ptr],
+    "mpc_debug_set_knob": [_int, _i64],
 }
 
 # kernels each entry point enqueues (cudaMemsetAsync calls not counted)
@@ -57,6 +58,7 @@ KERNELS_PER_CALL = {
     "mpc_linear_wgrad_f32": 1,
     "mpc_linear_dgrad_f32": 1,
     "mpc_debug_trace_buffer": 0,
+    "mpc_debug_set_knob": 0,
 }
 
 _lib = None

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(AT)
 attn_feat_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ kf,
                      const float* __restrict__ vf, int64_t ldkv, const int64_t* __restrict__ idx,
                      float* __restrict__ ctx, int S, int N, int CV, float sqrtc, int64_t total) {
+    pdl_prologue();
     for (int64_t t = (int64_t)blockIdx.x * AT + threadIdx.x; t < total; t += (int64_t)gridDim.x * AT) {
         const int64_t row = t / CV;
         const int c4 = (int)(t - row * CV) * 4;
@@ -124,6 +125,7 @@ attn_feat_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ q
                      const int64_t* __restrict__ idx, float* __restrict__ gq, int64_t ldgq,
                      float* __restrict__ gkf, float* __restrict__ gvf, int64_t ldgkv, float* __restrict__ gbias,
                      int S, int N, int CV, float sqrtc, int64_t total) {
+    pdl_prologue();
     // column sums of grad_q / grad_k / grad_v (= the bias gradients of the three projections): AT % CV == 0, so a
     // thread's channel group never changes across its grid-stride rows and the sums live in registers
     float4 sq = make_float4(0.f, 0.f, 0.f, 0.f), sk = sq, sv = sq;
@@ -203,6 +205,7 @@ attn_xyz_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ 
                     const float* __restrict__ bv, const float* __restrict__ wr, const float* __restrict__ br,
                     float* __restrict__ ctx, float* __restrict__ res_out, int64_t rows, int S, int N, int C,
                     int cin_rt, float sqrtc) {
+    pdl_prologue();
     const int cin = CIN > 0 ? CIN : cin_rt;
     constexpr int CM = CIN > 0 ? CIN : 16;
     const int Cb = C < 256 ? C : 256;  // channels per CTA; C > 256 is split along gridDim.y (C % 256 == 0)
@@ -266,6 +269,7 @@ attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ fe
                     float* __restrict__ gbk, float* __restrict__ gwv, float* __restrict__ gbv,
                     float* __restrict__ gwr, float* __restrict__ gbr,
                     float* __restrict__ gfeat, int64_t rows, int S, int N, int C, int cin_rt, float sqrtc) {
+    pdl_prologue();
     const int cin = CIN > 0 ? CIN : cin_rt;
     constexpr int CM = CIN > 0 ? CIN : 16;
     const int Cb = C < 256 ? C : 256;
@@ -456,7 +460,7 @@ MPC_API int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, 
     const int64_t total = B * S * CV;
     const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
-    MPC_DISPATCH_K(K, (attn_feat_fwd_kernel<KK><<<attn_grid(total, AT), AT, 0, st>>>(
+    MPC_DISPATCH_K(K, (pdl_launch(attn_feat_fwd_kernel<KK>, dim3(attn_grid(total, AT)), dim3(AT), 0, st, 
                           q, ldq, kf, vf, ldkv, idx, ctx_out, (int)S, (int)N, CV, sqrtc, total)));
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -480,7 +484,7 @@ MPC_API int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t
     const int64_t total = B * S * CV;
     const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
-    MPC_DISPATCH_K(K, (attn_feat_bwd_kernel<KK><<<attn_grid(total, AT), AT, 0, st>>>(
+    MPC_DISPATCH_K(K, (pdl_launch(attn_feat_bwd_kernel<KK>, dim3(attn_grid(total, AT)), dim3(AT), 0, st, 
                           grad_ctx, q, ldq, kf, vf, ldkv, idx, grad_q, ldgq, grad_kf, grad_vf, ldgkv, grad_bias, (int)S,
                           (int)N, CV, sqrtc, total)));
     MPC_LAUNCH_CHECK();
@@ -505,11 +509,11 @@ MPC_API int mpc_attn_xyz_fwd_f32(const float* feat, const int64_t* center_idx, c
     const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 3) {
-        MPC_DISPATCH_K(K, (attn_xyz_fwd_kernel<KK, 3><<<grid, threads, 0, st>>>(
+        MPC_DISPATCH_K(K, (pdl_launch(attn_xyz_fwd_kernel<KK, 3>, dim3(grid), dim3(threads), 0, st, 
                               feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, br, ctx_out, res_out, rows, (int)S,
                               (int)N, (int)C, 3, sqrtc)));
     } else {
-        MPC_DISPATCH_K(K, (attn_xyz_fwd_kernel<KK, 0><<<grid, threads, 0, st>>>(
+        MPC_DISPATCH_K(K, (pdl_launch(attn_xyz_fwd_kernel<KK, 0>, dim3(grid), dim3(threads), 0, st, 
                               feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, br, ctx_out, res_out, rows, (int)S,
                               (int)N, (int)C, (int)Cin, sqrtc)));
     }
@@ -542,12 +546,12 @@ MPC_API int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const
     const float sqrtc = 1.0f / sqrtf((float)C);  // passed to the kernels as the reciprocal scale
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 3) {
-        MPC_DISPATCH_K(K, (attn_xyz_bwd_kernel<KK, 3><<<grid, threads, 0, st>>>(
+        MPC_DISPATCH_K(K, (pdl_launch(attn_xyz_bwd_kernel<KK, 3>, dim3(grid), dim3(threads), 0, st, 
                               grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, grad_res, grad_wq, grad_bq,
                               grad_wk, grad_bk, grad_wv, grad_bv, grad_wr, grad_br, grad_feat, rows, (int)S, (int)N,
                               (int)C, 3, sqrtc)));
     } else {
-        MPC_DISPATCH_K(K, (attn_xyz_bwd_kernel<KK, 0><<<grid, threads, 0, st>>>(
+        MPC_DISPATCH_K(K, (pdl_launch(attn_xyz_bwd_kernel<KK, 0>, dim3(grid), dim3(threads), 0, st, 
                               grad_ctx, feat, center_idx, idx, wq, bq, wk, bk, wv, bv, wr, grad_res, grad_wq, grad_bq,
                               grad_wk, grad_bk, grad_wv, grad_bv, grad_wr, grad_br, grad_feat, rows, (int)S, (int)N,
                               (int)C, (int)Cin, sqrtc)));

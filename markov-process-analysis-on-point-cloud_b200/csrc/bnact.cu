@@ -9,6 +9,11 @@
 
 namespace mpc {
 
+// tuning knobs (mpc_debug_set_knob; 0 = built-in default): 0 = elementwise CTAs per SM, 1 = column-reduction CTAs
+// per SM, 2 = elementwise float4 per thread the grid is sized for
+static int64_t g_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static inline int64_t knob(int i, int64_t dflt) { return g_knob[i] > 0 ? g_knob[i] : dflt; }
+
 constexpr int BN_TX = 32;  // lanes along channels (float4 each => 128 channels per CTA column)
 constexpr int BN_TY = 8;   // row slots per CTA
 
@@ -82,6 +87,7 @@ __device__ __forceinline__ void block_reduce_to_scratch(float4 a, float4 b, doub
 template <bool VEC4>
 __global__ void __launch_bounds__(BN_TX* BN_TY)
 bn_sums_kernel(const float* __restrict__ y, double* __restrict__ s1, double* __restrict__ s2, int64_t M, int C) {
+    pdl_prologue();
     const int cw = VEC4 ? 4 : 1;
     const int cbase = (blockIdx.x * BN_TX + threadIdx.x) * cw;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -138,6 +144,7 @@ col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, c
                   const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float eps, float slope, double* __restrict__ s1, double* __restrict__ s2,
                   unsigned* __restrict__ ticket, StatsFinal fin, int64_t M, int C, int CV) {
+    pdl_prologue();
     __shared__ float4 ra[RT], rb[RT];
     __shared__ bool last;
     const int v = threadIdx.x % CV, slot = threadIdx.x / CV, slots = RT / CV;
@@ -240,7 +247,7 @@ static inline bool fast_cv(int64_t C) {
 static inline unsigned col_reduce_grid(int64_t M, int CV) {
     const int slots = RT / CV;
     int64_t g = ceil_div(M, (int64_t)slots * 8);  // >= 8 rows per thread
-    const int64_t cap = (int64_t)kNumSMs * 8;
+    const int64_t cap = (int64_t)kNumSMs * knob(1, 2);  // few CTAs: the fp64 atomics per channel serialise in L2
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -249,6 +256,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ s1, double* __restrict__
                                    float* __restrict__ stats, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked,
                                    float momentum, int64_t M, int C) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ var,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
                   float* __restrict__ out, int C, int64_t total) {
+    pdl_prologue();
     const int cw = VEC4 ? 4 : 1;
     for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
         const int c = (int)((t * cw) % C);
@@ -305,6 +314,7 @@ __global__ void __launch_bounds__(256)
 bn_act_fwd_fast_kernel(const float4* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ var,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
                        const float4* __restrict__ residual, float4* __restrict__ out, int C, int64_t total) {
+    pdl_prologue();
     const int c = (threadIdx.x * 4) % C;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
     const float4 vr = __ldg(reinterpret_cast<const float4*>(var + c));
@@ -350,6 +360,7 @@ bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restri
                          int train, double* __restrict__ s1, double* __restrict__ s2,
                          float4* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta,
                          float* __restrict__ zero_buf, int64_t zero_count, int64_t M, int C, int64_t total) {
+    pdl_prologue();
     zero_service(zero_buf, zero_count);
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < C; i += 256) {
@@ -401,6 +412,7 @@ bn_act_fwd_sums_kernel(const float4* __restrict__ y, double* __restrict__ s1, do
                        float* __restrict__ running_mean,
                        float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked, float momentum,
                        int64_t M, int C, int64_t total) {
+    pdl_prologue();
     if (blockIdx.x == 0) {
         StatsFinal fin{stats, running_mean, running_var, num_batches_tracked, momentum};
         for (int i = threadIdx.x; i < C; i += 256) finalize_channel(s1, s2, fin, M, C, i);
@@ -408,10 +420,11 @@ bn_act_fwd_sums_kernel(const float4* __restrict__ y, double* __restrict__ s1, do
     }
     const int c = (threadIdx.x * 4) % C;
     float mu[4], sc[4], be[4];
+    const double invM = 1.0 / (double)M;  // one fp64 division per thread instead of eight
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const double mean = s1[c + i] / (double)M;
-        double var = s2[c + i] / (double)M - mean * mean;
+        const double mean = s1[c + i] * invM;
+        double var = s2[c + i] * invM - mean * mean;
         var = var < 0.0 ? 0.0 : var;
         mu[i] = (float)mean;
         sc[i] = gamma[c + i] * (1.0f / sqrtf((float)var + eps));
@@ -457,6 +470,7 @@ __global__ void __launch_bounds__(BN_TX* BN_TY)
 bn_bwd_sums_kernel(const float* __restrict__ gout, const float* __restrict__ y, const float* __restrict__ mean,
                    const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, float slope, double* __restrict__ s1, double* __restrict__ s2, int64_t M, int C) {
+    pdl_prologue();
     const int cw = VEC4 ? 4 : 1;
     const int cbase = (blockIdx.x * BN_TX + threadIdx.x) * cw;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -506,6 +520,7 @@ bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ y,
                     float eps, float slope, int train, double* __restrict__ s1, double* __restrict__ s2,
                     float* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta,
                     float* __restrict__ zero_buf, int64_t zero_count, int64_t M, int C, int64_t total) {
+    pdl_prologue();
     zero_service(zero_buf, zero_count);
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < C; c += 256) {
@@ -547,8 +562,10 @@ bn_bwd_apply_kernel(const float* __restrict__ gout, const float* __restrict__ y,
 }
 
 static inline unsigned ew_grid(int64_t total) {
-    int64_t g = ceil_div(total, 256);
-    const int64_t cap = (int64_t)kNumSMs * 16;
+    // sized for >= 4 float4 per thread (the unrolled loop keeps 4 loads in flight) and at most 4 CTAs per SM: a
+    // per-thread prologue (coefficients from fp64 sums) amortised over 1-2 elements was the whole cost before
+    int64_t g = ceil_div(total, 256 * knob(2, 4));
+    const int64_t cap = (int64_t)kNumSMs * knob(0, 4);
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -565,7 +582,7 @@ MPC_API int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, 
     if (fast_cv(C) && al16(y)) {
         const int CV = (int)(C / 4);
         StatsFinal fin{stats, running_mean, running_var, num_batches_tracked, momentum};
-        col_reduce_kernel<0><<<col_reduce_grid(M, CV), RT, 0, st>>>(
+        pdl_launch(col_reduce_kernel<0>, dim3(col_reduce_grid(M, CV)), dim3(RT), 0, st, 
             y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, scratch, scratch + C,
             reinterpret_cast<unsigned*>(scratch + 2 * C), fin, M, (int)C, CV);
         MPC_LAUNCH_CHECK();
@@ -574,11 +591,11 @@ MPC_API int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, 
     const bool v4 = C % 4 == 0 && al16(y);
     const Dims d = bn_dims(M, (int)(v4 ? C / 4 : C));
     if (v4)
-        bn_sums_kernel<true><<<d.grid, d.block, 0, st>>>(y, scratch, scratch + C, M, (int)C);
+        pdl_launch(bn_sums_kernel<true>, dim3(d.grid), dim3(d.block), 0, st, y, scratch, scratch + C, M, (int)C);
     else
-        bn_sums_kernel<false><<<d.grid, d.block, 0, st>>>(y, scratch, scratch + C, M, (int)C);
+        pdl_launch(bn_sums_kernel<false>, dim3(d.grid), dim3(d.block), 0, st, y, scratch, scratch + C, M, (int)C);
     MPC_LAUNCH_CHECK();
-    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(scratch, scratch + C, stats, running_mean, running_var,
+    pdl_launch(bn_finalize_kernel, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, scratch, scratch + C, stats, running_mean, running_var,
                                                                    num_batches_tracked, momentum, M, (int)C);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -594,13 +611,13 @@ MPC_API int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* v
     const bool v4 = C % 4 == 0 && al16(y) && al16(out) && al16(mean) && al16(var) && al16(gamma) && al16(beta);
     const int64_t total = M * (v4 ? C / 4 : C);
     if (v4 && fast_ew(C))
-        bn_act_fwd_fast_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float4*>(y), mean, var, gamma, beta,
+        pdl_launch(bn_act_fwd_fast_kernel, dim3(ew_grid(total)), dim3(256), 0, st, reinterpret_cast<const float4*>(y), mean, var, gamma, beta,
                                                               eps, slope, reinterpret_cast<const float4*>(residual),
                                                               reinterpret_cast<float4*>(out), (int)C, total);
     else if (v4)
-        bn_act_fwd_kernel<true><<<ew_grid(total), 256, 0, st>>>(y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
+        pdl_launch(bn_act_fwd_kernel<true>, dim3(ew_grid(total)), dim3(256), 0, st, y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
     else
-        bn_act_fwd_kernel<false><<<ew_grid(total), 256, 0, st>>>(y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
+        pdl_launch(bn_act_fwd_kernel<false>, dim3(ew_grid(total)), dim3(256), 0, st, y, mean, var, gamma, beta, eps, slope, out, (int)C, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }
@@ -620,28 +637,28 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
     if (v4) {
         if (fast_cv(C) && al16(mean) && al16(var) && al16(gamma) && al16(beta)) {
             const int CV = (int)(C / 4);
-            col_reduce_kernel<1><<<col_reduce_grid(M, CV), RT, 0, st>>>(y, grad_out, mean, var, gamma, beta, eps, slope,
+            pdl_launch(col_reduce_kernel<1>, dim3(col_reduce_grid(M, CV)), dim3(RT), 0, st, y, grad_out, mean, var, gamma, beta, eps, slope,
                                                                        scratch, scratch + C, nullptr, StatsFinal{}, M,
                                                                        (int)C, CV);
         } else {
-            bn_bwd_sums_kernel<true><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
+            pdl_launch(bn_bwd_sums_kernel<true>, dim3(d.grid), dim3(d.block), 0, st, grad_out, y, mean, var, gamma, beta, eps, slope,
                                                                 scratch, scratch + C, M, (int)C);
         }
         MPC_LAUNCH_CHECK();
         if (fast_ew(C))
-            bn_bwd_apply_fast_kernel<<<ew_grid(total), 256, 0, st>>>(
+            pdl_launch(bn_bwd_apply_fast_kernel, dim3(ew_grid(total)), dim3(256), 0, st, 
                 reinterpret_cast<const float4*>(grad_out), reinterpret_cast<const float4*>(y), mean, var, gamma, beta, eps,
                 slope, train, scratch, scratch + C, reinterpret_cast<float4*>(grad_y), grad_gamma, grad_beta, zero_buf,
                 zero_count, M, (int)C, total);
         else
-            bn_bwd_apply_kernel<true><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
+            pdl_launch(bn_bwd_apply_kernel<true>, dim3(ew_grid(total)), dim3(256), 0, st, grad_out, y, mean, var, gamma, beta, eps, slope,
                                                                      train, scratch, scratch + C, grad_y, grad_gamma,
                                                                      grad_beta, zero_buf, zero_count, M, (int)C, total);
     } else {
-        bn_bwd_sums_kernel<false><<<d.grid, d.block, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope, scratch,
+        pdl_launch(bn_bwd_sums_kernel<false>, dim3(d.grid), dim3(d.block), 0, st, grad_out, y, mean, var, gamma, beta, eps, slope, scratch,
                                                              scratch + C, M, (int)C);
         MPC_LAUNCH_CHECK();
-        bn_bwd_apply_kernel<false><<<ew_grid(total), 256, 0, st>>>(grad_out, y, mean, var, gamma, beta, eps, slope,
+        pdl_launch(bn_bwd_apply_kernel<false>, dim3(ew_grid(total)), dim3(256), 0, st, grad_out, y, mean, var, gamma, beta, eps, slope,
                                                                   train, scratch, scratch + C, grad_y, grad_gamma,
                                                                   grad_beta, zero_buf, zero_count, M, (int)C, total);
     }
@@ -653,7 +670,7 @@ MPC_API int mpc_bn_finalize_f32(double* sums, float* stats, float* running_mean,
                                 int64_t* num_batches_tracked, float momentum, int64_t M, int64_t C,
                                 mpc_stream_t stream) {
     if (!sums || !stats || M <= 0 || C <= 0) return MPC_ERR_INVALID;
-    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+    pdl_launch(bn_finalize_kernel, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, 
         sums, sums + C, stats, running_mean, running_var, num_batches_tracked, momentum, M, (int)C);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -666,7 +683,7 @@ MPC_API int mpc_bn_act_fwd_sums_f32(const float* y, double* sums, const float* g
     if (!y || !sums || !gamma || !beta || !out || !stats || M <= 0 || C <= 0) return MPC_ERR_INVALID;
     if (!fast_ew(C) || !al16(y) || !al16(out) || (residual && !al16(residual))) return MPC_ERR_UNSUPPORTED;
     const int64_t total = M * (C / 4);
-    bn_act_fwd_sums_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+    pdl_launch(bn_act_fwd_sums_kernel, dim3(ew_grid(total)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<const float4*>(y), sums, sums + C, gamma, beta, eps, slope,
         reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), stats, running_mean, running_var,
         num_batches_tracked, momentum, M, (int)C, total);
@@ -680,11 +697,17 @@ MPC_API int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     const int CV = (int)(C / 4);
     StatsFinal fin{out, nullptr, nullptr, nullptr, 0.f};
-    col_reduce_kernel<2><<<col_reduce_grid(M, CV), RT, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,
+    pdl_launch(col_reduce_kernel<2>, dim3(col_reduce_grid(M, CV)), dim3(RT), 0, st, y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,
                                                                scratch, scratch + C,
                                                                reinterpret_cast<unsigned*>(scratch + 2 * C), fin, M, (int)C,
                                                                CV);
     MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_debug_set_knob(int id, int64_t value) {
+    if (id < 0 || id >= 8) return MPC_ERR_INVALID;
+    mpc::g_knob[id] = value;
     return MPC_OK;
 }
 

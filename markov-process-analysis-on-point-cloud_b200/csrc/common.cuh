@@ -30,6 +30,33 @@ __device__ __forceinline__ int clamp_index(int64_t i, int n) {
     return i < 0 ? 0 : (i >= n ? n - 1 : (int)i);
 }
 
+// Programmatic dependent launch.  Every kernel of the short streaming family starts with pdl_prologue(): it lets the
+// NEXT kernel in the stream be scheduled right away (its CTAs park in their own griddepcontrol.wait until this grid
+// has completed and flushed), and waits for the PREVIOUS kernel before touching global memory.  Launched through
+// pdl_launch() the ~2-3 us of launch/drain latency between two dependent kernels overlaps; launched normally both
+// instructions are no-ops.  (Long-running kernels -- FPS, kNN -- do not trigger early: parked dependents would hold
+// SM slots that other streams need.)
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface in MPC_LAUNCH_CHECK()
+}
+
 // 128-bit reduction into global memory (sm_90+: red.global.add.v4.f32).
 __device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),

@@ -22,6 +22,7 @@ template <typename VEC>
 __global__ void __launch_bounds__(GT)
 gather_kernel(const VEC* __restrict__ points, const int64_t* __restrict__ idx, VEC* __restrict__ out,
               int N, int64_t M, int CV, int64_t total) {
+    pdl_prologue();
     // total = B*M*CV vector elements; CV = vectors per row
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / CV;
@@ -36,6 +37,7 @@ gather_kernel(const VEC* __restrict__ points, const int64_t* __restrict__ idx, V
 __global__ void __launch_bounds__(GT)
 scatter_add_v4_kernel(const float4* __restrict__ grad_out, const int64_t* __restrict__ idx,
                       float* __restrict__ grad_points, int N, int64_t M, int CV, int64_t total) {
+    pdl_prologue();
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / CV;
         const int v = (int)(t - row * CV);
@@ -47,6 +49,7 @@ scatter_add_v4_kernel(const float4* __restrict__ grad_out, const int64_t* __rest
 __global__ void __launch_bounds__(GT)
 scatter_add_s_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
                      float* __restrict__ grad_points, int N, int64_t M, int C, int64_t total) {
+    pdl_prologue();
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / C;
         const int c = (int)(t - row * C);
@@ -64,6 +67,7 @@ __global__ void __launch_bounds__(GT)
 transition_scatter_kernel(const float* __restrict__ points, const int64_t* __restrict__ idx,
                           float* __restrict__ out, float* __restrict__ cnt, int S, int K, int C, int N,
                           int64_t total) {
+    pdl_prologue();
     const int CV = VEC4 ? C / 4 : C;
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t rk = t / CV;  // (row, k)
@@ -94,6 +98,7 @@ transition_scatter_kernel(const float* __restrict__ points, const int64_t* __res
 template <bool VEC4>
 __global__ void __launch_bounds__(GT)
 transition_normalise_kernel(float* __restrict__ out, float* __restrict__ cnt, int C, int64_t total) {
+    pdl_prologue();
     const int CV = VEC4 ? C / 4 : C;
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / CV;
@@ -115,6 +120,7 @@ transition_normalise_kernel(float* __restrict__ out, float* __restrict__ cnt, in
     }
 }
 __global__ void __launch_bounds__(GT) transition_fix_cnt_kernel(float* __restrict__ cnt, int64_t total) {
+    pdl_prologue();
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT)
         if (cnt[t] == 0.0f) cnt[t] = 1.0f;
 }
@@ -133,6 +139,7 @@ __device__ __forceinline__ bool dup_before(const int64_t* irow, int k, int64_t r
 
 __global__ void __launch_bounds__(GT)
 csr_count_kernel(const int64_t* __restrict__ idx, int* __restrict__ deg, int S, int K, int N, int64_t total) {
+    pdl_prologue();
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / K;
         const int k = (int)(t - row * K);
@@ -147,6 +154,7 @@ csr_count_kernel(const int64_t* __restrict__ idx, int* __restrict__ deg, int S, 
 // one contiguous chunk: local sum, one block-wide scan of the 1024 chunk sums, local rewrite (two barriers in all).
 __global__ void __launch_bounds__(1024)
 csr_scan_kernel(int* __restrict__ deg, int* __restrict__ cursor, int N) {
+    pdl_prologue();
     __shared__ int warp_sums[32];
     int* d = deg + (int64_t)blockIdx.x * (N + 1);
     int* cur = cursor + (int64_t)blockIdx.x * N;
@@ -209,6 +217,7 @@ __device__ __forceinline__ int block_inclusive_scan_1024(int v, int* warp_sums) 
 
 __global__ void __launch_bounds__(1024)
 csr_block_sums_kernel(const int* __restrict__ deg, int* __restrict__ bsum, int N, int nblk) {
+    pdl_prologue();
     __shared__ int warp_sums[32];
     const int* d = deg + (int64_t)blockIdx.y * (N + 1);
     const int i = blockIdx.x * 1024 + threadIdx.x;
@@ -217,7 +226,8 @@ csr_block_sums_kernel(const int* __restrict__ deg, int* __restrict__ bsum, int N
 }
 
 __global__ void __launch_bounds__(1024)
-csr_scan_block_sums_kernel(int* __restrict__ bsum, int nblk) {  // nblk <= 1024*... handled by chunks, carry in smem
+csr_scan_block_sums_kernel(int* __restrict__ bsum, int nblk) {
+    pdl_prologue();  // nblk <= 1024*... handled by chunks, carry in smem
     __shared__ int warp_sums[32];
     __shared__ int carry;
     int* bs = bsum + (int64_t)blockIdx.x * nblk;
@@ -238,6 +248,7 @@ csr_scan_block_sums_kernel(int* __restrict__ bsum, int nblk) {  // nblk <= 1024*
 __global__ void __launch_bounds__(1024)
 csr_block_rescan_kernel(int* __restrict__ deg, int* __restrict__ cursor, const int* __restrict__ bsum, int N,
                         int nblk) {
+    pdl_prologue();
     __shared__ int warp_sums[32];
     int* d = deg + (int64_t)blockIdx.y * (N + 1);
     int* cur = cursor + (int64_t)blockIdx.y * N;
@@ -252,6 +263,7 @@ csr_block_rescan_kernel(int* __restrict__ deg, int* __restrict__ cursor, const i
 __global__ void __launch_bounds__(GT)
 csr_fill_kernel(const int64_t* __restrict__ idx, int* __restrict__ cursor, int* __restrict__ list, int S, int K, int N,
                 int64_t total) {
+    pdl_prologue();
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / K;
         const int k = (int)(t - row * K);
@@ -268,6 +280,7 @@ template <bool VEC4>
 __global__ void __launch_bounds__(GT)
 transition_gather_kernel(const float* __restrict__ points, const int* __restrict__ offs, const int* __restrict__ list,
                          float* __restrict__ out, float* __restrict__ cnt, int S, int K, int C, int N, int64_t total) {
+    pdl_prologue();
     const int CV = VEC4 ? C / 4 : C;
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / CV;  // (b, n)
@@ -314,6 +327,7 @@ __global__ void __launch_bounds__(GT)
 transition_bwd_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
                       const float* __restrict__ cnt, float* __restrict__ grad_points, int S, int K, int C,
                       int N, int64_t total) {
+    pdl_prologue();
     const int CV = VEC4 ? C / 4 : C;
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / CV;
@@ -349,6 +363,7 @@ transition_bwd_kernel(const float* __restrict__ grad_out, const int64_t* __restr
 // ---- three_interpolate ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT)
 three_weights_kernel(const float* __restrict__ dist, float* __restrict__ weight, int64_t rows) {
+    pdl_prologue();
     for (int64_t r = (int64_t)blockIdx.x * GT + threadIdx.x; r < rows; r += (int64_t)gridDim.x * GT) {
         const float r0 = __fdiv_rn(1.0f, __fadd_rn(dist[r * 3 + 0], 1e-8f));
         const float r1 = __fdiv_rn(1.0f, __fadd_rn(dist[r * 3 + 1], 1e-8f));
@@ -365,6 +380,7 @@ __global__ void __launch_bounds__(GT)
 three_interp_fwd_kernel(const float* __restrict__ points2, const float* __restrict__ weight,
                         const int64_t* __restrict__ idx, float* __restrict__ out, int N, int S, int C,
                         int64_t total) {
+    pdl_prologue();
     const int CV = VEC4 ? C / 4 : C;
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / CV;
@@ -399,6 +415,7 @@ __global__ void __launch_bounds__(GT)
 three_interp_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ weight,
                         const int64_t* __restrict__ idx, float* __restrict__ grad_points2, int N, int S, int C,
                         int64_t total) {
+    pdl_prologue();
     const int CV = VEC4 ? C / 4 : C;
     for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
         const int64_t row = t / CV;
@@ -437,11 +454,11 @@ MPC_API int mpc_gather_f32(const float* points, const int64_t* idx, float* out, 
     if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
         const int CV = (int)(C / 4);
         const int64_t total = B * M * CV;
-        gather_kernel<float4><<<grid_for(total), GT, 0, st>>>(reinterpret_cast<const float4*>(points), idx,
+        pdl_launch(gather_kernel<float4>, dim3(grid_for(total)), dim3(GT), 0, st, reinterpret_cast<const float4*>(points), idx,
                                                              reinterpret_cast<float4*>(out), (int)N, M, CV, total);
     } else {
         const int64_t total = B * M * C;
-        gather_kernel<float><<<grid_for(total), GT, 0, st>>>(points, idx, out, (int)N, M, (int)C, total);
+        pdl_launch(gather_kernel<float>, dim3(grid_for(total)), dim3(GT), 0, st, points, idx, out, (int)N, M, (int)C, total);
     }
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -453,7 +470,7 @@ MPC_API int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* o
     if (B == 0 || M == 0) return MPC_OK;
     if (!values || !idx || !out) return MPC_ERR_INVALID;
     const int64_t total = B * M;
-    gather_kernel<long long><<<grid_for(total), GT, 0, (cudaStream_t)stream>>>(
+    pdl_launch(gather_kernel<long long>, dim3(grid_for(total)), dim3(GT), 0, (cudaStream_t)stream, 
         reinterpret_cast<const long long*>(values), idx, reinterpret_cast<long long*>(out), (int)N, M, 1, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -471,11 +488,11 @@ MPC_API int mpc_gather_bwd_f32(const float* grad_out, const int64_t* idx, float*
     if (C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points)) {
         const int CV = (int)(C / 4);
         const int64_t total = B * M * CV;
-        scatter_add_v4_kernel<<<grid_for(total), GT, 0, st>>>(reinterpret_cast<const float4*>(grad_out), idx,
+        pdl_launch(scatter_add_v4_kernel, dim3(grid_for(total)), dim3(GT), 0, st, reinterpret_cast<const float4*>(grad_out), idx,
                                                               grad_points, (int)N, M, CV, total);
     } else {
         const int64_t total = B * M * C;
-        scatter_add_s_kernel<<<grid_for(total), GT, 0, st>>>(grad_out, idx, grad_points, (int)N, M, (int)C, total);
+        pdl_launch(scatter_add_s_kernel, dim3(grid_for(total)), dim3(GT), 0, st, grad_out, idx, grad_points, (int)N, M, (int)C, total);
     }
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -495,20 +512,20 @@ MPC_API int mpc_transition_fwd_f32(const float* points, const int64_t* idx, floa
     if (S > 0) {
         const int64_t total = B * S * K * CV;
         if (v4)
-            transition_scatter_kernel<true><<<grid_for(total), GT, 0, st>>>(points, idx, out, cnt, (int)S, (int)K,
+            pdl_launch(transition_scatter_kernel<true>, dim3(grid_for(total)), dim3(GT), 0, st, points, idx, out, cnt, (int)S, (int)K,
                                                                            (int)C, (int)N, total);
         else
-            transition_scatter_kernel<false><<<grid_for(total), GT, 0, st>>>(points, idx, out, cnt, (int)S, (int)K,
+            pdl_launch(transition_scatter_kernel<false>, dim3(grid_for(total)), dim3(GT), 0, st, points, idx, out, cnt, (int)S, (int)K,
                                                                             (int)C, (int)N, total);
         MPC_LAUNCH_CHECK();
     }
     const int64_t total = B * N * CV;
     if (v4)
-        transition_normalise_kernel<true><<<grid_for(total), GT, 0, st>>>(out, cnt, (int)C, total);
+        pdl_launch(transition_normalise_kernel<true>, dim3(grid_for(total)), dim3(GT), 0, st, out, cnt, (int)C, total);
     else
-        transition_normalise_kernel<false><<<grid_for(total), GT, 0, st>>>(out, cnt, (int)C, total);
+        pdl_launch(transition_normalise_kernel<false>, dim3(grid_for(total)), dim3(GT), 0, st, out, cnt, (int)C, total);
     MPC_LAUNCH_CHECK();
-    transition_fix_cnt_kernel<<<grid_for(B * N), GT, 0, st>>>(cnt, B * N);
+    pdl_launch(transition_fix_cnt_kernel, dim3(grid_for(B * N)), dim3(GT), 0, st, cnt, B * N);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }
@@ -528,35 +545,35 @@ MPC_API int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, 
     MPC_CUDA(cudaMemsetAsync(offs, 0, sizeof(int) * (size_t)B * (N + 1), st));
     if (S > 0) {
         const int64_t total = B * S * K;
-        csr_count_kernel<<<grid_for(total), GT, 0, st>>>(idx, offs, (int)S, (int)K, (int)N, total);
+        pdl_launch(csr_count_kernel, dim3(grid_for(total)), dim3(GT), 0, st, idx, offs, (int)S, (int)K, (int)N, total);
         MPC_LAUNCH_CHECK();
     }
     if (N + 1 <= 8192) {
-        csr_scan_kernel<<<(unsigned)B, 1024, 0, st>>>(offs, cursor, (int)N);
+        pdl_launch(csr_scan_kernel, dim3((unsigned)B), dim3(1024), 0, st, offs, cursor, (int)N);
         MPC_LAUNCH_CHECK();
     } else {  // the block sums live at the head of the (not yet filled) list area
         const int nblk = (int)ceil_div(N + 1, 1024);
         if ((int64_t)nblk > S * K) return MPC_ERR_UNSUPPORTED;
         int* bsum = list;
-        csr_block_sums_kernel<<<dim3((unsigned)nblk, (unsigned)B), 1024, 0, st>>>(offs, bsum, (int)N, nblk);
+        pdl_launch(csr_block_sums_kernel, dim3(dim3((unsigned)nblk, (unsigned)B)), dim3(1024), 0, st, offs, bsum, (int)N, nblk);
         MPC_LAUNCH_CHECK();
-        csr_scan_block_sums_kernel<<<(unsigned)B, 1024, 0, st>>>(bsum, nblk);
+        pdl_launch(csr_scan_block_sums_kernel, dim3((unsigned)B), dim3(1024), 0, st, bsum, nblk);
         MPC_LAUNCH_CHECK();
-        csr_block_rescan_kernel<<<dim3((unsigned)nblk, (unsigned)B), 1024, 0, st>>>(offs, cursor, bsum, (int)N, nblk);
+        pdl_launch(csr_block_rescan_kernel, dim3(dim3((unsigned)nblk, (unsigned)B)), dim3(1024), 0, st, offs, cursor, bsum, (int)N, nblk);
         MPC_LAUNCH_CHECK();
     }
     if (S > 0) {
         const int64_t total = B * S * K;
-        csr_fill_kernel<<<grid_for(total), GT, 0, st>>>(idx, cursor, list, (int)S, (int)K, (int)N, total);
+        pdl_launch(csr_fill_kernel, dim3(grid_for(total)), dim3(GT), 0, st, idx, cursor, list, (int)S, (int)K, (int)N, total);
         MPC_LAUNCH_CHECK();
     }
     const bool v4 = C % 4 == 0 && aligned16(points) && aligned16(out);
     const int64_t total = B * N * (v4 ? C / 4 : C);
     if (v4)
-        transition_gather_kernel<true><<<grid_for(total), GT, 0, st>>>(points, offs, list, out, cnt, (int)S, (int)K, (int)C,
+        pdl_launch(transition_gather_kernel<true>, dim3(grid_for(total)), dim3(GT), 0, st, points, offs, list, out, cnt, (int)S, (int)K, (int)C,
                                                                       (int)N, total);
     else
-        transition_gather_kernel<false><<<grid_for(total), GT, 0, st>>>(points, offs, list, out, cnt, (int)S, (int)K,
+        pdl_launch(transition_gather_kernel<false>, dim3(grid_for(total)), dim3(GT), 0, st, points, offs, list, out, cnt, (int)S, (int)K,
                                                                        (int)C, (int)N, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -574,10 +591,10 @@ MPC_API int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, co
     const int CV = (int)(v4 ? C / 4 : C);
     const int64_t total = B * S * CV;
     if (v4)
-        transition_bwd_kernel<true><<<grid_for(total), GT, 0, st>>>(grad_out, idx, cnt, grad_points, (int)S, (int)K,
+        pdl_launch(transition_bwd_kernel<true>, dim3(grid_for(total)), dim3(GT), 0, st, grad_out, idx, cnt, grad_points, (int)S, (int)K,
                                                                    (int)C, (int)N, total);
     else
-        transition_bwd_kernel<false><<<grid_for(total), GT, 0, st>>>(grad_out, idx, cnt, grad_points, (int)S, (int)K,
+        pdl_launch(transition_bwd_kernel<false>, dim3(grid_for(total)), dim3(GT), 0, st, grad_out, idx, cnt, grad_points, (int)S, (int)K,
                                                                     (int)C, (int)N, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -590,15 +607,15 @@ MPC_API int mpc_three_interpolate_fwd_f32(const float* points2, const float* dis
     if (B == 0 || N == 0) return MPC_OK;
     if (!points2 || !dist || !idx || !weight_out || !out) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    three_weights_kernel<<<grid_for(B * N), GT, 0, st>>>(dist, weight_out, B * N);
+    pdl_launch(three_weights_kernel, dim3(grid_for(B * N)), dim3(GT), 0, st, dist, weight_out, B * N);
     MPC_LAUNCH_CHECK();
     const bool v4 = C % 4 == 0 && aligned16(points2) && aligned16(out);
     const int64_t total = B * N * (v4 ? C / 4 : C);
     if (v4)
-        three_interp_fwd_kernel<true><<<grid_for(total), GT, 0, st>>>(points2, weight_out, idx, out, (int)N, (int)S,
+        pdl_launch(three_interp_fwd_kernel<true>, dim3(grid_for(total)), dim3(GT), 0, st, points2, weight_out, idx, out, (int)N, (int)S,
                                                                      (int)C, total);
     else
-        three_interp_fwd_kernel<false><<<grid_for(total), GT, 0, st>>>(points2, weight_out, idx, out, (int)N, (int)S,
+        pdl_launch(three_interp_fwd_kernel<false>, dim3(grid_for(total)), dim3(GT), 0, st, points2, weight_out, idx, out, (int)N, (int)S,
                                                                       (int)C, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
@@ -617,10 +634,10 @@ MPC_API int mpc_three_interpolate_bwd_f32(const float* grad_out, const float* we
     const bool v4 = C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points2);
     const int64_t total = B * N * (v4 ? C / 4 : C);
     if (v4)
-        three_interp_bwd_kernel<true><<<grid_for(total), GT, 0, st>>>(grad_out, weight, idx, grad_points2, (int)N,
+        pdl_launch(three_interp_bwd_kernel<true>, dim3(grid_for(total)), dim3(GT), 0, st, grad_out, weight, idx, grad_points2, (int)N,
                                                                      (int)S, (int)C, total);
     else
-        three_interp_bwd_kernel<false><<<grid_for(total), GT, 0, st>>>(grad_out, weight, idx, grad_points2, (int)N,
+        pdl_launch(three_interp_bwd_kernel<false>, dim3(grid_for(total)), dim3(GT), 0, st, grad_out, weight, idx, grad_points2, (int)N,
                                                                       (int)S, (int)C, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;

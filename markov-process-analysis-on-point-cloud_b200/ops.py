@@ -585,6 +585,9 @@ def bn_act(y2d, gamma, beta, running_mean, running_var, num_batches_tracked, tra
 # ------------------------------------------------------------------------------------------------------
 # shared-MLP projection on the tensor cores
 # ------------------------------------------------------------------------------------------------------
+# dgrad || wgrad of a Linear+BN block on two streams: measured 2 % SLOWER on the part-seg step (both GEMMs want every
+# SM), so off by default
+_BWD_PAIR = os.environ.get("MPC_BWD_PAIR", "0") == "1"
 _GEMM_IMPL = os.environ.get("MPC_GEMM", "tcgen05")  # "cublas" forces the library GEMM (A/B comparisons)
 
 
@@ -745,14 +748,21 @@ class LinearBNAct(torch.autograd.Function):
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
              ptr(gb), ptr(scratch), ptr(gw), _i64(N * K if tc_wgrad else 0), _i64(M), _i64(N),
              algo_bytes=3 * M * N * 4)
-        if ctx.needs_input_grad[0]:
-            gx = _tc_dgrad(gy, w, x2d)
-        if ctx.needs_input_grad[1]:
+        def wgrad():
+            call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(K), ptr(gw), _i64(K), _i64(M), _i64(K),
+                 _i64(N), _i64(1), algo_bytes=(M * K + M * N + N * K) * 4)
+            return gw
+
+        if ctx.needs_input_grad[0] and tc_wgrad and _BWD_PAIR:
+            # grad-input and grad-weight only share their input: side by side (two graph branches)
+            gx, _ = parallel(lambda: _tc_dgrad(gy, w, x2d), wgrad)
+        else:
+            if ctx.needs_input_grad[0]:
+                gx = _tc_dgrad(gy, w, x2d)
             if tc_wgrad:
-                call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(K), ptr(gw), _i64(K), _i64(M), _i64(K),
-                     _i64(N), _i64(1), algo_bytes=(M * K + M * N + N * K) * 4)
-            else:
-                gw = gy.t().mm(x2d)
+                wgrad()
+        if ctx.needs_input_grad[1] and not tc_wgrad:
+            gw = gy.t().mm(x2d)
         if has_bias and ctx.needs_input_grad[2]:
             gbias = torch.zeros_like(gb) if training else gamma * torch.rsqrt(var + eps) * gb
         # out = act(BN(y)) + residual: the residual's gradient is the incoming gradient itself

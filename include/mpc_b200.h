@@ -49,7 +49,9 @@ int mpc_compiled_arch(void);
  * Bit-exact contract: running min distance starts at 1e10; dist = ((dx*dx + dy*dy) + dz*dz) with
  * separately rounded mul/add (no fma); update on strict <; next = argmax, lowest index on ties.
  * C == 3: one persistent CTA per cloud for N <= 8192, one thread-block cluster (<= 16 CTAs, DSMEM argmax
- * exchange) per cloud for N <= 262144.  C != 3 (feature-space FPS): N * 4 bytes of shared memory, N <= 50000.
+ * exchange) per cloud for N <= 262144, and one cooperative launch across the whole GPU (<= 148 CTAs x 8192 points in
+ * registers, grid barrier per round through library-global barrier words: one such call in flight per device) for
+ * N <= 1 212 416.  C != 3 (feature-space FPS): N * 4 bytes of shared memory, N <= 50000.
  * Otherwise MPC_ERR_UNSUPPORTED.
  * ------------------------------------------------------------------------------------------------- */
 int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, int64_t B, int64_t N, int64_t C,
@@ -247,7 +249,8 @@ int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t l
 int mpc_debug_trace_buffer(void* device_buffer);
 /* Debug facility: launch-geometry knobs of the streaming BatchNorm kernels (0 restores the built-in default).
  * id 0: elementwise CTAs per SM, 1: column-reduction CTAs per SM, 2: float4 per thread the elementwise grid is sized
- * for.  Process-global; used by scratch/bench_bn.py to pick the defaults. */
+ * for, 3: non-zero forces the grid-wide FPS variant for every cloud above 8192 points (parity tests of that variant
+ * at sizes the CPU oracle finishes).  Process-global; used by scratch/bench_bn.py to pick the defaults. */
 int mpc_debug_set_knob(int id, int64_t value);
 
 #ifdef __cplusplus

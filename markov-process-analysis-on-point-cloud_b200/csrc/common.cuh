@@ -23,6 +23,9 @@ namespace mpc {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// debug / tuning knobs (mpc_debug_set_knob, defined in bnact.cu; 0 = built-in default)
+extern int64_t g_knob[8];
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Clamp an API-level int64 index into [0, n): out-of-range indices are never dereferenced.

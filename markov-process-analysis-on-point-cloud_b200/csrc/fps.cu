@@ -183,6 +183,115 @@ fps_cluster_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ st
     cluster.sync();  // no CTA exits while a peer may still write into its shared memory
 }
 
+// ---- variant D: one cloud across the whole GPU (N > 262144, up to 148 x 8192 points), C == 3 ---------------
+// The running minimum distances of a 1M-point cloud (16 MB with the coordinates) only fit in the register files of
+// ~128 SMs together.  One cooperative launch per cloud: CTA g keeps points [g*8192, (g+1)*8192) in registers, publishes
+// its local winner (key + coordinates) into a double-buffered global slot array and a grid-wide barrier (one
+// monotonically increasing counter, release/acquire) decides the round: ~3 us per round, HBM traffic still ~0.
+// Barrier words and candidate slots are library-global: one such launch at a time per device.
+constexpr int GRID_MAX = kNumSMs;
+__device__ unsigned g_fps_barrier;
+__device__ Cand g_fps_cand[2][GRID_MAX];
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_grid_kernel(const float* __restrict__ p, const int64_t* __restrict__ start, int64_t* __restrict__ o, int N,
+                int npoint) {
+    extern __shared__ float smem[];  // this CTA's slice, SoA
+    __shared__ unsigned long long slots[2][32];
+    __shared__ float win[4];
+    constexpr int NW = THREADS / 32;
+    constexpr int SL = PPT * THREADS;
+    const int G = gridDim.x, rank = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int base = rank * SL;
+    float* sx = smem;
+    float* sy = sx + SL;
+    float* sz = sy + SL;
+    const int cntp = max(0, min(SL, N - base));
+    for (int i = tid; i < cntp * 3; i += THREADS) {
+        int n = i / 3, c = i - n * 3;
+        smem[c * SL + n] = p[(size_t)base * 3 + i];
+    }
+    __syncthreads();
+    float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        int n = tid + i * THREADS;
+        bool ok = n < cntp;
+        px[i] = ok ? sx[n] : 0.f;
+        py[i] = ok ? sy[n] : 0.f;
+        pz[i] = ok ? sz[n] : 0.f;
+        md[i] = ok ? 1e10f : -1.0f;
+    }
+    int far = clamp_index(start[0], N);
+    float cx = p[(size_t)far * 3 + 0], cy = p[(size_t)far * 3 + 1], cz = p[(size_t)far * 3 + 2];
+    for (int it = 0; it < npoint; ++it) {
+        if (rank == 0 && tid == 0) o[it] = far;
+        unsigned bhi, blo;
+        update_slice<PPT>(px, py, pz, md, cx, cy, cz, base + tid, THREADS, bhi, blo);
+        unsigned long long k = warp_max_key(bhi, blo);
+        if (lane == 0) slots[it & 1][warp] = k;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = lane < NW ? slots[it & 1][lane] : 0ull;
+            k = warp_max_key((unsigned)(v >> 32), (unsigned)v);
+            if (lane == 0) {  // publish this CTA's winner, then arrive at the grid barrier of this round
+                int li = (int)(~(unsigned)k) - base;
+                li = li < 0 ? 0 : (li >= SL ? SL - 1 : li);
+                Cand c;
+                c.key = k;
+                c.x = sx[li];
+                c.y = sy[li];
+                c.z = sz[li];
+                c.pad = 0.f;
+                g_fps_cand[it & 1][rank] = c;
+                __threadfence();
+                atomicAdd(&g_fps_barrier, 1u);
+                const unsigned target = (unsigned)(it + 1) * (unsigned)G;
+                while (ld_acquire_u32(&g_fps_barrier) < target) {
+                }
+            }
+            __syncwarp();
+            // every candidate of this round is visible: lane l reduces candidates l, l + 32, ...
+            unsigned long long best = 0ull;
+            int bsrc = 0;
+            for (int r = lane; r < G; r += 32) {
+                const unsigned long long kk = __ldcg(&g_fps_cand[it & 1][r].key);
+                if (kk > best) {
+                    best = kk;
+                    bsrc = r;
+                }
+            }
+            const unsigned long long kmax = warp_max_key((unsigned)(best >> 32), (unsigned)best);
+            const unsigned src_lane = __ffs(__ballot_sync(0xffffffffu, best == kmax)) - 1;
+            if (lane == src_lane) {
+                const Cand* c = &g_fps_cand[it & 1][bsrc];
+                win[0] = __ldcg(&c->x);
+                win[1] = __ldcg(&c->y);
+                win[2] = __ldcg(&c->z);
+                win[3] = __int_as_float((int)(~(unsigned)kmax));
+            }
+        }
+        __syncthreads();
+        cx = win[0];
+        cy = win[1];
+        cz = win[2];
+        far = __float_as_int(win[3]);
+    }
+    // leave the barrier word zero for the next launch: the last CTA through the final barrier resets it
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned done = atomicAdd(&g_fps_barrier, 1u) + 1u;
+        if (done == (unsigned)(npoint + 1) * (unsigned)G) g_fps_barrier = 0u;
+    }
+}
+
 // ---- variant B: generic channel count (feature-space FPS), one CTA per cloud -----------------------------
 __global__ void __launch_bounds__(512, 1)
 fps_generic_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start,
@@ -276,6 +385,25 @@ static int launch_cluster(const float* xyz, const int64_t* start, int64_t* out, 
     return MPC_OK;
 }
 
+template <int PPT, int THREADS>
+static int launch_grid(const float* xyz, const int64_t* start, int64_t* out, int B, int N, int npoint, cudaStream_t st) {
+    const int SL = PPT * THREADS;
+    const int G = (N + SL - 1) / SL;
+    if (G > GRID_MAX) return MPC_ERR_UNSUPPORTED;
+    if ((long long)(npoint + 1) * G >= 0xffffffffll) return MPC_ERR_UNSUPPORTED;  // barrier counter range
+    size_t smem = spread_smem((size_t)SL * 3 * sizeof(float), G);
+    auto kern = fps_grid_kernel<PPT, THREADS>;
+    MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int b = 0; b < B; ++b) {  // one cloud at a time: the grid barrier words are shared
+        const float* p = xyz + (size_t)b * N * 3;
+        const int64_t* s0 = start + b;
+        int64_t* o = out + (size_t)b * npoint;
+        void* args[] = {(void*)&p, (void*)&s0, (void*)&o, (void*)&N, (void*)&npoint};
+        MPC_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(G), dim3(THREADS), args, smem, st));
+    }
+    return MPC_OK;
+}
+
 }  // namespace mpc
 
 MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, int64_t B, int64_t N, int64_t C,
@@ -295,6 +423,7 @@ MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, in
         return MPC_OK;
     }
     const int b = (int)B, n = (int)N, np = (int)npoint;
+    if (n > 8192 && g_knob[3] > 0) return launch_grid<8, 1024>(xyz, start, out, b, n, np, st);  // debug: force variant D
     // single CTA: THREADS * PPT >= N, xyz copy N*12 bytes of shared memory (<= 192 KB at N = 16384)
     if (n <= 128) return launch_cta<1, 128>(xyz, start, out, b, n, np, st);
     if (n <= 256) return launch_cta<2, 128>(xyz, start, out, b, n, np, st);
@@ -311,5 +440,6 @@ MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, in
     if (n <= 16 * 4096) return launch_cluster<8, 512>(xyz, start, out, b, n, np, 16, st);
     if (n <= 16 * 8192) return launch_cluster<8, 1024>(xyz, start, out, b, n, np, 16, st);
     if (n <= 16 * 16384) return launch_cluster<16, 1024>(xyz, start, out, b, n, np, 16, st);
+    if (n <= GRID_MAX * 8192) return launch_grid<8, 1024>(xyz, start, out, b, n, np, st);  // up to 1 212 416 points
     return MPC_ERR_UNSUPPORTED;
 }

@@ -742,11 +742,20 @@ class LinearBNAct(torch.autograd.Function):
         scratch = _scratch(w, "bn_bwd", N)
         gx = gw = gbias = None
         tc_wgrad = ctx.needs_input_grad[1] and K % 32 == 0 and N % 4 == 0
-        if tc_wgrad:  # cleared by the BatchNorm-backward launch: no memset node in front of the wgrad GEMM
-            gw = torch.empty(N, K, dtype=torch.float32, device=dev)
+        zero_bias = has_bias and ctx.needs_input_grad[2] and training and N % 4 == 0
+        flat = None
+        if tc_wgrad or zero_bias:
+            # one buffer cleared by the BatchNorm-backward launch: the weight gradient (split-reduction target of the
+            # wgrad GEMM: no memset node in front of it) and the Linear bias gradient, which is exactly zero under
+            # batch statistics (no fill launch)
+            flat = torch.empty((N * K if tc_wgrad else 0) + (N if zero_bias else 0), dtype=torch.float32, device=dev)
+            if tc_wgrad:
+                gw = flat[:N * K].view(N, K)
+            if zero_bias:
+                gbias = flat[flat.numel() - N:]
         call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
-             ptr(gb), ptr(scratch), ptr(gw), _i64(N * K if tc_wgrad else 0), _i64(M), _i64(N),
+             ptr(gb), ptr(scratch), ptr(flat), _i64(flat.numel() if flat is not None else 0), _i64(M), _i64(N),
              algo_bytes=3 * M * N * 4)
         def wgrad():
             call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(K), ptr(gw), _i64(K), _i64(M), _i64(K),
@@ -763,7 +772,7 @@ class LinearBNAct(torch.autograd.Function):
                 wgrad()
         if ctx.needs_input_grad[1] and not tc_wgrad:
             gw = gy.t().mm(x2d)
-        if has_bias and ctx.needs_input_grad[2]:
+        if has_bias and ctx.needs_input_grad[2] and gbias is None:
             gbias = torch.zeros_like(gb) if training else gamma * torch.rsqrt(var + eps) * gb
         # out = act(BN(y)) + residual: the residual's gradient is the incoming gradient itself
         gres = grad_out if ctx.has_residual else None

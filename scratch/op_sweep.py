@@ -13,7 +13,7 @@ def timeit(fn, n=3):
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ts.sort(); return ts[len(ts) // 2]
-sizes = [int(a) for a in sys.argv[1:]] or [16384, 65536, 262144]
+sizes = [int(a) for a in sys.argv[1:]] or [16384, 65536, 262144, 1048576]
 print("%-22s %8s %3s %10s %12s" % ("op", "N", "B", "ms", "rate"))
 for N in sizes:
     B = 8 if N <= 16384 else 1

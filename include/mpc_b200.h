@@ -243,6 +243,20 @@ int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t l
 int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t ldx, float* gw, int64_t ldw,
                          int64_t M, int64_t K, int64_t N, int64_t gw_is_zero, mpc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Umbrella surface features.  Replaces group_by_umbrella + cal_normal(is_group=True) +
+ * cal_center + xyz2sphere + cal_const + check_nan_umb as composed by UmbrellaSurfaceConstructor.forward,
+ * R/modules/pointnet2_utils.py:310-378 (helpers in R/modules/recons_utils.py, R/modules/polar_utils.py:10-31).
+ *   xyz [B,N,3] f32; idx [B,N,ldk] i64 = the k nearest neighbours of every point in its own cloud, column 0 the point
+ *   itself (mpc_knn_f32 with ref = qry), columns 1..k-1 used; sign [B] f32 (+1/-1, the per-cloud random_inv draw of
+ *   recons_utils.py:50) or NULL; out [B,N,k-1,C] f32 with C = 10 (centroid 3, spherical coordinates of the centroid
+ *   3, unit normal 3, plane constant 1) or C = 9 (no constant).
+ * Neighbours are sorted by azimuth (stable); triangle g = (point, s_g, s_{g+1 mod k-1}); triangles with a NaN normal
+ * take normal / centroid / constant of the first valid triangle of the same point.  3 <= k <= 13 or k = 16.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_umbrella_features_f32(const float* xyz, const int64_t* idx, int64_t ldk, const float* sign, float* out,
+                              int64_t B, int64_t N, int64_t k, int64_t C, mpc_stream_t stream);
+
 /* Debug facility (not part of the data path): when set to a device buffer of 1024 int64, CTA 0 of the tensor-core
  * kernels records a clock64() timeline per warp role (producer / splitter / MMA / epilogue: 256 slots each).
  * Pass NULL to switch it off (the default).  Process-global. */

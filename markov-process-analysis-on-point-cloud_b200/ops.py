@@ -215,6 +215,25 @@ def query_ball_point(radius, nsample, xyz, new_xyz, cuda=False):
     return out
 
 
+@torch.no_grad()
+def umbrella_features(center, k=9, return_dist=True, sign=None):
+    """The umbrella feature UmbrellaSurfaceConstructor feeds to its MLP (R/modules/pointnet2_utils.py:360-378):
+    center [B,N,3] -> [B,N,k-1,10] (9 without the plane constant): centroid, spherical coordinates, unit normal,
+    constant of the k-1 triangles around every point.  `sign` [B] (+1/-1) is the per-cloud random_inv flip.  One
+    kNN launch + one fused kernel; coordinates carry no gradient on this path."""
+    require_cuda(center)
+    B, N, _ = center.shape
+    center = _f32c(center.detach())
+    _, idx = knn_point(k, center, center)
+    C = 10 if return_dist else 9
+    out = torch.empty(B, N, k - 1, C, dtype=torch.float32, device=center.device)
+    if sign is not None:
+        sign = _f32c(sign.to(center.device).reshape(B))
+    call("mpc_umbrella_features_f32", ptr(center), ptr(idx), _i64(idx.stride(1)), ptr(sign), ptr(out), _i64(B),
+         _i64(N), _i64(k), _i64(C), algo_bytes=B * N * (12 + k * 8 + (k - 1) * C * 4))
+    return out
+
+
 def _check_index(idx, n, what):
     if _CHECK_INDEX and idx.numel():
         lo, hi = int(idx.min()), int(idx.max())

@@ -282,6 +282,57 @@ class KeepHighResolutionModulePartSeg(nn.Module):
         return xyz, final
 
 
+class UmbrellaSurfaceConstructor(nn.Module):
+    """Umbrella-based surface abstraction, R/modules/pointnet2_utils.py:336-399: same constructor,
+    forward(center [B,3,N]) -> [B,in_channel,N] and state_dict (mlps.0 / .1 / .3 / .4 / .6).  The geometry -- kNN,
+    azimuth sort, the k-1 triangles' centroid / polar / normal / constant, NaN repair -- is one kNN launch plus one
+    fused kernel (ops.umbrella_features) instead of the reference's ~40 ATen ops on [B,N,G,3,3] tensors; the 10-channel
+    1x1 convolutions stay torch modules.  random_inv draws its per-cloud sign on the CPU generator exactly like
+    R/modules/recons_utils.py:50."""
+
+    def __init__(self, k, in_channel, aggr_type='sum', return_dist=False, random_inv=True, cuda=False):
+        super().__init__()
+        self.k = k
+        self.return_dist = return_dist
+        self.random_inv = random_inv
+        self.aggr_type = aggr_type
+        self.cuda_ops = cuda  # the reference stores this as `self.cuda`, shadowing nn.Module.cuda()
+        self.mlps = nn.Sequential(
+            nn.Conv2d(in_channel, in_channel, 1, bias=False),
+            nn.BatchNorm2d(in_channel),
+            nn.ReLU(True),
+            nn.Conv2d(in_channel, in_channel, 1, bias=True),
+            nn.BatchNorm2d(in_channel),
+            nn.ReLU(True),
+            nn.Conv2d(in_channel, in_channel, 1, bias=True),
+        )
+
+    def forward(self, center):
+        center = center.permute(0, 2, 1).contiguous()
+        sign = None
+        if self.random_inv:
+            sign = torch.randint(0, 2, (center.size(0), 1, 1)).float() * 2. - 1.
+        feat = ops.umbrella_features(center, self.k, self.return_dist, sign)  # [B,N,G,C]
+        B, N, G, C = feat.shape
+        # mlps on the [B*N*G, C] row view: a 1x1 Conv2d is a Linear over channels and BatchNorm2d over (B,G,N) is
+        # BatchNorm over the rows.  fp32 GEMMs (cuDNN's convolution would default to TF32: 1e-3 off the reference)
+        # and this repo's BatchNorm+ReLU kernels (LeakyReLU with slope 0)
+        x = feat.reshape(-1, C)
+        conv0, bn1, _, conv3, bn4, _, conv6 = self.mlps
+        for conv, bn in ((conv0, bn1), (conv3, bn4)):
+            x = F.linear(x, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
+            x = ops.bn_act(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                           bn.training, momentum=bn.momentum, eps=bn.eps, slope=0.0)
+        x = F.linear(x, conv6.weight.view(conv6.out_channels, conv6.in_channels), conv6.bias).view(B, N, G, -1)
+        if self.aggr_type == 'max':
+            x = torch.max(x, 2)[0]
+        elif self.aggr_type == 'avg':
+            x = torch.mean(x, 2)
+        else:
+            x = torch.sum(x, 2)
+        return x.permute(0, 2, 1)  # [B,C,N]
+
+
 class PointNetFeaturePropagation(nn.Module):
     """three_nn + three_interpolate + Linear, R/modules/pointnet2_utils.py:860-912.  Inputs are [B,N,C]
     (the reference's docstring says [B,C,N] but its permutes are commented out, :887-892); points1 is unused

@@ -448,6 +448,73 @@ def feature_propagation(P, pre, xyz1, xyz2, points1, points2, ctx, act=False):
 
 
 # --------------------------------------------------------------------------------------------------
+# umbrella surface features (RepSurf), R/modules/pointnet2_utils.py:310-399
+# --------------------------------------------------------------------------------------------------
+def sphere_coords(v):
+    """xyz2sphere with normalize=True, R/modules/polar_utils.py:10-31: (rho, theta/pi, phi/(2 pi) + 0.5);
+    theta = 0 where rho = 0."""
+    rho = torch.sqrt((v * v).sum(-1, keepdim=True)).clamp(min=0)
+    theta = torch.acos(v[..., 2:3] / rho)
+    theta = torch.where(rho == 0, torch.zeros_like(theta), theta)
+    phi = torch.atan2(v[..., 1:2], v[..., 0:1])
+    return torch.cat([rho, theta / math.pi, phi / (2 * math.pi) + 0.5], -1)
+
+
+def umbrella_features(center, k=9, return_dist=True, sign=None):
+    """The per-point umbrella feature the reference feeds to UmbrellaSurfaceConstructor.mlps
+    (R/modules/pointnet2_utils.py:360-378): for every point, its k-1 nearest neighbours (self excluded) relative to
+    the point, sorted counter-clockwise by azimuth (:310-334), consecutive pairs (s_g, s_{g+1}) with the point itself
+    (the origin) form G = k-1 triangles; per triangle: centroid (recons_utils.py:cal_center), its spherical
+    coordinates, unit normal with the first triangle's x-component made positive (cal_normal, is_group=True), optional
+    per-cloud sign flip `sign` [B] (random_inv, drawn by the caller like recons_utils.py:50), plane constant
+    normal.centroid / sqrt(3) (cal_const); triangles with a NaN normal take normal / centroid / constant of the first
+    valid triangle of the same point (check_nan_umb; the polar channels keep their own values).
+    center [B,N,3] -> [B,N,G,10] (or 9 without the constant): centroid, polar, normal, constant."""
+    B, N, _ = center.shape
+    _, idx = knn_point(k, center, center)
+    rel = index_points(center, idx)[:, :, 1:] - center.unsqueeze(2)  # [B,N,G,3]
+    phi = sphere_coords(rel)[..., 2]
+    order = torch.argsort(phi, dim=-1, stable=True)
+    srt = torch.gather(rel, 2, order.unsqueeze(-1).expand(-1, -1, -1, 3))
+    nxt = torch.roll(srt, -1, dims=2)
+    nor = torch.cross(srt, nxt, dim=-1)  # (s_g - 0) x (s_{g+1} - 0)
+    unit = nor / torch.norm(nor, dim=-1, keepdim=True)
+    pos = (unit[:, :, 0:1, 0] > 0).float() * 2.0 - 1.0
+    unit = unit * pos.unsqueeze(-1)
+    if sign is not None:
+        unit = unit * sign.view(B, 1, 1, 1).to(unit.dtype)
+    cen = (torch.zeros_like(srt) + srt + nxt) / 3.0
+    polar = sphere_coords(cen)
+    const = (unit * cen).sum(-1, keepdim=True) / math.sqrt(3.0)
+    bad = torch.isnan(unit).any(-1)  # [B,N,G]
+    first = torch.argmax((~bad).int(), dim=-1)  # first valid triangle (0 when none is)
+    pick = first.view(B, N, 1, 1)
+    unit = torch.where(bad.unsqueeze(-1), torch.gather(unit, 2, pick.expand(-1, -1, 1, 3)).expand_as(unit), unit)
+    cen = torch.where(bad.unsqueeze(-1), torch.gather(cen, 2, pick.expand(-1, -1, 1, 3)).expand_as(cen), cen)
+    const = torch.where(bad.unsqueeze(-1), torch.gather(const, 2, pick).expand_as(const), const)
+    parts = [cen, polar, unit] + ([const] if return_dist else [])
+    return torch.cat(parts, -1)
+
+
+def umbrella_constructor(P, pre, center_b3n, ctx, k=9, aggr="sum", sign=None):
+    """UmbrellaSurfaceConstructor.forward, R/modules/pointnet2_utils.py:360-399 (return_dist=True): umbrella features
+    -> 1x1 Conv2d/BatchNorm2d/ReLU x2 -> Conv2d -> aggregate over the G triangles.  center [B,3,N] -> [B,10,N]."""
+    feat = umbrella_features(center_b3n.permute(0, 2, 1).contiguous(), k=k, return_dist=True, sign=sign)
+    x = feat.permute(0, 3, 2, 1)  # [B,C,G,N]
+    for conv, bn in (("0", "1"), ("3", "4")):
+        x = F.conv2d(x, P[pre + "mlps.%s.weight" % conv], P.get(pre + "mlps.%s.bias" % conv))
+        x = F.batch_norm(x, P[pre + "mlps.%s.running_mean" % bn], P[pre + "mlps.%s.running_var" % bn],
+                         P[pre + "mlps.%s.weight" % bn], P[pre + "mlps.%s.bias" % bn], ctx.train, 0.1, 1e-5)
+        x = F.relu(x)
+    x = F.conv2d(x, P[pre + "mlps.6.weight"], P[pre + "mlps.6.bias"])
+    if aggr == "max":
+        return x.max(2)[0]
+    if aggr == "avg":
+        return x.mean(2)
+    return x.sum(2)
+
+
+# --------------------------------------------------------------------------------------------------
 # deterministic synthetic parameters: a function of (key, shape) only, so the reference, the oracle
 # and the CUDA modules can all be loaded with identical weights without shipping a checkpoint.
 # --------------------------------------------------------------------------------------------------

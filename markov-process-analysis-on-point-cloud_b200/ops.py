@@ -215,6 +215,19 @@ def query_ball_point(radius, nsample, xyz, new_xyz, cuda=False):
     return out
 
 
+def xyz2sphere(xyz, normalize=True):
+    """R/modules/polar_utils.py:10-31: [..., 3] -> (rho, theta, phi), theta = 0 where rho = 0; normalised to
+    [0, 1] when `normalize`.  Elementwise on the device (coordinates carry no gradient on this path)."""
+    rho = torch.sqrt(torch.sum(torch.pow(xyz, 2), dim=-1, keepdim=True)).clamp(min=0)
+    theta = torch.acos(xyz[..., 2, None] / rho)
+    phi = torch.atan2(xyz[..., 1, None], xyz[..., 0, None])
+    theta = torch.where(rho == 0, torch.zeros_like(theta), theta)
+    if normalize:
+        theta = theta / np.pi
+        phi = phi / (2 * np.pi) + .5
+    return torch.cat([rho, theta, phi], dim=-1)
+
+
 @torch.no_grad()
 def umbrella_features(center, k=9, return_dist=True, sign=None):
     """The umbrella feature UmbrellaSurfaceConstructor feeds to its MLP (R/modules/pointnet2_utils.py:360-378):

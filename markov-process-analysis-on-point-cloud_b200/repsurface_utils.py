@@ -9,8 +9,136 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .ops import farthest_point_sample, index_points, knn_point, query_knn_point, square_distance  # noqa: F401
-from .pointnet2_utils import Linear, LocalTrans
+from .ops import (farthest_point_sample, index_points, knn_point, query_ball_point, query_knn_point,  # noqa: F401
+                  square_distance, xyz2sphere)
+from .pointnet2_utils import Linear, LocalTrans, UmbrellaSurfaceConstructor  # noqa: F401
+
+
+# ------------------------------------------------------------------------------------------------------
+# RepSurf set abstraction (R/modules/repsurface_utils.py:12-84, 206-319)
+# ------------------------------------------------------------------------------------------------------
+def sample_and_group(npoint, radius, nsample, center, normal, feature, return_normal=True, return_polar=False,
+                     cuda=False):
+    """R/modules/repsurface_utils.py:12-59: FPS -> ball query -> grouped (relative coordinates [+ polar], normal,
+    feature).  center [B,N,3], normal [B,N,Cn], feature [B,N,D] or None ->
+    (new_center [B,S,3], new_normal [B,S,Cn], new_feature [B,S,nsample,C'])."""
+    fps_idx = farthest_point_sample(center, npoint)
+    new_center = index_points(center, fps_idx)
+    new_normal = index_points(normal, fps_idx)
+    idx = query_ball_point(radius, nsample, center, new_center, cuda=cuda)
+    group_normal = index_points(normal, idx)
+    group_center_norm = index_points(center, idx) - new_center.unsqueeze(2)
+    if return_polar:
+        group_center_norm = torch.cat([group_center_norm, xyz2sphere(group_center_norm)], dim=-1)
+    if feature is not None:
+        group_feature = index_points(feature, idx)
+        new_feature = torch.cat([group_center_norm, group_normal, group_feature], dim=-1) if return_normal \
+            else torch.cat([group_center_norm, group_feature], dim=-1)
+    else:
+        new_feature = torch.cat([group_center_norm, group_normal], dim=-1)
+    return new_center, new_normal, new_feature
+
+
+def sample_and_group_all(center, normal, feature, return_normal=True, return_polar=False):
+    """R/modules/repsurface_utils.py:61-84: one group holding the whole cloud."""
+    B, N, C = normal.shape
+    new_center = torch.zeros(B, 1, 3, device=center.device)
+    new_normal = new_center
+    group_normal = normal.view(B, 1, N, C)
+    group_center = center.view(B, 1, N, 3)
+    if return_polar:
+        group_center = torch.cat([group_center, xyz2sphere(group_center)], dim=-1)
+    new_feature = torch.cat([group_center, group_normal, feature.view(B, 1, N, -1)], dim=-1) if return_normal \
+        else torch.cat([group_center, feature.view(B, 1, N, -1)], dim=-1)
+    return new_center, new_normal, new_feature
+
+
+def _conv_bn(x, conv, bn, slope):
+    """Conv2d(1x1) + BatchNorm2d [+ ReLU] of the reference on the channel-last row view [..., Cin]: the same
+    arithmetic as Linear -> BatchNorm over all leading axes -> LeakyReLU(slope) (slope 0 = ReLU, 1 = none), i.e. the
+    shared-MLP node of this repo (tcgen05 GEMM when Cin % 32 == 0, BatchNorm statistics from its epilogue)."""
+    return ops.linear_bn_act(x, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias, bn, bn.training,
+                             slope)
+
+
+class SurfaceAbstraction(nn.Module):
+    """R/modules/repsurface_utils.py:206-254, same constructor / forward / state_dict (mlp_convs.i, mlp_bns.i).
+    forward(center [B,3,N], normal [B,Cn,N], feature [B,D,N] or None) -> (new_center [B,3,S], new_normal [B,Cn,S],
+    new_feature [B,mlp[-1],S])."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all, return_polar=True, return_normal=True,
+                 cuda=False):
+        super().__init__()
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.return_normal = return_normal
+        self.return_polar = return_polar
+        self.cuda_ops = cuda  # the reference stores this as `self.cuda`, shadowing nn.Module.cuda()
+        self.group_all = group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last_channel, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last_channel = out_channel
+
+    def _group(self, center, normal, feature):
+        normal = normal.permute(0, 2, 1).contiguous()
+        center = center.permute(0, 2, 1).contiguous()
+        if feature is not None:
+            feature = feature.permute(0, 2, 1).contiguous()
+        if self.group_all:
+            return sample_and_group_all(center, normal, feature, return_polar=self.return_polar,
+                                        return_normal=self.return_normal)
+        return sample_and_group(self.npoint, self.radius, self.nsample, center, normal, feature,
+                                return_polar=self.return_polar, return_normal=self.return_normal, cuda=self.cuda_ops)
+
+    def forward(self, center, normal, feature):
+        new_center, new_normal, x = self._group(center, normal, feature)  # x [B,S,K,C] channel-last
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            x = _conv_bn(x, conv, bn, 0.0)
+        new_feature = torch.max(x, 2)[0].permute(0, 2, 1)  # max over the group -> [B,C,S]
+        return new_center.permute(0, 2, 1), new_normal.permute(0, 2, 1), new_feature
+
+
+class SurfaceAbstractionCD(SurfaceAbstraction):
+    """R/modules/repsurface_utils.py:256-319: the first layer is split into a position branch (mlp_l0 / bn_l0 over
+    the first pos_channel channels) and a feature branch (mlp_f0 / bn_f0), summed before the ReLU."""
+
+    def __init__(self, npoint, radius, nsample, feat_channel, pos_channel, mlp, group_all, return_normal=True,
+                 return_polar=False, cuda=False):
+        nn.Module.__init__(self)
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.return_normal = return_normal
+        self.return_polar = return_polar
+        self.cuda_ops = cuda
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        self.pos_channel = pos_channel
+        self.group_all = group_all
+        self.mlp_l0 = nn.Conv2d(self.pos_channel, mlp[0], 1)
+        self.mlp_f0 = nn.Conv2d(feat_channel, mlp[0], 1)
+        self.bn_l0 = nn.BatchNorm2d(mlp[0])
+        self.bn_f0 = nn.BatchNorm2d(mlp[0])
+        last_channel = mlp[0]
+        for out_channel in mlp[1:]:
+            self.mlp_convs.append(nn.Conv2d(last_channel, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last_channel = out_channel
+
+    def forward(self, center, normal, feature):
+        new_center, new_normal, x = self._group(center, normal, feature)
+        loc = _conv_bn(x[..., :self.pos_channel].contiguous(), self.mlp_l0, self.bn_l0, 1.0)
+        feat = _conv_bn(x[..., self.pos_channel:].contiguous(), self.mlp_f0, self.bn_f0, 1.0)
+        x = F.relu(loc + feat)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            x = _conv_bn(x, conv, bn, 0.0)
+        new_feature = torch.max(x, 2)[0].permute(0, 2, 1)
+        return new_center.permute(0, 2, 1), new_normal.permute(0, 2, 1), new_feature
 
 
 class LocalMerge(nn.Module):

@@ -515,6 +515,50 @@ def umbrella_constructor(P, pre, center_b3n, ctx, k=9, aggr="sum", sign=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# RepSurf set abstraction, R/modules/repsurface_utils.py:12-84, 206-319
+# --------------------------------------------------------------------------------------------------
+def sample_and_group(npoint, radius, nsample, center, normal, feature, ctx, return_normal=True, return_polar=False):
+    """R/modules/repsurface_utils.py:12-59 (channel-last tensors)."""
+    fps_idx = ctx.fps(center, npoint)
+    new_center = index_points(center, fps_idx)
+    new_normal = index_points(normal, fps_idx)
+    idx = query_ball_point(radius, nsample, center, new_center)
+    ctx.tape.append(("ball", idx))
+    group_normal = index_points(normal, idx)
+    rel = index_points(center, idx) - new_center.unsqueeze(2)
+    if return_polar:
+        rel = torch.cat([rel, sphere_coords(rel)], -1)
+    parts = [rel] + ([group_normal] if (return_normal or feature is None) else [])
+    if feature is not None:
+        parts.append(index_points(feature, idx))
+    return new_center, new_normal, torch.cat(parts, -1)
+
+
+def _conv_bn_relu(P, conv, bn, x, ctx, relu=True):
+    x = F.conv2d(x, P[conv + ".weight"], P[conv + ".bias"])
+    x = F.batch_norm(x, P[bn + ".running_mean"], P[bn + ".running_var"], P[bn + ".weight"], P[bn + ".bias"],
+                     ctx.train, 0.1, 1e-5)
+    return F.relu(x) if relu else x
+
+
+def surface_abstraction(P, pre, center, normal, feature, ctx, npoint, radius, nsample, n_layers, return_polar=True,
+                        return_normal=True, pos_channel=None):
+    """SurfaceAbstraction.forward (:229-254) or, with pos_channel, SurfaceAbstractionCD.forward (:287-319); group_all
+    = False.  Channel-first inputs [B,C,N] like the reference; returns (new_center [B,3,S], new_normal, new_feature)."""
+    c, n = center.permute(0, 2, 1), normal.permute(0, 2, 1)
+    f = feature.permute(0, 2, 1) if feature is not None else None
+    new_center, new_normal, g = sample_and_group(npoint, radius, nsample, c, n, f, ctx, return_normal, return_polar)
+    x = g.permute(0, 3, 2, 1)  # [B,C,K,S]
+    if pos_channel is not None:
+        loc = _conv_bn_relu(P, pre + "mlp_l0", pre + "bn_l0", x[:, :pos_channel], ctx, relu=False)
+        feat = _conv_bn_relu(P, pre + "mlp_f0", pre + "bn_f0", x[:, pos_channel:], ctx, relu=False)
+        x = F.relu(loc + feat)
+    for i in range(n_layers):
+        x = _conv_bn_relu(P, pre + "mlp_convs.%d" % i, pre + "mlp_bns.%d" % i, x, ctx)
+    return new_center.permute(0, 2, 1), new_normal.permute(0, 2, 1), x.max(2)[0]
+
+
+# --------------------------------------------------------------------------------------------------
 # deterministic synthetic parameters: a function of (key, shape) only, so the reference, the oracle
 # and the CUDA modules can all be loaded with identical weights without shipping a checkpoint.
 # --------------------------------------------------------------------------------------------------

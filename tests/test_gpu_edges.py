@@ -133,3 +133,21 @@ def test_classifier_config1_shape(mpc):
     finally:
         mpc.ops._STREAMS_ENABLED = old
     assert torch.equal(a, b)
+
+
+def test_reduction_scratch_is_left_zero(mpc):
+    """include/mpc_b200.h scratch contract: zero on entry, zero again once the consumer has run -- forward (GEMM
+    epilogue sums -> normalise kernel), backward (column reduction -> apply kernel) and the bias column sum."""
+    torch.manual_seed(0)
+    lin = mpc.pointnet2_utils.Linear(64, 128, bn=False).cuda().train()
+    x = torch.randn(4, 500, 64, device="cuda", requires_grad=True)
+    for _ in range(2):
+        lin(x).sum().backward()
+    q = torch.randn(2000, 64, device="cuda", requires_grad=True)
+    w = torch.randn(32, 64, device="cuda", requires_grad=True)
+    b = torch.zeros(32, device="cuda", requires_grad=True)
+    mpc.ops.linear(q, w, b).sum().backward()
+    torch.cuda.synchronize()
+    assert len(mpc.ops._scratch_pool) >= 3
+    for key, buf in mpc.ops._scratch_pool.items():
+        assert float(buf.abs().sum()) == 0.0, key

@@ -89,6 +89,10 @@ def load():
             fn.argtypes = args
             fn.restype = ctypes.c_int
         _lib = lib
+        # debug / tuning: MPC_KNOBS="id=value,..." applies mpc_debug_set_knob at load (A/B runs of bench.py)
+        for kv in filter(None, os.environ.get("MPC_KNOBS", "").split(",")):
+            k, v = kv.split("=")
+            lib.mpc_debug_set_knob(int(k), int(v))
     return _lib
 
 

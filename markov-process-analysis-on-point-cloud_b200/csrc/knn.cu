@@ -448,6 +448,163 @@ knn64x2_kernel(const float* __restrict__ ref, const float* __restrict__ qry, flo
     }
 }
 
+// ---- feature-space search, register-tiled (C % 64 == 0, C <= 256) ---------------------------------------------
+// knn64 / knn64x2 keep whole query vectors in registers and stream reference points through broadcast shared-memory
+// loads: 4-8 FFMA per LDS.128, shared-memory-issue bound (ncu) at 30-46 % of the FP32 peak.  This variant tiles the
+// distance computation like an SGEMM: a CTA of 128 threads owns 128 queries (transposed in shared memory for the whole
+// kernel) and walks the reference set in tiles of 64 points; a thread accumulates an 8 x 8 block of dot products
+// (64 FFMA per 4 LDS.128 = 16 per load), every dot product still ONE fma chain over c = 0..C-1 from 0 -- the
+// oracle's order, so indices stay bit-exact.  The finished 128 x 64 distance tile goes through shared memory to the
+// selection phase, where thread = query scans its row against its current K-th distance (the same queued insertion
+// as the other kernels).
+constexpr int KT_THREADS = 128;
+constexpr int KT_Q = 128;   // queries per CTA
+constexpr int KT_R = 64;    // reference points per tile
+constexpr int KT_CK = 64;   // channels per shared-memory chunk of the reference tile
+constexpr int KT_DLD = KT_R + 1;  // distance tile row pitch (odd: conflict-free row scans)
+
+template <int K>
+__global__ void __launch_bounds__(KT_THREADS, 2)
+knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
+                 int64_t* __restrict__ idx_out, int N, int S, int C) {
+    extern __shared__ __align__(16) float sm[];
+    float* qt = sm;                              // [C][KT_Q]   queries, transposed
+    float* rt = qt + (size_t)C * KT_Q;           // [KT_CK][KT_R] reference chunk, transposed
+    float* dt = rt + KT_CK * KT_R;               // [KT_Q][KT_DLD] distance tile
+    float* qn_s = dt + KT_Q * KT_DLD;            // [KT_Q]
+    float* rn_s = qn_s + KT_Q;                   // [KT_R]
+    __shared__ CandQueue queue;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int tx = tid & 7, ty = tid >> 3;       // 8 x 16 thread grid: columns tx*4+{0..3}, 32+tx*4+{0..3}; rows alike
+    const int q0 = blockIdx.x * KT_Q;
+    const float* rb = ref + (size_t)b * N * C;
+    const float* qb = qry + (size_t)b * S * C;
+    // Transposed tiles are stored with the 4-column groups of row c XOR-swizzled by (c / 4): lanes that read 16
+    // consecutive float4 of one point (coalesced 256-byte global rows) then hit 16 different bank groups, and the
+    // compute loop's float4 reads of one row stay conflict-free (the XOR term is uniform per row).
+    auto swz = [](int c, int col, int groups) { return ((((col >> 2) ^ (c >> 2)) & (groups - 1)) << 2) | (col & 3); };
+    // queries -> shared (transposed), once
+    for (int i = tid; i < KT_Q * (C / 4); i += KT_THREADS) {
+        const int c4 = (i % (C / 4)) * 4, q = i / (C / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + q < S) v = __ldg(reinterpret_cast<const float4*>(qb + (size_t)(q0 + q) * C + c4));
+        const int col = swz(c4, q, KT_Q / 4);
+        qt[(c4 + 0) * KT_Q + col] = v.x;
+        qt[(c4 + 1) * KT_Q + col] = v.y;
+        qt[(c4 + 2) * KT_Q + col] = v.z;
+        qt[(c4 + 3) * KT_Q + col] = v.w;
+    }
+    __syncthreads();
+    {   // |q|^2, sequential non-fused like the oracle; thread = query
+        float a = __fmul_rn(qt[swz(0, tid, KT_Q / 4)], qt[swz(0, tid, KT_Q / 4)]);
+        for (int c = 1; c < C; ++c) {
+            const float v = qt[c * KT_Q + swz(c, tid, KT_Q / 4)];
+            a = __fadd_rn(a, __fmul_rn(v, v));
+        }
+        qn_s[tid] = a;
+    }
+    const int s = q0 + tid;
+    const bool active = s < S;
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        bd[k] = __int_as_float(0x7f800000);
+        bi[k] = 0;
+    }
+    float thr = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+    int qcnt = 0;
+    for (int t0 = 0; t0 < N; t0 += KT_R) {
+        const int tn = min(KT_R, N - t0);
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        float rnorm = 0.f;  // thread j < 64: running |r_j|^2 across the channel chunks
+        for (int c0 = 0; c0 < C; c0 += KT_CK) {
+            __syncthreads();  // previous chunk / previous tile's selection are done with rt, dt
+            for (int i = tid; i < KT_R * (KT_CK / 4); i += KT_THREADS) {
+                const int c4 = (i % (KT_CK / 4)) * 4, j = i / (KT_CK / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < tn) v = __ldg(reinterpret_cast<const float4*>(rb + (size_t)(t0 + j) * C + c0 + c4));
+                const int col = swz(c4, j, KT_R / 4);
+                rt[(c4 + 0) * KT_R + col] = v.x;
+                rt[(c4 + 1) * KT_R + col] = v.y;
+                rt[(c4 + 2) * KT_R + col] = v.z;
+                rt[(c4 + 3) * KT_R + col] = v.w;
+            }
+            __syncthreads();
+            if (tid < KT_R) {
+                int c = 0;
+                if (c0 == 0) {
+                    const float v0 = rt[swz(0, tid, KT_R / 4)];
+                    rnorm = __fmul_rn(v0, v0);
+                    c = 1;
+                }
+                for (; c < KT_CK; ++c) {
+                    const float v = rt[c * KT_R + swz(c, tid, KT_R / 4)];
+                    rnorm = __fadd_rn(rnorm, __fmul_rn(v, v));
+                }
+            }
+            const float* qc = qt + (size_t)c0 * KT_Q;
+#pragma unroll 4
+            for (int c = 0; c < KT_CK; ++c) {
+                const int g = c >> 2, gq = (c0 + c) >> 2;  // swizzle terms: chunk-local row (rt), global channel (qt)
+                const float4 qa = *reinterpret_cast<const float4*>(qc + c * KT_Q + (((ty) ^ gq) & 31) * 4);
+                const float4 qb4 = *reinterpret_cast<const float4*>(qc + c * KT_Q + (((16 + ty) ^ gq) & 31) * 4);
+                const float4 ra = *reinterpret_cast<const float4*>(rt + c * KT_R + (((tx) ^ g) & 15) * 4);
+                const float4 rb4 = *reinterpret_cast<const float4*>(rt + c * KT_R + (((8 + tx) ^ g) & 15) * 4);
+                const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb4.x, qb4.y, qb4.z, qb4.w};
+                const float rv[8] = {ra.x, ra.y, ra.z, ra.w, rb4.x, rb4.y, rb4.z, rb4.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(qv[i], rv[j], acc[i][j]);
+            }
+        }
+        if (tid < KT_R) rn_s[tid] = rnorm;
+        __syncthreads();
+        // distance tile: d = ((-2 dot) + |q|^2) + |r|^2, the reference's order
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int qi = (i < 4 ? 0 : 60) + ty * 4 + i;  // rows ty*4+{0..3}, 64+ty*4+{0..3}
+            const float qn = qn_s[qi];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int rj = (j < 4 ? 0 : 28) + tx * 4 + j;  // cols tx*4+{0..3}, 32+tx*4+{0..3}
+                dt[qi * KT_DLD + rj] = sqdist_from_dot(acc[i][j], qn, rn_s[rj]);
+            }
+        }
+        __syncthreads();
+        // selection: thread = query, candidates in ascending index order
+        const float* row = dt + tid * KT_DLD;
+#pragma unroll 1
+        for (int j0 = 0; j0 < KT_R; j0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                const float d = row[j];
+                if (j < tn && d < thr) {
+                    queue.d[qcnt][tid] = d;
+                    queue.i[qcnt][tid] = t0 + j;
+                    ++qcnt;
+                }
+            }
+            if (__any_sync(0xffffffffu, qcnt > KNN_QFLUSH)) drain_queue<K>(queue, qcnt, bd, bi, thr);
+        }
+    }
+    drain_queue<K>(queue, qcnt, bd, bi, thr);
+    if (active) {
+        const size_t o = ((size_t)b * S + s) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (dist_out) dist_out[o + k] = bd[k];
+            idx_out[o + k] = bi[k];
+        }
+    }
+}
+
 // ---- generic C ------------------------------------------------------------------------------------------------
 // CTA = 128 queries.  Queries live in shared memory [q][C+1]; reference tiles of 32 points are stored
 // transposed [c][32+4]; a thread advances 8 reference points at once.
@@ -571,6 +728,23 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
             knn3_kernel<K, 4><<<grid, 128, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
         else
             knn3_kernel<K, 16><<<grid, 512, 0, st>>>(ref, qry, dist_out, idx_out, N, S);
+        MPC_LAUNCH_CHECK();
+        return MPC_OK;
+    }
+    const bool al = (reinterpret_cast<uintptr_t>(ref) & 15u) == 0 && (reinterpret_cast<uintptr_t>(qry) & 15u) == 0;
+    if (al && C % 64 == 0 && C <= 256 && K <= 16 && g_knob[4] != 1 &&
+        (C >= 128 || N <= 8192 || g_knob[4] == 2)) {
+        // register-tiled variant.  C = 128 / 192 / 256: 2x the generic kernel below.  C = 64: alone it is no faster
+        // than the query-in-registers kernels (19-21 vs 23-28 TFLOP/s; 3-register FFMA issues at one warp
+        // instruction per 2 cycles per scheduler, ~37 TFLOP/s is the SIMT ceiling and both designs show "issue slots
+        // busy 50 %" in ncu), but inside the training step, where the search shares the GPU with the other two
+        // branches of its LocalMerge, it is worth 5 % of the step (12.97 vs 13.62 ms, A/B on one box); for the
+        // 24 000-point blocks the old kernels stay ahead (21.8 vs 28.2 ms per search).  (knob 4: 1 = never, 2 = always)
+        const size_t smem = ((size_t)C * KT_Q + KT_CK * KT_R + KT_Q * KT_DLD + KT_Q + KT_R) * sizeof(float);
+        auto kern = knn_tiled_kernel<(K <= 16 ? K : 16)>;
+        MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)ceil_div(S, KT_Q), (unsigned)B);
+        kern<<<grid, KT_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C);
         MPC_LAUNCH_CHECK();
         return MPC_OK;
     }

@@ -9,13 +9,14 @@
 // which recovers ~fp32 accuracy at one third of the TF32 rate -- still ~5x the FP32 SIMT pipe, enough to put
 // every layer width of both models back under the HBM roofline.
 //
-// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warps 0-3  epilogue   : tcgen05.ld accumulator rows (TMEM lane = output row), + bias, 128-bit global stores
-//   warps 4-7  splitters  : wait for a TMA stage, split A and B tiles in place into hi / lo, fence to the
-//                           async proxy, hand the stage to the MMA warp
-//   warp  8    TMA producer (one elected lane): cp.async.bulk.tensor 2D, 128B swizzle, fp32 boxes 32 x 128 (A)
+// Structure (one persistent CTA per SM, 448 threads, warp-specialised):
+//   warps 0-3   epilogue  : each warp owns 32 accumulator rows (TMEM lanes) end to end: tcgen05.ld, + bias, its own
+//                           4 KB swizzled staging slab, its own 32 x 32 TMA store -- no CTA-level barrier per slab
+//   warps 4-11  splitters : wait for a TMA stage, write lo = x - trunc_tf32(x) next to the raw tile (which doubles as
+//                           the hi term), fence to the async proxy, hand the stage to the MMA warp
+//   warp  12    TMA producer (one elected lane): cp.async.bulk.tensor 2D, 128B swizzle, fp32 boxes 32 x 128 (A)
 //                           and 32 x BLOCK_N (B) per stage
-//   warp  9    MMA issuer (one elected lane) + TMEM allocation: 12 tcgen05.mma.kind::tf32 per stage
+//   warp  13    MMA issuer (one elected lane) + TMEM allocation: 12 tcgen05.mma.kind::tf32 per stage
 //                           (4 K-steps of 8 x 3 split terms), tcgen05.commit frees the stage / publishes the tile
 // Pipelines: smem stages (full -> split -> empty), 2 TMEM accumulator stages (tmem_full / tmem_empty), so the
 // epilogue of tile i overlaps the main loop of tile i+1.
@@ -32,7 +33,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;               // fp32 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;  // warps 0-3 epilogue, 4-11 splitters, 12 TMA producer, 13 MMA issuer
+constexpr int SPLIT_THREADS = 256;
 constexpr int MAX_STAGES = 6;
 constexpr uint32_t TF32_MASK = 0xffffe000u;
 
@@ -165,8 +167,8 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __shared__ uint64_t bar_full[MAX_STAGES], bar_split[MAX_STAGES], bar_empty[MAX_STAGES];
     __shared__ uint64_t bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float stat_red[2][4][32];
-    __shared__ double stat_acc[2][256];  // per-CTA column sums over all of this CTA's tiles (one atomic per column)
+    __shared__ float stat_accw[4][2][256];  // per-epilogue-warp column sums over all of this CTA's tiles; combined in
+                                            // fp64 at the end: one atomic per column per CTA
 
     // programmatic dependent launch: let the next kernel in the stream start its own prologue now ...
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -193,7 +195,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_split[s], 128);
+            mbar_init(&bar_split[s], SPLIT_THREADS);
             mbar_init(&bar_empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -217,19 +219,19 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.zero_n4; i += (long long)gridDim.x * 256)
             p.zero_ptr[i] = z;
     }
-    if (warp == 9) {  // TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns
+    if (warp == 13) {  // TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                      "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    if (warp == 9 || warp < 4) {  // only the MMA issuer and the epilogue warps need the TMEM address
+    if (warp == 13 || warp < 4) {  // only the MMA issuer and the epilogue warps need the TMEM address
         tc_fence_before();
         asm volatile("bar.sync 2, 160;" ::: "memory");
         tc_fence_after();
         tmem_base = tmem_base_slot;
     }
 
-    if (warp == 8) {
+    if (warp == 12) {
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0, tn_ = 0;
@@ -262,7 +264,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 12) {
         // ===== splitters: lo = x - trunc_tf32(x) next to the raw tile, 16 bytes per thread per step =====
         const int t = threadIdx.x - 128;
         int it = 0, tn_ = 0;
@@ -288,27 +290,27 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & TF32_MASK));
                 };
                 {   // all loads first (independent), then split + store: one shared-memory latency, not eight
-                    uint4 v[A_TILE_BYTES / 16 / 128];
+                    uint4 v[A_TILE_BYTES / 16 / SPLIT_THREADS];
 #pragma unroll
-                    for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) v[i] = a_hi[t + i * 128];
+                    for (int i = 0; i < A_TILE_BYTES / 16 / SPLIT_THREADS; ++i) v[i] = a_hi[t + i * SPLIT_THREADS];
 #pragma unroll
-                    for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+                    for (int i = 0; i < A_TILE_BYTES / 16 / SPLIT_THREADS; ++i) {
                         uint4 lo;
                         split(v[i], lo);
-                        a_lo[t + i * 128] = lo;
+                        a_lo[t + i * SPLIT_THREADS] = lo;
                     }
                 }
-                for (int i0 = t; i0 < b_tile_bytes / 16; i0 += 4 * 128) {
+                for (int i0 = t; i0 < b_tile_bytes / 16; i0 += 4 * SPLIT_THREADS) {
                     uint4 v[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (i0 + u * 128 < b_tile_bytes / 16) v[u] = b_hi[i0 + u * 128];
+                        if (i0 + u * SPLIT_THREADS < b_tile_bytes / 16) v[u] = b_hi[i0 + u * SPLIT_THREADS];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (i0 + u * 128 < b_tile_bytes / 16) {
+                        if (i0 + u * SPLIT_THREADS < b_tile_bytes / 16) {
                             uint4 lo;
                             split(v[u], lo);
-                            b_lo[i0 + u * 128] = lo;
+                            b_lo[i0 + u * SPLIT_THREADS] = lo;
                         }
                 }
                 fence_async_proxy();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -316,7 +318,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 if (t == 0) MPC_TRACE(1, tn_);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         // ===== MMA issuer =====
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10),
@@ -364,56 +366,68 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows 32w..32w+31 of the tile =====
         int tile_it = 0, tn_ = 0, slab_it = 0;
-        int stat_n0 = -1;  // column offset the per-CTA statistics accumulators currently belong to
-        auto stat_flush = [&]() {  // warp 0 only: lane owns columns lane, lane + 32, ...
+        int stat_n0 = -1;  // column offset the statistics accumulators currently belong to
+        int bias_n0 = -1;  // column offset bias_s currently holds
+        float* my_acc0 = &stat_accw[warp][0][0];
+        float* my_acc1 = &stat_accw[warp][1][0];
+        auto stat_flush = [&]() {  // all four epilogue warps: combine the per-warp sums in fp64, warp 0 publishes
             if (stat_n0 < 0) return;
-            for (int i = lane; i < p.block_n; i += 32)
-                if (stat_n0 + i < p.N) {
-                    atomicAdd(p.stat_sum + stat_n0 + i, stat_acc[0][i]);
-                    atomicAdd(p.stat_sum + p.N + stat_n0 + i, stat_acc[1][i]);
-                }
+            epi_barrier();
+            if (warp == 0)
+                for (int i = lane; i < p.block_n; i += 32)
+                    if (stat_n0 + i < p.N) {
+                        const double a = (double)stat_accw[0][0][i] + (double)stat_accw[1][0][i] +
+                                         (double)stat_accw[2][0][i] + (double)stat_accw[3][0][i];
+                        const double b = (double)stat_accw[0][1][i] + (double)stat_accw[1][1][i] +
+                                         (double)stat_accw[2][1][i] + (double)stat_accw[3][1][i];
+                        atomicAdd(p.stat_sum + stat_n0 + i, a);
+                        atomicAdd(p.stat_sum + p.N + stat_n0 + i, b);
+                    }
+            epi_barrier();
         };
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
             int mt, nt, kc0, kc1;
             decode(tile, mt, nt, kc0, kc1);
-            if (p.stat_sum && warp == 0 && nt * p.block_n != stat_n0) {
-                stat_flush();
-                stat_n0 = nt * p.block_n;
-                for (int i = lane; i < p.block_n; i += 32) stat_acc[0][i] = stat_acc[1][i] = 0.0;
-            }
             const int as = tile_it & 1;
             const uint32_t aph = (tile_it >> 1) & 1;
             const int row = mt * BLOCK_M + warp * 32 + lane;
             const int n0 = nt * p.block_n;
-            if (p.tma_out) {
-                // bias of this tile's columns -> shared (broadcast reads below), fetched while the main loop of
-                // this tile is still running; the first barrier orders the reuse of bias_s across tiles
+            if (p.stat_sum && n0 != stat_n0) {  // (the four warps walk the same tile sequence: uniform decision)
+                stat_flush();
+                stat_n0 = n0;
+                for (int i = lane; i < p.block_n; i += 32) my_acc0[i] = my_acc1[i] = 0.f;
+            }
+            if (p.tma_out && n0 != bias_n0) {
+                // bias of this column tile -> shared (broadcast reads below); reloaded only when the column tile
+                // changes, which for a persistent CTA is once per kernel in every layer of both models
                 epi_barrier();
                 for (int i = threadIdx.x; i < p.block_n; i += 128)
                     bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+                epi_barrier();
+                bias_n0 = n0;
             }
             mbar_wait(&bar_tmem_full[as], aph);
             if (threadIdx.x == 0) MPC_TRACE(3, tn_);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(warp * 32) << 16);
             if (p.tma_out) {
-                epi_barrier();
-                const int r_in = warp * 32 + lane;  // row inside the tile = TMEM lane
+                const int rows_valid = min(32, p.M - (mt * BLOCK_M + warp * 32));  // rows of this warp inside M
                 for (int c = 0; c < p.block_n; c += 32, ++slab_it) {
-                    uint8_t* staging = staging0 + (p.epi_bufs == 2 ? (slab_it & 1) * STAGING_BYTES : 0);
-                    uint4* srow = reinterpret_cast<uint4*>(staging + r_in * 128);
+                    // this warp's 4 KB slab (32 rows x 128 B, 1024-aligned: the 128B swizzle pattern repeats every 8 rows)
+                    uint8_t* staging = staging0 + (p.epi_bufs == 2 ? (slab_it & 1) * STAGING_BYTES : 0) + warp * 4096;
+                    uint4* srow = reinterpret_cast<uint4*>(staging + lane * 128);
                     uint32_t r0[16], r1[16];
                     tmem_ld16(taddr + c, r0);
                     tmem_ld16(taddr + c + 16, r1);
                     tmem_ld_wait();
-                    // the TMA store that last used this staging slab must have finished READING it
-                    if (threadIdx.x == 0) {
+                    // the TMA store of this warp that last used this slab must have finished READING it
+                    if (lane == 0) {
                         if (p.epi_bufs == 2)
                             bulk_wait_read1();
                         else
                             bulk_wait_read0();
                     }
-                    epi_barrier();
+                    __syncwarp();
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {  // 8 x 16 B of this row, 128B-swizzled like the TMA box expects
                         const uint32_t* src = q4 < 4 ? &r0[q4 * 4] : &r1[(q4 - 4) * 4];
@@ -422,43 +436,32 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         o.y = __float_as_uint(__uint_as_float(src[1]) + bias_s[c + q4 * 4 + 1]);
                         o.z = __float_as_uint(__uint_as_float(src[2]) + bias_s[c + q4 * 4 + 2]);
                         o.w = __float_as_uint(__uint_as_float(src[3]) + bias_s[c + q4 * 4 + 3]);
-                        srow[q4 ^ (r_in & 7)] = o;
+                        srow[q4 ^ (lane & 7)] = o;
                     }
                     fence_async_proxy();
-                    epi_barrier();
-                    if (threadIdx.x == 0) {
+                    __syncwarp();
+                    if (lane == 0 && rows_valid > 0) {
                         if (p.splits > 1)
-                            tma_reduce_add_2d(&map_y, staging, n0 + c, mt * BLOCK_M);
+                            tma_reduce_add_2d(&map_y, staging, n0 + c, mt * BLOCK_M + warp * 32);
                         else
-                            tma_store_2d(&map_y, staging, n0 + c, mt * BLOCK_M);
-                        bulk_commit();
+                            tma_store_2d(&map_y, staging, n0 + c, mt * BLOCK_M + warp * 32);
                     }
+                    if (lane == 0) bulk_commit();
                     if (p.stat_sum) {
-                        // BatchNorm statistics of this slab straight from shared memory: lane = column, warp =
-                        // group of 32 rows (conflict-free: one 128-byte row per step), rows beyond M excluded
+                        // BatchNorm statistics of this warp's 32 x 32 slab straight from shared memory: lane = column
+                        // (conflict-free: one 128-byte row per step), rows beyond M excluded
                         const float* sf = reinterpret_cast<const float*>(staging);
-                        const int rows_valid = min(BLOCK_M, p.M - mt * BLOCK_M);
                         float su = 0.f, sq2 = 0.f;
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r) {
-                            const int rr = warp * 32 + r;
-                            if (rr < rows_valid) {
-                                const float v = sf[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+                            if (r < rows_valid) {
+                                const float v = sf[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
                                 su += v;
                                 sq2 = fmaf(v, v, sq2);
                             }
                         }
-                        stat_red[0][warp][lane] = su;
-                        stat_red[1][warp][lane] = sq2;
-                        epi_barrier();
-                        if (warp == 0) {
-                            const double a = (double)stat_red[0][0][lane] + (double)stat_red[0][1][lane] +
-                                             (double)stat_red[0][2][lane] + (double)stat_red[0][3][lane];
-                            const double b = (double)stat_red[1][0][lane] + (double)stat_red[1][1][lane] +
-                                             (double)stat_red[1][2][lane] + (double)stat_red[1][3][lane];
-                            stat_acc[0][c + lane] += a;
-                            stat_acc[1][c + lane] += b;
-                        }
+                        my_acc0[c + lane] += su;
+                        my_acc1[c + lane] += sq2;
                     }
                 }
             } else {
@@ -500,13 +503,13 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             mbar_arrive(&bar_tmem_empty[as]);
             if (threadIdx.x == 0) MPC_TRACE(3, tn_);
         }
-        if (p.stat_sum && warp == 0) stat_flush();
+        if (p.stat_sum) stat_flush();
+        if (lane == 0 && p.tma_out) bulk_wait0();  // this warp's staged results have left shared memory
     }
 
-    if (threadIdx.x == 0 && p.tma_out) bulk_wait0();  // staged results have left shared memory
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 13) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
@@ -593,7 +596,7 @@ static cudaError_t launch_pdl(int grid, size_t smem, cudaStream_t st, const CUte
 // Shared-memory budget (224 KB opt-in, 1 KB alignment slack): as many operand stages as fit; a second epilogue
 // staging slab only if at least 3 operand stages remain (TMA latency ~1.3 us needs >= 3 stages in flight).
 static void pick_pipeline(int stage_bytes, int* stages, int* epi_bufs) {
-    const int budget = 217 * 1024 - EPI_BIAS_BYTES;  // 227 KB per CTA minus static shared memory and alignment slack
+    const int budget = 214 * 1024 - EPI_BIAS_BYTES;  // 227 KB per CTA minus static shared memory and alignment slack
     int s2 = (budget - 2 * STAGING_BYTES) / stage_bytes;
     int s1 = (budget - STAGING_BYTES) / stage_bytes;
     if (s2 >= 3) {
@@ -608,7 +611,7 @@ static void pick_pipeline(int stage_bytes, int* stages, int* epi_bufs) {
 static cudaError_t ensure_smem_optin() {
     static bool done = false;  // idempotent attribute; a benign race at worst sets it twice
     if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024);  // + 7 KB static <= 227 KB
+    cudaError_t e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + ~10 KB static <= 227 KB
     done = e == cudaSuccess;
     return e;
 }
@@ -679,7 +682,7 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     if (rc) return rc;
     CUtensorMap map_y = map_a;  // placeholder when results are stored directly
     if (tma_out) {
-        rc = make_map(&map_y, y, M, N, ldy, BLOCK_M);  // box 32 columns x 128 rows, 128B swizzle
+        rc = make_map(&map_y, y, M, N, ldy, 32);  // box 32 columns x 32 rows (one epilogue warp), 128B swizzle
         if (rc) return rc;
     }
     const size_t smem = (size_t)stages * stage_bytes + p.epi_bufs * STAGING_BYTES + EPI_BIAS_BYTES + 1024;
@@ -746,7 +749,7 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     }
     CUtensorMap map_y = map_a;
     if (p.tma_out) {
-        rc = make_map(&map_y, gw, N, K, ldw, BLOCK_M);  // TMA reduce-add (or store) of 32 x 128 slabs
+        rc = make_map(&map_y, gw, N, K, ldw, 32);  // TMA reduce-add (or store) of 32 x 32 slabs
         if (rc) return rc;
     }
     const size_t smem = (size_t)stages * stage_bytes + p.epi_bufs * STAGING_BYTES + EPI_BIAS_BYTES + 1024;
@@ -807,7 +810,7 @@ MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, i
     if (rc) return rc;
     CUtensorMap map_y = map_a;
     if (p.tma_out) {
-        rc = make_map(&map_y, gx, M, K, ldx, BLOCK_M);
+        rc = make_map(&map_y, gx, M, K, ldx, 32);
         if (rc) return rc;
     }
     const size_t smem = (size_t)stages * stage_bytes + p.epi_bufs * STAGING_BYTES + EPI_BIAS_BYTES + 1024;

@@ -86,3 +86,36 @@ def test_knn_million_point_reference_set(mpc):
     got = idx[0, :256]
     same = (got.sort(dim=1).values == ref.sort(dim=1).values).float().mean()
     assert same > 0.999  # fp32 vs fp64 distances may swap a near-tie at the k-th place
+
+
+@pytest.fixture()
+def tiled_knn(mpc):
+    """Force the register-tiled feature-space kNN kernel regardless of the query count."""
+    lib = mpc._lib.load()
+    lib.mpc_debug_set_knob(4, 2)
+    yield
+    lib.mpc_debug_set_knob(4, 0)
+
+
+@pytest.mark.parametrize("B,N,S,C,K", [(2, 300, 200, 64, 8), (1, 1000, 1000, 128, 16), (2, 513, 129, 256, 8),
+                                       (3, 2048, 2048, 64, 8), (1, 64, 1, 64, 3), (2, 4100, 700, 64, 9)])
+def test_knn_tiled_variant_bit_exact(mpc, orc, tiled_knn, B, N, S, C, K):
+    g = torch.Generator().manual_seed(N + S + C)
+    ref = torch.randn(B, N, C, generator=g)
+    qry = torch.randn(B, S, C, generator=g)
+    if S <= N:
+        qry[:, : S // 2] = ref[:, : S // 2]  # self-queries: distance ~0 first
+    d0, i0 = orc.knn_point(K, ref, qry)
+    d1, i1 = mpc.ops.knn_point(K, ref.cuda(), qry.cuda())
+    assert torch.equal(i1.cpu(), i0)
+    assert torch.equal(d1.cpu(), d0)
+
+
+def test_knn_tiled_variant_identical_features(mpc, orc, tiled_knn):
+    """After a transition many points share one feature vector: exact ties must resolve to the lower index."""
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(1, 40, 64, generator=g)
+    ref = base[:, torch.randint(0, 40, (600,), generator=g)]
+    d0, i0 = orc.knn_point(8, ref, ref[:, :300].contiguous())
+    d1, i1 = mpc.ops.knn_point(8, ref.cuda(), ref[:, :300].contiguous().cuda())
+    assert torch.equal(i1.cpu(), i0) and torch.equal(d1.cpu(), d0)

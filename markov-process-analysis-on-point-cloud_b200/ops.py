@@ -481,11 +481,17 @@ class FeatAttention(torch.autograd.Function):
         if zeroed:  # each dgrad launch also clears the split-reduction target of the wgrad GEMM that follows
             g_center = _tc_dgrad(gq, wq, c2d, zero=gwq).view(B, S, Cin)
             g_feat = _tc_dgrad(gkv, wkv, f2d, zero=gwkv).view(B, N, Cin)
-        call("mpc_linear_wgrad_f32", ptr(gq), _i64(C), ptr(c2d), _i64(Cin), ptr(gwq), _i64(Cin), _i64(B * S),
-             _i64(Cin), _i64(C), _i64(1 if zeroed else 0), algo_bytes=(B * S * (Cin + C) + C * Cin) * 4)
-        call("mpc_linear_wgrad_f32", ptr(gkv), _i64(2 * C), ptr(f2d), _i64(Cin), ptr(gwkv), _i64(Cin), _i64(B * N),
-             _i64(Cin), _i64(2 * C), _i64(1 if zeroed else 0),
-             algo_bytes=(B * N * (Cin + 2 * C) + 2 * C * Cin) * 4)
+        def wgrads():
+            call("mpc_linear_wgrad_f32", ptr(gq), _i64(C), ptr(c2d), _i64(Cin), ptr(gwq), _i64(Cin), _i64(B * S),
+                 _i64(Cin), _i64(C), _i64(1 if zeroed else 0), algo_bytes=(B * S * (Cin + C) + C * Cin) * 4)
+            call("mpc_linear_wgrad_f32", ptr(gkv), _i64(2 * C), ptr(f2d), _i64(Cin), ptr(gwkv), _i64(Cin),
+                 _i64(B * N), _i64(Cin), _i64(2 * C), _i64(1 if zeroed else 0),
+                 algo_bytes=(B * N * (Cin + 2 * C) + 2 * C * Cin) * 4)
+
+        if zeroed and _DEFER_WGRAD and _STREAMS_ENABLED:
+            _defer_wgrad(wgrads, (gq, c2d, gkv, f2d, gwq, gwkv))  # off the critical path, see _defer_wgrad
+        else:
+            wgrads()
         return (g_center, g_feat, None, gwq, gbias[:C], gwkv[:C], gbias[C:2 * C], gwkv[C:], gbias[2 * C:])
 
 
@@ -617,6 +623,35 @@ def bn_act(y2d, gamma, beta, running_mean, running_var, num_batches_tracked, tra
 # ------------------------------------------------------------------------------------------------------
 # shared-MLP projection on the tensor cores
 # ------------------------------------------------------------------------------------------------------
+# Weight gradients off the backward critical path: only the optimiser (after backward) reads them, so the wgrad GEMM
+# of a Linear+BN block is issued on a dedicated stream and joined once, by an autograd end-of-backward callback.
+_DEFER_WGRAD = os.environ.get("MPC_DEFER_WGRAD", "1") == "1"
+_wgrad_streams = {}
+_wgrad_pending = set()
+
+
+def _defer_wgrad(fn, tensors):
+    cur = torch.cuda.current_stream()
+    st = _wgrad_streams.get(cur.device)
+    if st is None:
+        st = _wgrad_streams[cur.device] = torch.cuda.Stream(device=cur.device)
+    st.wait_stream(cur)  # everything issued so far (the operands, the cleared output) is visible
+    with torch.cuda.stream(st):
+        fn()
+    for t in tensors:
+        if t is not None:
+            t.record_stream(st)
+    if cur.device not in _wgrad_pending:
+        _wgrad_pending.add(cur.device)
+        dev = cur.device
+
+        def join():
+            _wgrad_pending.discard(dev)
+            torch.cuda.current_stream(dev).wait_stream(st)
+
+        torch.autograd.Variable._execution_engine.queue_callback(join)
+
+
 # dgrad || wgrad of a Linear+BN block on two streams: measured 2 % SLOWER on the part-seg step (both GEMMs want every
 # SM), so off by default
 _BWD_PAIR = os.environ.get("MPC_BWD_PAIR", "0") == "1"
@@ -797,6 +832,11 @@ class LinearBNAct(torch.autograd.Function):
         if ctx.needs_input_grad[0] and tc_wgrad and _BWD_PAIR:
             # grad-input and grad-weight only share their input: side by side (two graph branches)
             gx, _ = parallel(lambda: _tc_dgrad(gy, w, x2d), wgrad)
+        elif ctx.needs_input_grad[0] and tc_wgrad and _DEFER_WGRAD and _STREAMS_ENABLED:
+            # nothing upstream waits for a weight gradient: it runs on the weight-gradient stream, ordered after the
+            # BatchNorm backward above, and rejoins at the end of the backward pass (see _defer_wgrad)
+            _defer_wgrad(wgrad, (gy, x2d, flat))
+            gx = _tc_dgrad(gy, w, x2d)
         else:
             if ctx.needs_input_grad[0]:
                 gx = _tc_dgrad(gy, w, x2d)

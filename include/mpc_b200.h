@@ -244,6 +244,20 @@ int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, int64_t l
                          int64_t M, int64_t K, int64_t N, int64_t gw_is_zero, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Label-smoothed cross entropy of the part-seg head.  Replaces get_loss.forward,
+ * R/models/repsurf/pointnet2_part_seg_msg.py:159-180 (one_hot smoothing + log_softmax + sum + mean; ~10 launches).
+ *   pred [M,C] f32 with row stride ld floats, target [M] i64, eps = smoothing (0.1 in the reference);
+ *   fwd: lse [M] f32 (log-sum-exp per row, kept for backward), loss [1] f32 = mean over rows; scratch: 2 doubles under
+ *   the scratch contract below (zero on entry, zero on exit).
+ *   bwd: grad_pred [M,C] (row stride ldg) = grad_loss[0] / M * (softmax(pred) - smoothed target).
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_smooth_ce_fwd_f32(const float* pred, int64_t ld, const int64_t* target, float eps, float* lse, float* loss,
+                          double* scratch, int64_t M, int64_t C, mpc_stream_t stream);
+int mpc_smooth_ce_bwd_f32(const float* pred, int64_t ld, const int64_t* target, float eps, const float* lse,
+                          const float* grad_loss, float* grad_pred, int64_t ldg, int64_t M, int64_t C,
+                          mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Umbrella surface features.  Replaces group_by_umbrella + cal_normal(is_group=True) +
  * cal_center + xyz2sphere + cal_const + check_nan_umb as composed by UmbrellaSurfaceConstructor.forward,
  * R/modules/pointnet2_utils.py:310-378 (helpers in R/modules/recons_utils.py, R/modules/polar_utils.py:10-31).

@@ -44,6 +44,8 @@ SIGNATURES = {
     "mpc_bn_finalize_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i64, _i64, _ptr],
     "mpc_linear_wgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr],
     "mpc_linear_dgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
+    "mpc_smooth_ce_fwd_f32": [_ptr, _i64, _ptr, _f32, _ptr, _ptr, _ptr, _i64, _i64, _ptr],
+    "mpc_smooth_ce_bwd_f32": [_ptr, _i64, _ptr, _f32, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr],
     "mpc_umbrella_features_f32": [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr],
     "mpc_debug_trace_buffer": [_ptr],
     "mpc_debug_set_knob": [_int, _i64],
@@ -58,6 +60,7 @@ KERNELS_PER_CALL = {
     "mpc_bn_act_fwd_f32": 1, "mpc_bn_act_bwd_f32": 2, "mpc_linear_fwd_f32": 1,
     "mpc_linear_wgrad_f32": 1,
     "mpc_linear_dgrad_f32": 1,
+    "mpc_smooth_ce_fwd_f32": 1, "mpc_smooth_ce_bwd_f32": 1,
     "mpc_umbrella_features_f32": 1,
     "mpc_debug_trace_buffer": 0,
     "mpc_debug_set_knob": 0,

@@ -713,3 +713,112 @@ MPC_API int mpc_debug_set_knob(int id, int64_t value) {
 
 MPC_API int mpc_version(void) { return 100; }  /* 0.1.0 */
 MPC_API int mpc_compiled_arch(void) { return 1000; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Label-smoothed cross entropy of the part-seg head (get_loss, R/models/repsurf/pointnet2_part_seg_msg.py:159-180):
+// one_hot*(1-eps) + (1-one_hot)*eps/(C-1) against log_softmax(pred), summed over classes, mean over rows.  The
+// reference's chain is ~10 elementwise / reduce launches over [M,C]; here one warp per row does it in one pass
+// (forward) and one pass (backward), rows may be strided (the 50-class head writes 52-float rows).
+// ---------------------------------------------------------------------------------------------------------------
+namespace mpc {
+
+constexpr int CE_WARPS = 8;
+
+__global__ void __launch_bounds__(CE_WARPS * 32)
+smooth_ce_fwd_kernel(const float* __restrict__ pred, int64_t ld, const int64_t* __restrict__ target, float eps,
+                     float* __restrict__ lse_out, float* __restrict__ loss, double* __restrict__ scratch, int64_t M,
+                     int C) {
+    pdl_prologue();
+    __shared__ double part[CE_WARPS];
+    __shared__ bool last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int64_t row = (int64_t)blockIdx.x * CE_WARPS + warp; row < M; row += (int64_t)gridDim.x * CE_WARPS) {
+        const float* x = pred + row * ld;
+        float mx = -INFINITY, sx = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float v = x[c];
+            mx = fmaxf(mx, v);
+            sx += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        }
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += expf(x[c] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        const float lse = mx + logf(se);
+        if (lane == 0) {
+            const int t = clamp_index(target[row], C);
+            const float lp_t = x[t] - lse;
+            const float sum_lp = sx - (float)C * lse;  // sum over classes of log p
+            const float off = eps / (float)(C - 1);
+            acc += (double)(-((1.0f - eps) * lp_t + off * (sum_lp - lp_t)));
+            lse_out[row] = lse;
+        }
+    }
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < CE_WARPS; ++w) s += part[w];
+        atomicAdd(scratch, s);
+        __threadfence();
+        last = atomicAdd(reinterpret_cast<unsigned*>(scratch + 1), 1u) == gridDim.x - 1;
+        if (last) {  // scratch contract: the last CTA publishes the mean and leaves the scratch zeroed
+            __threadfence();
+            *loss = (float)(__ldcg(scratch) / (double)M);
+            scratch[0] = 0.0;
+            scratch[1] = 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CE_WARPS * 32)
+smooth_ce_bwd_kernel(const float* __restrict__ pred, int64_t ld, const int64_t* __restrict__ target, float eps,
+                     const float* __restrict__ lse, const float* __restrict__ grad_loss, float* __restrict__ grad_pred,
+                     int64_t ldg, int64_t M, int C) {
+    pdl_prologue();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float g = __ldg(grad_loss) / (float)M;
+    const float off = eps / (float)(C - 1);
+    for (int64_t row = (int64_t)blockIdx.x * CE_WARPS + warp; row < M; row += (int64_t)gridDim.x * CE_WARPS) {
+        const float* x = pred + row * ld;
+        const float l = lse[row];
+        const int t = clamp_index(target[row], C);
+        for (int c = lane; c < C; c += 32) {
+            const float w = c == t ? 1.0f - eps : off;
+            grad_pred[row * ldg + c] = g * (expf(x[c] - l) - w);  // the smoothed target sums to 1
+        }
+    }
+}
+
+}  // namespace mpc
+
+MPC_API int mpc_smooth_ce_fwd_f32(const float* pred, int64_t ld, const int64_t* target, float eps, float* lse,
+                                  float* loss, double* scratch, int64_t M, int64_t C, mpc_stream_t stream) {
+    if (!pred || !target || !lse || !loss || !scratch || M <= 0 || C <= 1 || ld < C) return MPC_ERR_INVALID;
+    if (C > INT32_MAX) return MPC_ERR_UNSUPPORTED;
+    int64_t g = ceil_div(M, CE_WARPS * 4);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    pdl_launch(smooth_ce_fwd_kernel, dim3((unsigned)(g > cap ? cap : g)), dim3(CE_WARPS * 32), 0, (cudaStream_t)stream,
+               pred, ld, target, eps, lse, loss, scratch, M, (int)C);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_smooth_ce_bwd_f32(const float* pred, int64_t ld, const int64_t* target, float eps, const float* lse,
+                                  const float* grad_loss, float* grad_pred, int64_t ldg, int64_t M, int64_t C,
+                                  mpc_stream_t stream) {
+    if (!pred || !target || !lse || !grad_loss || !grad_pred || M <= 0 || C <= 1 || ld < C || ldg < C)
+        return MPC_ERR_INVALID;
+    int64_t g = ceil_div(M, CE_WARPS * 4);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    pdl_launch(smooth_ce_bwd_kernel, dim3((unsigned)(g > cap ? cap : g)), dim3(CE_WARPS * 32), 0, (cudaStream_t)stream,
+               pred, ld, target, eps, lse, grad_loss, grad_pred, ldg, M, (int)C);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}

@@ -215,6 +215,53 @@ def query_ball_point(radius, nsample, xyz, new_xyz, cuda=False):
     return out
 
 
+class SmoothCE(torch.autograd.Function):
+    """Label-smoothed cross entropy of the part-seg head (R/models/repsurf/pointnet2_part_seg_msg.py:159-180) in one
+    forward and one backward kernel; pred [M,C] may have padded rows."""
+
+    @staticmethod
+    def forward(ctx, pred, target, eps):
+        M, C = pred.shape
+        if pred.stride(1) != 1:
+            pred = pred.contiguous()
+        target = _i64c(target.reshape(-1))
+        lse = torch.empty(M, dtype=torch.float32, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        scratch = _ce_scratch(pred.device)
+        call("mpc_smooth_ce_fwd_f32", ptr(pred), _i64(pred.stride(0)), ptr(target), ctypes.c_float(eps), ptr(lse),
+             ptr(loss), ptr(scratch), _i64(M), _i64(C), algo_bytes=M * (C * 4 + 12))
+        ctx.save_for_backward(pred, target, lse)
+        ctx.eps = eps
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        pred, target, lse = ctx.saved_tensors
+        M, C = pred.shape
+        Cp = (C + 3) & ~3
+        g = torch.empty(M, Cp, dtype=torch.float32, device=pred.device)[:, :C]  # padded rows: TMA-ready for the head GEMM
+        grad_loss = _f32c(grad_loss.reshape(1))
+        call("mpc_smooth_ce_bwd_f32", ptr(pred), _i64(pred.stride(0)), ptr(target), ctypes.c_float(ctx.eps), ptr(lse),
+             ptr(grad_loss), ptr(g), _i64(g.stride(0)), _i64(M), _i64(C), algo_bytes=2 * M * C * 4)
+        return g, None, None
+
+
+_ce_scratch_pool = {}
+
+
+def _ce_scratch(device):
+    buf = _ce_scratch_pool.get(device)
+    if buf is None:
+        buf = _ce_scratch_pool[device] = torch.zeros(2, dtype=torch.float64, device=device)
+    return buf
+
+
+def smooth_cross_entropy(pred, target, eps=0.1):
+    """mean_rows( -sum_c smooth_one_hot(target)[c] * log_softmax(pred)[c] ), pred [M,C] f32 on the device."""
+    require_cuda(pred)
+    return SmoothCE.apply(pred if pred.dtype == torch.float32 else pred.float(), target, float(eps))
+
+
 def xyz2sphere(xyz, normalize=True):
     """R/modules/polar_utils.py:10-31: [..., 3] -> (rho, theta, phi), theta = 0 where rho = 0; normalised to
     [0, 1] when `normalize`.  Elementwise on the device (coordinates carry no gradient on this path)."""
@@ -563,7 +610,7 @@ def _scratch(owner, role, C):
 
 def reset_scratch():
     """Re-zero every pooled scratch buffer (only needed after a CUDA error interrupted a producer/consumer pair)."""
-    for buf in _scratch_pool.values():
+    for buf in list(_scratch_pool.values()) + list(_ce_scratch_pool.values()):
         buf.zero_()
 
 

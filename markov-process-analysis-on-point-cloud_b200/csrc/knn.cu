@@ -457,6 +457,20 @@ knn64x2_kernel(const float* __restrict__ ref, const float* __restrict__ qry, flo
 // oracle's order, so indices stay bit-exact.  The finished 128 x 64 distance tile goes through shared memory to the
 // selection phase, where thread = query scans its row against its current K-th distance (the same queued insertion
 // as the other kernels).
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 constexpr int KT_THREADS = 128;
 constexpr int KT_Q = 128;   // queries per CTA
 constexpr int KT_R = 64;    // reference points per tile
@@ -516,11 +530,13 @@ knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, f
     int qcnt = 0;
     for (int t0 = 0; t0 < N; t0 += KT_R) {
         const int tn = min(KT_R, N - t0);
-        float acc[8][8];
+        // accumulators as packed pairs (acc[i][2m], acc[i][2m+1]): Blackwell's FFMA2 (fma.rn.f32x2) retires two IEEE
+        // fp32 FMAs per lane per issue slot -- bit-identical to two scalar fmaf, twice the SIMT FP32 rate
+        unsigned long long acc2[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            for (int m = 0; m < 4; ++m) acc2[i][m] = 0ull;
         float rnorm = 0.f;  // thread j < 64: running |r_j|^2 across the channel chunks
         for (int c0 = 0; c0 < C; c0 += KT_CK) {
             __syncthreads();  // previous chunk / previous tile's selection are done with rt, dt
@@ -556,11 +572,14 @@ knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, f
                 const float4 ra = *reinterpret_cast<const float4*>(rt + c * KT_R + (((tx) ^ g) & 15) * 4);
                 const float4 rb4 = *reinterpret_cast<const float4*>(rt + c * KT_R + (((8 + tx) ^ g) & 15) * 4);
                 const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb4.x, qb4.y, qb4.z, qb4.w};
-                const float rv[8] = {ra.x, ra.y, ra.z, ra.w, rb4.x, rb4.y, rb4.z, rb4.w};
+                const unsigned long long rp[4] = {pack2(ra.x, ra.y), pack2(ra.z, ra.w), pack2(rb4.x, rb4.y),
+                                                  pack2(rb4.z, rb4.w)};
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned long long qq = pack2(qv[i], qv[i]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(qv[i], rv[j], acc[i][j]);
+                    for (int m = 0; m < 4; ++m) acc2[i][m] = ffma2(qq, rp[m], acc2[i][m]);
+                }
             }
         }
         if (tid < KT_R) rn_s[tid] = rnorm;
@@ -573,7 +592,9 @@ knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, f
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int rj = (j < 4 ? 0 : 28) + tx * 4 + j;  // cols tx*4+{0..3}, 32+tx*4+{0..3}
-                dt[qi * KT_DLD + rj] = sqdist_from_dot(acc[i][j], qn, rn_s[rj]);
+                float lo, hi;
+                unpack2(acc2[i][j >> 1], lo, hi);
+                dt[qi * KT_DLD + rj] = sqdist_from_dot((j & 1) ? hi : lo, qn, rn_s[rj]);
             }
         }
         __syncthreads();

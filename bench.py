@@ -310,10 +310,12 @@ def run_own(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION and =WARN, so file
+    # descriptor 1 is pointed at stderr for everything but the final print
+    json_out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.distributed.init_process_group("nccl", device_id=device)
     mpc = importlib.import_module(PKG)
     mpc._lib.load()
@@ -488,7 +490,7 @@ def run_own(args):
             r = cpu_reference_run(2, 1)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

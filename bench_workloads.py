@@ -35,9 +35,10 @@ def main():
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_out = os.fdopen(os.dup(1), "w")  # stdout carries the one JSON line only (NCCL prints its banner on fd 1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.distributed.init_process_group("nccl", device_id=dev)
     mpc = importlib.import_module(PKG)
     mpc._lib.load()
@@ -134,7 +135,7 @@ def main():
             "config": {"workload": a.workload, "clouds_per_gpu": B, "points": N, "points_per_s": total * N / ms * 1e3,
                        "optimizer": "Adam (torch fused, capturable)" if opt else None,
                        "launch": "CUDA graph replay + NCCL all-reduce" if world > 1 else "CUDA graph replay"},
-            "last_loss": float(loss)}), flush=True)
+            "last_loss": float(loss.detach())}), file=json_out, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

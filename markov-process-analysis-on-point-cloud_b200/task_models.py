@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .pointnet2_utils import KeepHighResolutionModulePartSeg, Linear
-from .repsurface_utils import KeepHighResolutionModule
+from .repsurface_utils import KeepHighResolutionModule, SurfaceAbstractionCD, UmbrellaSurfaceConstructor
 
 
 class Model(nn.Module):
@@ -40,6 +40,49 @@ class Model(nn.Module):
         x = self.drop1(self.lrelu(self.bn1(self.fc1(x))))
         x = self.drop2(self.lrelu(self.bn2(self.fc2(x))))
         return F.log_softmax(self.fc3(x), -1)
+
+
+class Model2x(nn.Module):
+    """RepSurf-U 2x classifier, R/models/repsurf/repsurf_ssg_umb_2x.py:12-61 (`Model` there): umbrella surface
+    constructor -> four SurfaceAbstractionCD stages -> MLP head.  Same constructor arguments (args.return_center,
+    return_polar, num_point, return_dist, group_size, umb_pool, cuda_ops, num_class) and state_dict layout; it is the
+    end-to-end consumer of the umbrella-feature and ball-query kernels."""
+
+    def __init__(self, args):
+        super().__init__()
+        center_channel = 0 if not args.return_center else (6 if args.return_polar else 3)
+        repsurf_channel = 10
+        self.init_nsample = args.num_point
+        self.return_dist = args.return_dist
+        self.surface_constructor = UmbrellaSurfaceConstructor(args.group_size + 1, repsurf_channel,
+                                                              return_dist=args.return_dist, aggr_type=args.umb_pool,
+                                                              cuda=args.cuda_ops)
+        self.sa1 = SurfaceAbstractionCD(npoint=512, radius=0.1, nsample=24, feat_channel=repsurf_channel,
+                                        pos_channel=center_channel, mlp=[128, 128, 256], group_all=False,
+                                        return_polar=args.return_polar, cuda=args.cuda_ops)
+        self.sa2 = SurfaceAbstractionCD(npoint=128, radius=0.2, nsample=24, feat_channel=256 + repsurf_channel,
+                                        pos_channel=center_channel, mlp=[256, 256, 512], group_all=False,
+                                        return_polar=args.return_polar, cuda=args.cuda_ops)
+        self.sa3 = SurfaceAbstractionCD(npoint=32, radius=0.4, nsample=24, feat_channel=512 + repsurf_channel,
+                                        pos_channel=center_channel, mlp=[512, 512, 1024], group_all=False,
+                                        return_polar=args.return_polar, cuda=args.cuda_ops)
+        self.sa4 = SurfaceAbstractionCD(npoint=None, radius=None, nsample=None, feat_channel=1024 + repsurf_channel,
+                                        pos_channel=center_channel, mlp=[1024, 1024, 2048], group_all=True,
+                                        return_polar=args.return_polar, cuda=args.cuda_ops)
+        self.classfier = nn.Sequential(  # (sic) the reference's attribute name, part of the state_dict keys
+            nn.Linear(2048, 512), nn.BatchNorm1d(512), nn.ReLU(True), nn.Dropout(0.4),
+            nn.Linear(512, 256), nn.BatchNorm1d(256), nn.ReLU(True), nn.Dropout(0.4),
+            nn.Linear(256, args.num_class))
+
+    def forward(self, points):
+        center = points[:, :3, :]
+        normal = self.surface_constructor(center)
+        center, normal, feature = self.sa1(center, normal, None)
+        center, normal, feature = self.sa2(center, normal, feature)
+        center, normal, feature = self.sa3(center, normal, feature)
+        center, normal, feature = self.sa4(center, normal, feature)
+        feature = self.classfier(feature.reshape(-1, 2048))
+        return F.log_softmax(feature, -1)
 
 
 class get_model(nn.Module):

@@ -100,3 +100,31 @@ def test_gpu_umbrella_random_inv_draws_on_cpu_generator(mpc):
     m(c)
     assert torch.equal(torch.rand(1), after)  # exactly one randint(0, 2, (B,1,1)) was consumed, like the reference
     assert expect.shape == (5, 1, 1)
+
+
+@pytest.mark.gpu
+def test_gpu_umbrella_module_backward_vs_float64_chain(mpc, orc, gold):
+    """Parameter gradients of the umbrella MLP (odd channel count 10: the generic BatchNorm kernels) against the same
+    chain evaluated with torch ops in float64 on the same features."""
+    import torch.nn.functional as F
+    m = mpc.pointnet2_utils.UmbrellaSurfaceConstructor(9, 10, aggr_type="sum", return_dist=True, random_inv=False)
+    m.load_state_dict(_params(orc, gold))
+    m = m.cuda().train()
+    c = torch.from_numpy(gold["center"]).permute(0, 2, 1).cuda()
+    out = m(c)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(0)).cuda()
+    (out * w).sum().backward()
+    feat = mpc.ops.umbrella_features(c.permute(0, 2, 1).contiguous(), 9, True, None).double()
+    P = {k: v.detach().double().cuda().requires_grad_(v.dtype.is_floating_point and "running" not in k)
+         for k, v in _params(orc, gold).items()}
+    x = feat.reshape(-1, 10)
+    for conv, bn in (("0", "1"), ("3", "4")):
+        x = F.linear(x, P["mlps.%s.weight" % conv].view(10, 10), P.get("mlps.%s.bias" % conv))
+        x = F.batch_norm(x, None, None, P["mlps.%s.weight" % bn], P["mlps.%s.bias" % bn], True, 0.1, 1e-5)
+        x = F.relu(x)
+    x = F.linear(x, P["mlps.6.weight"].view(10, 10), P["mlps.6.bias"]).view(*feat.shape[:3], 10).sum(2).permute(0, 2, 1)
+    (x * w.double()).sum().backward()
+    for k, p in m.named_parameters():
+        if P[k].grad is not None and "mlps.3.bias" not in k:  # (a conv bias in front of BatchNorm: exactly zero)
+            ref = P[k].grad.float().cpu().numpy().reshape(p.shape)
+            np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=1e-3, atol=1e-4 * np.abs(ref).max(), err_msg=k)

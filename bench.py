@@ -319,6 +319,8 @@ def run_own(args):
         torch.distributed.init_process_group("nccl", device_id=device)
     mpc = importlib.import_module(PKG)
     mpc._lib.load()
+    if os.environ.get("MPC_DEFER_WGRAD", "1") == "1":
+        mpc.ops.set_defer_wgrad(True)  # gradients are read after backward only (all-reduce / optimiser): see ops._defer_wgrad
     step = Step(mpc, device, world)
     gen = torch.Generator().manual_seed(1 + rank)
     B = B_PER_GPU

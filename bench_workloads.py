@@ -42,6 +42,8 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     mpc = importlib.import_module(PKG)
     mpc._lib.load()
+    if os.environ.get("MPC_DEFER_WGRAD", "1") == "1":
+        mpc.ops.set_defer_wgrad(True)  # gradients are read after backward only (all-reduce / optimiser): see ops._defer_wgrad
     gen = torch.Generator().manual_seed(1 + rank)
     torch.manual_seed(0)
     opt = None

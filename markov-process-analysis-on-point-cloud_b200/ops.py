@@ -672,7 +672,18 @@ def bn_act(y2d, gamma, beta, running_mean, running_var, num_batches_tracked, tra
 # ------------------------------------------------------------------------------------------------------
 # Weight gradients off the backward critical path: only the optimiser (after backward) reads them, so the wgrad GEMM
 # of a Linear+BN block is issued on a dedicated stream and joined once, by an autograd end-of-backward callback.
-_DEFER_WGRAD = os.environ.get("MPC_DEFER_WGRAD", "1") == "1"
+# OPT-IN (set_defer_wgrad(True) or MPC_DEFER_WGRAD=1): safe whenever gradients are only read after backward() has
+# returned (this repo's training steps: all-reduce and optimiser follow backward); NOT safe under hooks that consume a
+# gradient the moment autograd accumulates it (torch DDP's reducer), hence off by default in the drop-in modules.
+_DEFER_WGRAD = os.environ.get("MPC_DEFER_WGRAD", "0") == "1"
+
+
+def set_defer_wgrad(on):
+    """Run the weight-gradient GEMMs of the shared-MLP blocks off the backward critical path (see above)."""
+    global _DEFER_WGRAD
+    _DEFER_WGRAD = bool(on)
+
+
 _wgrad_streams = {}
 _wgrad_pending = set()
 

@@ -19,6 +19,7 @@ Own arm:   `value` = device-resident inputs, timed with CUDA events around every
            threads on a bounded sample (4 clouds x 2048 points per step) of the same workload.
 """
 import argparse
+import ctypes
 import importlib
 import json
 import os
@@ -265,13 +266,14 @@ def rebind_gemm_calls(mpc, calls, device):
     out, keep = [], []
     for name, a, by in calls:
         if name == "mpc_linear_fwd_f32":
-            ldx, ldw, ldy, M, K, N = (val(a[i]) for i in (1, 3, 6, 8, 9, 10))
+            ldx, ldw, ldy, rpg, M, K, N = (val(a[i]) for i in (1, 3, 6, 9, 10, 11, 12))
             x, w, y = buf(M, ldx), buf(N, ldw), buf(M, ldy)
             bias = torch.randn(N, device=device) if val(a[4]) else None
             sc = torch.zeros(2 * N + 2, dtype=torch.float64, device=device) if val(a[7]) else None
-            keep += [x, w, y, bias, sc]
+            gbias = torch.randn(max(M // max(rpg, 1), 1), N, device=device) if val(a[8]) else None
+            keep += [x, w, y, bias, sc, gbias]
             P = mpc._lib.ptr
-            na = (P(x), a[1], P(w), a[3], P(bias), P(y), a[6], P(sc), a[8], a[9], a[10])
+            na = (P(x), a[1], P(w), a[3], P(bias), P(y), a[6], P(sc), P(gbias), a[9], a[10], a[11], a[12])
         elif name == "mpc_linear_dgrad_f32":
             ldg, ldw, ldx, M, K, N = (val(a[i]) for i in (1, 3, 5, 6, 7, 8))
             g, w, x = buf(M, ldg), buf(N, ldw), buf(M, ldx)
@@ -395,6 +397,16 @@ def run_own(args):
     dom_ms /= dom_reps
     dom_calls = len(calls)
     dom_bytes = sum(c[2] for c in calls)
+    # lower bound of the same launch mix when every launch runs at the faster of its two rooflines: HBM bytes at the
+    # measured copy bandwidth, or its 3 x 2MNK issued TF32 flops at half the measured dense bf16 rate
+    pk0, _ = peaks()
+    dom_ideal_ms = 0.0
+    for name, a, by in calls:
+        dims = [x.value for x in a if isinstance(x, ctypes.c_int64)]
+        Mg, Kg, Ng = dims[-3:] if name == "mpc_linear_fwd_f32" else dims[-4:-1]  # (dgrad / wgrad end in a flag)
+        t_hbm = by / (pk0["hbm_gbs"] * 1e9)
+        t_tc = 3 * 2.0 * Mg * Kg * Ng / (pk0["bf16_tflops"] * 0.5e12)
+        dom_ideal_ms += 1e3 * max(t_hbm, t_tc)
     del kgraph, keep
 
     run_step = step
@@ -482,6 +494,10 @@ def run_own(args):
                          "launches_per_step": n_calls, "avg_launch_us": 1e3 * ms / max(n_calls, 1),
                          "algo_bytes_per_launch": by / max(n_calls, 1),
                          "kernel_ms_per_step": ms, "share_of_step": ms / (dev_ms / args.steps),
+                         "frac_mixed_bound": dom_ideal_ms / ms if ms > 0 else None,
+                         "frac_mixed_bound_how": "sum over the launches of max(bytes / HBM peak, 3 x 2MNK / (bf16 peak "
+                                                 "/ 2)) divided by the measured time: the wide layers are tensor-pipe "
+                                                 "bound under the 3xTF32 split, not HBM bound",
                          "how": "all %d launches of one step re-issued back to back in a CUDA graph, CUDA events "
                                 "around %d replays; share_of_step relates that serialised time to the "
                                 "multi-stream graph step" % (n_calls, dom_reps)},

@@ -223,9 +223,14 @@ int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean,
  * per-column sum and sum of squares of y over the M rows -- the BatchNorm batch statistics of the `Linear` block --
  * from the tile while it is still in shared memory, one atomic per column per CTA; mpc_bn_act_fwd_sums_f32 or
  * mpc_bn_finalize_f32 consume (and clear) them.
+ * group_bias (optional, [M / rows_per_group, N] f32, rows_per_group % 128 == 0): a second bias shared by
+ * rows_per_group consecutive rows.  It carries the projection of input channels that are constant over a cloud's
+ * points (the broadcast global-pool and label channels of the part-seg head, R/modules/pointnet2_utils.py:843-853):
+ * y = x_a Wa^T + (g Wb^T)[cloud] + b equals the reference's Linear over cat(x_a, broadcast g) with 3.5x less work.
  * ------------------------------------------------------------------------------------------------- */
 int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
-                       int64_t ldy, double* stat_scratch, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+                       int64_t ldy, double* stat_scratch, const float* group_bias, int64_t rows_per_group, int64_t M,
+                       int64_t K, int64_t N, mpc_stream_t stream);
 /* stats[0:C] = mean, stats[C:2C] = biased variance from sums[0:C] = sum(y), sums[C:2C] = sum(y*y) over M rows;
  * running statistics / num_batches_tracked updated like nn.BatchNorm1d when non-NULL.  Consumes (clears) `sums`. */
 int mpc_bn_finalize_f32(double* sums, float* stats, float* running_mean, float* running_var,

@@ -93,7 +93,8 @@ attn_feat_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __re
     for (int64_t t = (int64_t)blockIdx.x * AT + threadIdx.x; t < total; t += (int64_t)gridDim.x * AT) {
         const int64_t row = t / CV;
         const int c4 = (int)(t - row * CV) * 4;
-        const int64_t b = row / S;
+        // 64-bit integer division is a ~100-instruction software routine; rows < 2^32 whenever B < 2^32 / S
+        const int64_t b = row < 0xffffffffll ? (int64_t)((unsigned)row / (unsigned)S) : row / S;
         const int64_t* irow = idx + row * K;
         float4 kk[K], vv[K];
 #pragma unroll
@@ -132,7 +133,8 @@ attn_feat_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ q
     for (int64_t t = (int64_t)blockIdx.x * AT + threadIdx.x; t < total; t += (int64_t)gridDim.x * AT) {
         const int64_t row = t / CV;
         const int c4 = (int)(t - row * CV) * 4;
-        const int64_t b = row / S;
+        // 64-bit integer division is a ~100-instruction software routine; rows < 2^32 whenever B < 2^32 / S
+        const int64_t b = row < 0xffffffffll ? (int64_t)((unsigned)row / (unsigned)S) : row / S;
         const int64_t* irow = idx + row * K;
         int nb[K];
         float4 kk[K], vv[K];
@@ -222,7 +224,8 @@ attn_xyz_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ 
         }
     const float Bq = bq[c], Bk = bk[c], Bv = bv[c], Br = wr ? br[c] : 0.f;
     for (int64_t row = (int64_t)blockIdx.x * rpb + threadIdx.x / Cb; row < rows; row += (int64_t)gridDim.x * rpb) {
-        const int64_t b = row / S;
+        // 64-bit integer division is a ~100-instruction software routine; rows < 2^32 whenever B < 2^32 / S
+        const int64_t b = row < 0xffffffffll ? (int64_t)((unsigned)row / (unsigned)S) : row / S;
         const int cn = cidx ? clamp_index(__ldg(cidx + row), N) : (int)(row - b * S);
         const float* cp = feat + ((size_t)b * N + cn) * cin;
         float cen[CM];
@@ -290,7 +293,8 @@ attn_xyz_bwd_kernel(const float* __restrict__ gctx, const float* __restrict__ fe
     const float Bq = bq[c], Bk = bk[c], Bv = bv[c];
     float GBq = 0.f, GBk = 0.f, GBv = 0.f, GBr = 0.f;
     for (int64_t row = (int64_t)blockIdx.x * rpb + threadIdx.x / Cb; row < rows; row += (int64_t)gridDim.x * rpb) {
-        const int64_t b = row / S;
+        // 64-bit integer division is a ~100-instruction software routine; rows < 2^32 whenever B < 2^32 / S
+        const int64_t b = row < 0xffffffffll ? (int64_t)((unsigned)row / (unsigned)S) : row / S;
         const int cn = cidx ? clamp_index(__ldg(cidx + row), N) : (int)(row - b * S);
         const float* cp = feat + ((size_t)b * N + cn) * cin;
         float cen[CM];

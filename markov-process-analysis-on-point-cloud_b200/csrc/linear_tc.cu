@@ -139,6 +139,8 @@ struct Params {
     int m_tiles;      // ceil(M / 128)
     int stages;
     const float* bias;  // may be null
+    const float* bias2; // optional [groups][N]: a second bias shared by `bias2_rows` consecutive rows (a per-cloud
+    int bias2_rows;     //   vector: the projection of channels that are constant over a cloud's points); % 128 == 0
     float* y;
     int ldy;
     int a_mn, b_mn;   // operand layouts: 0 = K-major (reduction index contiguous), 1 = MN-major (output index
@@ -368,6 +370,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         int tile_it = 0, tn_ = 0, slab_it = 0;
         int stat_n0 = -1;  // column offset the statistics accumulators currently belong to
         int bias_n0 = -1;  // column offset bias_s currently holds
+        int bias_grp = -1; // row group (per-cloud bias) bias_s currently holds
         float* my_acc0 = &stat_accw[warp][0][0];
         float* my_acc1 = &stat_accw[warp][1][0];
         auto stat_flush = [&]() {  // all four epilogue warps: combine the per-warp sums in fp64, warp 0 publishes
@@ -397,14 +400,19 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 stat_n0 = n0;
                 for (int i = lane; i < p.block_n; i += 32) my_acc0[i] = my_acc1[i] = 0.f;
             }
-            if (p.tma_out && n0 != bias_n0) {
-                // bias of this column tile -> shared (broadcast reads below); reloaded only when the column tile
-                // changes, which for a persistent CTA is once per kernel in every layer of both models
+            const int grp = p.bias2 ? (mt * BLOCK_M) / p.bias2_rows : 0;
+            if (p.tma_out && (n0 != bias_n0 || grp != bias_grp)) {
+                // bias of this column tile -> shared (broadcast reads below); reloaded only when the column tile (or
+                // the row group of a per-cloud bias) changes -- once per kernel in every plain layer of both models
                 epi_barrier();
-                for (int i = threadIdx.x; i < p.block_n; i += 128)
-                    bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+                for (int i = threadIdx.x; i < p.block_n; i += 128) {
+                    float v = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+                    if (p.bias2 && n0 + i < p.N) v += __ldg(p.bias2 + (size_t)grp * p.N + n0 + i);
+                    bias_s[i] = v;
+                }
                 epi_barrier();
                 bias_n0 = n0;
+                bias_grp = grp;
             }
             mbar_wait(&bar_tmem_full[as], aph);
             if (threadIdx.x == 0) MPC_TRACE(3, tn_);
@@ -635,8 +643,8 @@ static cudaError_t launch_pdl(int grid, size_t smem, cudaStream_t st, const CUte
 }  // namespace mpc
 
 MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
-                               int64_t ldy, double* stat_scratch, int64_t M, int64_t K, int64_t N,
-                               mpc_stream_t stream) {
+                               int64_t ldy, double* stat_scratch, const float* group_bias, int64_t rows_per_group,
+                               int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
     using namespace mpc;
     using namespace mpc::tc;
     if (!x || !w || !y || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
@@ -660,6 +668,9 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.tma_out = tma_out;
     p.stat_sum = stat_scratch;
     if (stat_scratch && !tma_out) return MPC_ERR_UNSUPPORTED;  // zero on entry is the caller's contract
+    if (group_bias && (!tma_out || rows_per_group <= 0 || rows_per_group % BLOCK_M)) return MPC_ERR_UNSUPPORTED;
+    p.bias2 = group_bias;
+    p.bias2_rows = (int)(group_bias ? rows_per_group : 1);
     p.zero_ptr = nullptr;
     p.zero_n4 = 0;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * bn * BLOCK_K * 4;
@@ -726,6 +737,8 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
     p.bias = nullptr;
+    p.bias2 = nullptr;
+    p.bias2_rows = 1;
     p.y = gw;
     p.ldy = (int)ldw;
     p.a_mn = 1;
@@ -797,6 +810,8 @@ MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, i
     if (stages < 2) return MPC_ERR_UNSUPPORTED;
     p.stages = stages;
     p.bias = nullptr;
+    p.bias2 = nullptr;
+    p.bias2_rows = 1;
     p.y = gx;
     p.ldy = (int)ldx;
     p.a_mn = 0;

@@ -722,13 +722,14 @@ def _tc_ok(x2d, w):
             and x2d.shape[0] > 0)
 
 
-def _tc_gemm(x2d, w, bias, out, stat_scratch=None):
-    """out[M,N] = x2d[M,K] @ w[N,K]^T (+ bias) through mpc_linear_fwd_f32 (3xTF32 tcgen05).  stat_scratch
-    (2N+1 doubles) additionally receives the per-column sum / sum of squares of `out` from the epilogue."""
+def _tc_gemm(x2d, w, bias, out, stat_scratch=None, group_bias=None, rows_per_group=0):
+    """out[M,N] = x2d[M,K] @ w[N,:K]^T (+ bias) (+ group_bias[row // rows_per_group]) through mpc_linear_fwd_f32
+    (3xTF32 tcgen05).  stat_scratch (2N+2 doubles) additionally receives the per-column sum / sum of squares of `out`
+    from the epilogue.  K is taken from x2d, so `w` may be wider (a column slice of it is used)."""
     M, K = x2d.shape
     N = w.shape[0]
     call("mpc_linear_fwd_f32", ptr(x2d), _i64(x2d.stride(0)), ptr(w), _i64(w.stride(0)), ptr(bias), ptr(out),
-         _i64(out.stride(0)), ptr(stat_scratch), _i64(M), _i64(K), _i64(N),
+         _i64(out.stride(0)), ptr(stat_scratch), ptr(group_bias), _i64(rows_per_group), _i64(M), _i64(K), _i64(N),
          algo_bytes=(M * K + M * N + N * K) * 4)
 
 
@@ -907,6 +908,107 @@ class LinearBNAct(torch.autograd.Function):
         # out = act(BN(y)) + residual: the residual's gradient is the incoming gradient itself
         gres = grad_out if ctx.has_residual else None
         return gx, gw, gbias, gg, gb, None, None, None, None, None, None, None, gres
+
+
+class LinearBNActSplit(torch.autograd.Function):
+    """Linear -> BatchNorm -> LeakyReLU over cat(x_a, broadcast(g)) WITHOUT building the concatenation: the channels
+    in g [G,Kb] are constant over the `rows` consecutive rows of a cloud, so  y = x_a Wa^T + (g Wb^T)[cloud] + b  with
+    w = [Wa | Wb].  The per-cloud term enters the tcgen05 GEMM's epilogue as a row-group bias (BatchNorm statistics
+    then come out of the same epilogue), and backward needs one per-cloud column sum of grad_y plus two tiny
+    matmuls for the g / Wb gradients.  The part-seg head's 896 -> 512 layer (640 broadcast channels,
+    R/modules/pointnet2_utils.py:843-853 + R/models/repsurf/pointnet2_part_seg_msg.py:137) shrinks 3.5x."""
+
+    @staticmethod
+    def forward(ctx, x2d, g, w, bias, gamma, beta, running_mean, running_var, num_batches_tracked, training, momentum,
+                eps, slope, rows):
+        M, Ka = x2d.shape
+        N = w.shape[0]
+        dev = x2d.device
+        wb = w[:, Ka:]
+        v = g.mm(wb.t()).contiguous()  # [G,N] per-cloud bias
+        y = torch.empty(M, N, dtype=torch.float32, device=dev)
+        out = torch.empty_like(y)
+        if training:
+            scratch = _scratch(w, "fwd_stats", N)
+            stats = torch.empty(2 * N, dtype=torch.float32, device=dev)
+            _tc_gemm(x2d, w, bias, y, stat_scratch=scratch, group_bias=v, rows_per_group=rows)
+            mean, var = stats[:N], stats[N:]
+            call("mpc_bn_act_fwd_sums_f32", ptr(y), ptr(scratch), ptr(gamma), ptr(beta), ctypes.c_float(eps),
+                 ctypes.c_float(slope), ptr(None), ptr(out), ptr(stats), ptr(running_mean), ptr(running_var),
+                 ptr(num_batches_tracked), ctypes.c_float(momentum), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
+        else:
+            _tc_gemm(x2d, w, bias, y, group_bias=v, rows_per_group=rows)
+            mean, var = running_mean, running_var
+            call("mpc_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta), ctypes.c_float(eps),
+                 ctypes.c_float(slope), ptr(None), ptr(out), _i64(M), _i64(N), algo_bytes=2 * M * N * 4)
+        ctx.save_for_backward(x2d, g, w, y, mean, var, gamma, beta)
+        ctx.cfg = (training, eps, slope, bias is not None, rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x2d, g, w, y, mean, var, gamma, beta = ctx.saved_tensors
+        training, eps, slope, has_bias, rows = ctx.cfg
+        M, Ka = x2d.shape
+        N, Kt = w.shape
+        dev = y.device
+        grad_out = _f32c(grad_out)
+        gy = torch.empty_like(y)
+        gg = torch.empty(N, dtype=torch.float32, device=dev)
+        gb = torch.empty(N, dtype=torch.float32, device=dev)
+        scratch = _scratch(w, "bn_bwd", N)
+        flat = torch.empty(N * Kt + N, dtype=torch.float32, device=dev)  # [grad_w | grad_bias], cleared by the launch below
+        gw = flat[:N * Kt].view(N, Kt)
+        call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
+             ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
+             ptr(gb), ptr(scratch), ptr(flat), _i64(flat.numel()), _i64(M), _i64(N), algo_bytes=3 * M * N * 4)
+
+        def wgrad():  # grad_w[:, :Ka] = gy^T x_a, written into the column slice of the full-width gradient
+            call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(Ka), ptr(gw), _i64(Kt), _i64(M), _i64(Ka),
+                 _i64(N), _i64(1), algo_bytes=(M * Ka + M * N + N * Ka) * 4)
+
+        if _DEFER_WGRAD and _STREAMS_ENABLED:
+            _defer_wgrad(wgrad, (gy, x2d, flat))
+        else:
+            wgrad()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(M, Ka, dtype=torch.float32, device=dev)
+            call("mpc_linear_dgrad_f32", ptr(gy), _i64(N), ptr(w), _i64(Kt), ptr(gx), _i64(Ka), _i64(M), _i64(Ka),
+                 _i64(N), ptr(None), _i64(0), algo_bytes=(M * Ka + M * N + N * Ka) * 4)
+        colsum = gy.view(-1, rows, N).sum(1)  # [G,N]: per-cloud column sums of grad_y
+        gg_ = colsum.mm(w[:, Ka:]) if ctx.needs_input_grad[1] else None
+        gwb = colsum.t().mm(g)  # [N,Kb]
+        if _DEFER_WGRAD and _STREAMS_ENABLED:
+            # the deferred wgrad owns `flat` on its stream: the Wb slice is written there too, after it
+            st = _wgrad_streams[dev]
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                gw[:, Ka:].copy_(gwb)
+            gwb.record_stream(st)
+        else:
+            gw[:, Ka:].copy_(gwb)
+        gbias = None
+        if has_bias and ctx.needs_input_grad[3]:
+            gbias = flat[N * Kt:] if training else gamma * torch.rsqrt(var + eps) * gb
+        return gx, gg_, gw, gbias, gg, gb, None, None, None, None, None, None, None, None
+
+
+def linear_bn_act_split(x_a, g, weight, bias, bn, training, slope):
+    """x_a [B,Np,Ka] (per-point channels), g [B,Kb] (per-cloud channels) -> act(BN(Linear(cat(x_a, broadcast g)))),
+    [B,Np,N]; see LinearBNActSplit.  Caller guarantees Np % 128 == 0 and Ka % 32 == 0."""
+    require_cuda(x_a, g)
+    B, Np, Ka = x_a.shape
+    N = weight.shape[0]
+    out = LinearBNActSplit.apply(_f32c(x_a.reshape(-1, Ka)), _f32c(g), weight.contiguous(), bias, bn.weight, bn.bias,
+                                 bn.running_mean, bn.running_var, bn.num_batches_tracked, bool(training),
+                                 float(bn.momentum), float(bn.eps), float(slope), int(Np))
+    return out.view(B, Np, N)
+
+
+def split_supported(n_points, Ka, N):
+    return (_GEMM_IMPL == "tcgen05" and n_points % 128 == 0 and Ka % 32 == 0 and N % 4 == 0 and N <= 1024
+            and 1024 % N == 0)
 
 
 def linear_bn_act(x, weight, bias, bn, training, slope, residual=None):

@@ -45,6 +45,12 @@ class Linear(nn.Module):
         return ops.linear_bn_act(input, self.linear.weight, self.linear.bias, self.norm2, self.training,
                                  0.2 if self.act_flag is True else 1.0, residual=residual)
 
+    def forward_split(self, x_a, g):
+        """forward(cat(x_a [B,N,Ka], g [B,Kb] broadcast over the N points)) without building the concatenation
+        (extension; ops.LinearBNActSplit).  BatchNorm branch only."""
+        return ops.linear_bn_act_split(x_a, g, self.linear.weight, self.linear.bias, self.norm2, self.training,
+                                       0.2 if self.act_flag is True else 1.0)
+
 
 class LocalTrans(nn.Module):
     """Difference-wise attention, R/modules/pointnet2_utils.py:479-574."""
@@ -234,13 +240,22 @@ class KeepHighResolutionModulePartSeg(nn.Module):
         with ops.geometry_scope():
             return self._forward(xyz, normal, label)
 
+    def forward_parts(self, xyz, normal, label):
+        """Same computation as forward, but the 896-channel head input is returned in its two parts instead of
+        concatenated: (xyz [B,N,3], per-point channels [B,N,256], per-cloud channels [B,640] = global max pools + label
+        embedding, which forward broadcasts over the N points).  cat(a, g[:, None].expand(-1, N, -1)) == forward()[1]."""
+        xyz = xyz.permute(0, 2, 1).contiguous()
+        normal = normal.permute(0, 2, 1).contiguous()
+        with ops.geometry_scope():
+            return self._forward(xyz, normal, label, parts=True)
+
     @staticmethod
     def _sample(points, npoint):
         """FPS + gather of the sampled coordinates, issued on the geometry stream (joined by the consumer's
         coordinate kNN, which follows it on that stream)."""
         return ops.geo_call(lambda: ops.fps_and_gather(points, npoint))
 
-    def _forward(self, xyz, normal, label):
+    def _forward(self, xyz, normal, label, parts=False):
         N = xyz.shape[1]
         n = [N, N // 2, N // 4, N // 8, N // 16]
         # the whole coordinate pyramid (4 sampling steps, 5 + 4 + 6 neighbour searches) only depends on xyz: issue
@@ -276,9 +291,10 @@ class KeepHighResolutionModulePartSeg(nn.Module):
         d0 = self.fuse5(n[0], f0=d0, f1=e1, f2=e2, f3=e3, f4=e4, **kw)[0]
         # head input (:843-853): per-state global max pool, label embedding, concat -> 896 channels
         global_rep = torch.cat([t.max(dim=1, keepdim=True)[0] for t in (d0, d1, d2, d3, d4)], dim=2)
-        global_rep = global_rep.expand(-1, N, -1)
-        label = self.conv7(label).expand(-1, N, -1)
-        final = torch.cat((self.conv5(d0), global_rep, label), 2)
+        label = self.conv7(label)
+        if parts:  # (per-point channels [B,N,256], per-cloud channels [B,640]): the caller projects them separately
+            return xyz, self.conv5(d0), torch.cat((global_rep, label), 2).squeeze(1)
+        final = torch.cat((self.conv5(d0), global_rep.expand(-1, N, -1), label.expand(-1, N, -1)), 2)
         return xyz, final
 
 

@@ -103,8 +103,14 @@ class get_model(nn.Module):
         self.drop2 = nn.Dropout(0.5)
 
     def forward(self, xyz, cls_label):
-        branch1_xyz, final_points = self.keepHigh(xyz, normal=xyz, label=cls_label)
-        x = self.drop1(self.conv8(final_points))
+        if xyz.is_cuda and ops.split_supported(xyz.shape[2], 256, self.conv8.linear.out_features):
+            # 640 of conv8's 896 input channels are constant over a cloud's points (global pools, label embedding):
+            # project them once per cloud instead of once per point (ops.LinearBNActSplit) -- same arithmetic
+            branch1_xyz, per_point, per_cloud = self.keepHigh.forward_parts(xyz, normal=xyz, label=cls_label)
+            x = self.drop1(self.conv8.forward_split(per_point, per_cloud))
+        else:
+            branch1_xyz, final_points = self.keepHigh(xyz, normal=xyz, label=cls_label)
+            x = self.drop1(self.conv8(final_points))
         x = self.conv9(x)
         x = self.conv10(x)
         x = ops.linear(x, self.conv11.weight, self.conv11.bias)  # conv11's arithmetic on the tcgen05 kernel

@@ -26,7 +26,7 @@ for c in calls:
     name, a, by = c
     v = lambda i: a[i].value if a[i].value is not None else 0
     if name == "mpc_linear_fwd_f32":
-        key = (name[11:-4], v(8), v(9), v(10), 1 if v(7) else 0)
+        key = (name[11:-4], v(10), v(11), v(12), 1 if v(7) else 0)
     else:
         key = (name[11:-4], v(6), v(7), v(8), 0)
     groups.setdefault(key, []).append(c)

@@ -198,3 +198,31 @@ def test_deferred_weight_gradients_match(mpc):
         torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4)
     for a, b in zip(grads[1], grads[2]):
         torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_split_projection_equals_concatenated_projection(mpc, train):
+    """Linear.forward_split(x_a, g) == Linear(cat(x_a, broadcast g)): outputs rtol 1e-4, gradients rtol 1e-3."""
+    torch.manual_seed(3)
+    B, Np, Ka, Kb, N = 3, 256, 64, 96, 128
+    lin = mpc.pointnet2_utils.Linear(Ka + Kb, N, bn=False).cuda().train(train)
+    ref = mpc.pointnet2_utils.Linear(Ka + Kb, N, bn=False).cuda().train(train)
+    ref.load_state_dict(lin.state_dict())
+    xa = torch.randn(B, Np, Ka, device="cuda")
+    g = torch.randn(B, Kb, device="cuda")
+    w = torch.randn(B, Np, N, device="cuda")
+    a1, g1 = xa.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    y1 = lin.forward_split(a1, g1)
+    (y1 * w).sum().backward()
+    a2, g2 = xa.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    y2 = ref(torch.cat((a2, g2[:, None, :].expand(-1, Np, -1)), 2))
+    (y2 * w).sum().backward()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(y1, y2, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(a1.grad, a2.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(g1.grad, g2.grad, rtol=1e-3, atol=1e-4)
+    for (k, p), (_, q) in zip(lin.named_parameters(), ref.named_parameters()):
+        if q.grad is not None:
+            torch.testing.assert_close(p.grad, q.grad, rtol=1e-3, atol=1e-4, msg=k)
+    if train:
+        torch.testing.assert_close(lin.norm2.running_var, ref.norm2.running_var, rtol=1e-5, atol=1e-6)

@@ -16,7 +16,7 @@ Own arm:   `value` = device-resident inputs, timed with CUDA events around every
            oracle (port of the reference path, torch CPU ops + C) on a bounded sample (rank 0, N = 1 only).
 --impl reference: the reference's CPU implementation of the same path.  /root/reference is pure Python and does
            not exist on the GPU box, so this arm times the oracle port (oracle/markov_oracle.py) with all host
-           threads on a bounded sample (4 clouds x 2048 points per step) of the same workload.
+           threads on a bounded sample (16 clouds x 2048 points per step) of the same workload.
 """
 import argparse
 import ctypes
@@ -38,7 +38,7 @@ PKG = "markov-process-analysis-on-point-cloud_b200"
 B_PER_GPU = 32
 N_POINTS = 2048
 N_CLASSES = 50
-CPU_SAMPLE_B = 4
+CPU_SAMPLE_B = 16  # clouds per CPU step: ~2 s of work on 16 cores, so the default legs spend ~10 s on the CPU arm
 METRIC = "point clouds/s (part-seg 32x2048 fwd+bwd per GPU)"
 UNIT = "clouds/s"
 
@@ -505,7 +505,7 @@ def run_own(args):
             "last_loss": loss_host,
         }
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(2, 1)
+            r = cpu_reference_run(4, 1)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), file=json_out, flush=True)

@@ -73,6 +73,9 @@ kernel_count = 0   # kernels of ours those calls launched (bench.py reports it a
 # With "calls": [] instead of "records", the matching calls are only logged as (name, args, bytes) so that bench.py
 # can re-issue exactly the same launches back to back inside a CUDA graph (pure device time, no host gaps).
 profiler = None
+# Called (if set) when an entry point fails, before MpcError is raised: ops.py re-zeroes the pooled reduction scratch,
+# because a failure between a producer and its consumer would otherwise leave partial sums behind (scratch contract).
+on_error = None
 
 
 class MpcError(RuntimeError):
@@ -123,6 +126,11 @@ def call(name, *args, algo_bytes=0):
     rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         kind = {-1: "invalid arguments", -2: "unsupported shape"}.get(rc, "CUDA error %d" % rc)
+        if on_error is not None and rc < 0:  # (after a CUDA error the context may be unusable: do not touch it)
+            try:
+                on_error()
+            except Exception:  # noqa: BLE001 -- the original failure is the one to report
+                pass
         raise MpcError("%s failed: %s" % (name, kind))
     if timed:
         ev1.record()

@@ -614,6 +614,9 @@ def reset_scratch():
         buf.zero_()
 
 
+_lib.on_error = reset_scratch
+
+
 class BNAct(torch.autograd.Function):
     """Tail of the reference's `Linear` block (R/modules/pointnet2_utils.py:417-423) with bn=False (=> BatchNorm1d)
     on the [M,C] view.  Running statistics are updated in place exactly like nn.BatchNorm1d (momentum 0.1,

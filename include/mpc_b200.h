@@ -188,6 +188,8 @@ int mpc_attn_xyz_bwd_f32(const float* grad_ctx, const float* feat, const int64_t
  *     (train = 1: batch statistics take part in the gradient; train = 0: running statistics are constants).
  *     zero_buf (optional, zero_count floats, 16-byte aligned, count % 4 == 0) is cleared by the same launches on
  *     behalf of a later call in the stream (the split-reduction target of mpc_linear_wgrad_f32).
+ *     ld_gout: row stride of grad_out in floats (C when contiguous); a wider stride -- grad_out is a column slice of
+ *     the gradient of a concatenation -- needs C a power of two in [4, 1024] and 16-byte aligned rows.
  * ------------------------------------------------------------------------------------------------- */
 int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float momentum, double* scratch, int64_t M, int64_t C,
@@ -210,7 +212,7 @@ int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* var, cons
 int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean, const float* var,
                        const float* gamma, const float* beta, float eps, float slope, int train,
                        float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, float* zero_buf,
-                       int64_t zero_count, int64_t M, int64_t C, mpc_stream_t stream);
+                       int64_t zero_count, int64_t ld_gout, int64_t M, int64_t C, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Shared-MLP projection on the tensor cores.  Replaces the nn.Linear inside `Linear` and the q/k/v projections

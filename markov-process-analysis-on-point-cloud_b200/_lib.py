@@ -39,7 +39,7 @@ SIGNATURES = {
                                 _i64, _ptr],
     "mpc_bn_act_fwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _ptr, _ptr, _i64, _i64, _ptr],
     "mpc_bn_act_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
-                           _i64, _i64, _ptr],
+                           _i64, _i64, _i64, _ptr],
     "mpc_linear_fwd_f32": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr],
     "mpc_bn_finalize_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i64, _i64, _ptr],
     "mpc_linear_wgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr],

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(RT)
 col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, const float* __restrict__ mean,
                   const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float eps, float slope, double* __restrict__ s1, double* __restrict__ s2,
-                  unsigned* __restrict__ ticket, StatsFinal fin, int64_t M, int C, int CV) {
+                  unsigned* __restrict__ ticket, StatsFinal fin, int64_t M, int C, int CV, int64_t gld4) {
     pdl_prologue();
     __shared__ float4 ra[RT], rb[RT];
     __shared__ bool last;
@@ -188,10 +188,10 @@ col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, c
         float4 y2 = __ldg(yp + (r + 2 * stride) * CV + v), y3 = __ldg(yp + (r + 3 * stride) * CV + v);
         float4 g0 = y0, g1 = y0, g2 = y0, g3 = y0;
         if (MODE == 1) {
-            g0 = __ldg(gp + r * CV + v);
-            g1 = __ldg(gp + (r + stride) * CV + v);
-            g2 = __ldg(gp + (r + 2 * stride) * CV + v);
-            g3 = __ldg(gp + (r + 3 * stride) * CV + v);
+            g0 = __ldg(gp + r * gld4 + v);  // (grad_out rows may be strided: a column slice of a wider gradient)
+            g1 = __ldg(gp + (r + stride) * gld4 + v);
+            g2 = __ldg(gp + (r + 2 * stride) * gld4 + v);
+            g3 = __ldg(gp + (r + 3 * stride) * gld4 + v);
         }
         accum(y0, g0);
         accum(y1, g1);
@@ -200,7 +200,7 @@ col_reduce_kernel(const float* __restrict__ y, const float* __restrict__ gout, c
     }
     for (; r < M; r += stride) {
         const float4 y0 = __ldg(yp + r * CV + v);
-        const float4 g0 = MODE == 1 ? __ldg(gp + r * CV + v) : y0;
+        const float4 g0 = MODE == 1 ? __ldg(gp + r * gld4 + v) : y0;
         accum(y0, g0);
     }
     ra[threadIdx.x] = a;
@@ -359,7 +359,8 @@ bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restri
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
                          int train, double* __restrict__ s1, double* __restrict__ s2,
                          float4* __restrict__ gy, float* __restrict__ ggamma, float* __restrict__ gbeta,
-                         float* __restrict__ zero_buf, int64_t zero_count, int64_t M, int C, int64_t total) {
+                         float* __restrict__ zero_buf, int64_t zero_count, int64_t M, int C, int64_t total,
+                         int64_t gld4, int cv_shift) {
     pdl_prologue();
     zero_service(zero_buf, zero_count);
     if (blockIdx.x == 0)
@@ -367,6 +368,8 @@ bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restri
             gbeta[i] = (float)s1[i];
             ggamma[i] = (float)s2[i];
         }
+    const int64_t cvm = ((int64_t)1 << cv_shift) - 1;  // C / 4 is a power of two on this path
+    auto gat = [&](int64_t t) { return __ldg(gout + (t >> cv_shift) * gld4 + (t & cvm)); };  // strided grad_out rows
     const int c = (threadIdx.x * 4) % C;
     const float invM = train ? (float)(1.0 / (double)M) : 0.f;
     float mu[4], is[4], g[4], be[4], c1[4], c2[4];
@@ -394,11 +397,11 @@ bn_bwd_apply_fast_kernel(const float4* __restrict__ gout, const float4* __restri
         return make_float4(o[0], o[1], o[2], o[3]);
     };
     for (; t + stride < total; t += 2 * stride) {  // 4 independent 128-bit loads in flight
-        const float4 y0 = __ldg(y + t), g0 = __ldg(gout + t), y1 = __ldg(y + t + stride), g1 = __ldg(gout + t + stride);
+        const float4 y0 = __ldg(y + t), g0 = gat(t), y1 = __ldg(y + t + stride), g1 = gat(t + stride);
         gy[t] = apply(y0, g0);
         gy[t + stride] = apply(y1, g1);
     }
-    for (; t < total; t += stride) gy[t] = apply(__ldg(y + t), __ldg(gout + t));
+    for (; t < total; t += stride) gy[t] = apply(__ldg(y + t), gat(t));
     clear_scratch_when_last(s1, C);
 }
 
@@ -584,7 +587,7 @@ MPC_API int mpc_bn_stats_f32(const float* y, float* stats, float* running_mean, 
         StatsFinal fin{stats, running_mean, running_var, num_batches_tracked, momentum};
         pdl_launch(col_reduce_kernel<0>, dim3(col_reduce_grid(M, CV)), dim3(RT), 0, st, 
             y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, scratch, scratch + C,
-            reinterpret_cast<unsigned*>(scratch + 2 * C), fin, M, (int)C, CV);
+            reinterpret_cast<unsigned*>(scratch + 2 * C), fin, M, (int)C, CV, (int64_t)CV);
         MPC_LAUNCH_CHECK();
         return MPC_OK;
     }
@@ -625,11 +628,16 @@ MPC_API int mpc_bn_act_fwd_f32(const float* y, const float* mean, const float* v
 MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean, const float* var,
                                const float* gamma, const float* beta, float eps, float slope, int train,
                                float* grad_y, float* grad_gamma, float* grad_beta, double* scratch, float* zero_buf,
-                               int64_t zero_count, int64_t M, int64_t C, mpc_stream_t stream) {
+                               int64_t zero_count, int64_t ld_gout, int64_t M, int64_t C, mpc_stream_t stream) {
     if (!grad_out || !y || !mean || !var || !gamma || !beta || !grad_y || !grad_gamma || !grad_beta || !scratch)
         return MPC_ERR_INVALID;
     if (M <= 0 || C <= 0) return MPC_ERR_INVALID;
     if (zero_buf && (!al16(zero_buf) || (zero_count & 3) || zero_count < 0)) return MPC_ERR_UNSUPPORTED;
+    if (ld_gout < C) return MPC_ERR_INVALID;
+    // strided grad_out rows only on the fast path (C a power of two in [4, 1024], 16-byte aligned rows)
+    const bool fast = C % 4 == 0 && fast_cv(C) && fast_ew(C) && al16(y) && al16(grad_out) && al16(grad_y) && al16(mean) &&
+                      al16(var) && al16(gamma) && al16(beta) && ld_gout % 4 == 0;
+    if (ld_gout != C && !fast) return MPC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = C % 4 == 0 && al16(y) && al16(grad_out) && al16(grad_y);
     const Dims d = bn_dims(M, (int)(v4 ? C / 4 : C));
@@ -639,7 +647,7 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
             const int CV = (int)(C / 4);
             pdl_launch(col_reduce_kernel<1>, dim3(col_reduce_grid(M, CV)), dim3(RT), 0, st, y, grad_out, mean, var, gamma, beta, eps, slope,
                                                                        scratch, scratch + C, nullptr, StatsFinal{}, M,
-                                                                       (int)C, CV);
+                                                                       (int)C, CV, ld_gout / 4);
         } else {
             pdl_launch(bn_bwd_sums_kernel<true>, dim3(d.grid), dim3(d.block), 0, st, grad_out, y, mean, var, gamma, beta, eps, slope,
                                                                 scratch, scratch + C, M, (int)C);
@@ -649,7 +657,7 @@ MPC_API int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const floa
             pdl_launch(bn_bwd_apply_fast_kernel, dim3(ew_grid(total)), dim3(256), 0, st, 
                 reinterpret_cast<const float4*>(grad_out), reinterpret_cast<const float4*>(y), mean, var, gamma, beta, eps,
                 slope, train, scratch, scratch + C, reinterpret_cast<float4*>(grad_y), grad_gamma, grad_beta, zero_buf,
-                zero_count, M, (int)C, total);
+                zero_count, M, (int)C, total, ld_gout / 4, __builtin_ctz((unsigned)(C / 4)));
         else
             pdl_launch(bn_bwd_apply_kernel<true>, dim3(ew_grid(total)), dim3(256), 0, st, grad_out, y, mean, var, gamma, beta, eps, slope,
                                                                      train, scratch, scratch + C, grad_y, grad_gamma,
@@ -700,7 +708,7 @@ MPC_API int mpc_col_sum_f32(const float* y, float* out, double* scratch, int64_t
     pdl_launch(col_reduce_kernel<2>, dim3(col_reduce_grid(M, CV)), dim3(RT), 0, st, y, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,
                                                                scratch, scratch + C,
                                                                reinterpret_cast<unsigned*>(scratch + 2 * C), fin, M, (int)C,
-                                                               CV);
+                                                               CV, (int64_t)CV);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

@@ -617,6 +617,17 @@ def reset_scratch():
 _lib.on_error = reset_scratch
 
 
+def _grad_rows(grad_out, C):
+    """grad_out [M,C] as the BatchNorm-backward kernels can read it: a column slice of a wider gradient (what
+    torch.cat's backward hands to each branch) is consumed in place when rows are 16-byte aligned and C is a power of
+    two in [4, 1024]; anything else is made contiguous.  Returns (tensor, row stride in floats)."""
+    if (grad_out.dim() == 2 and grad_out.dtype == torch.float32 and grad_out.stride(1) == 1
+            and grad_out.stride(0) >= C and grad_out.stride(0) % 4 == 0 and grad_out.data_ptr() % 16 == 0
+            and 4 <= C <= 1024 and (C & (C - 1)) == 0):
+        return grad_out, grad_out.stride(0)
+    return _f32c(grad_out), C
+
+
 class BNAct(torch.autograd.Function):
     """Tail of the reference's `Linear` block (R/modules/pointnet2_utils.py:417-423) with bn=False (=> BatchNorm1d)
     on the [M,C] view.  Running statistics are updated in place exactly like nn.BatchNorm1d (momentum 0.1,
@@ -658,7 +669,7 @@ class BNAct(torch.autograd.Function):
         scratch = _scratch(gamma, "bn_bwd", C)
         call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
-             ptr(gb), ptr(scratch), ptr(None), _i64(0), _i64(M), _i64(C), algo_bytes=3 * M * C * 4)
+             ptr(gb), ptr(scratch), ptr(None), _i64(0), _i64(C), _i64(M), _i64(C), algo_bytes=3 * M * C * 4)
         return gy, gg, gb, None, None, None, None, None, None, None
 
 
@@ -864,7 +875,7 @@ class LinearBNAct(torch.autograd.Function):
         M, K = x2d.shape
         N = w.shape[0]
         dev = y.device
-        grad_out = _f32c(grad_out)
+        grad_out, ld_gout = _grad_rows(grad_out, N)
         gy = torch.empty_like(y)
         gg = torch.empty(N, dtype=torch.float32, device=dev)
         gb = torch.empty(N, dtype=torch.float32, device=dev)
@@ -884,8 +895,8 @@ class LinearBNAct(torch.autograd.Function):
                 gbias = flat[flat.numel() - N:]
         call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
-             ptr(gb), ptr(scratch), ptr(flat), _i64(flat.numel() if flat is not None else 0), _i64(M), _i64(N),
-             algo_bytes=3 * M * N * 4)
+             ptr(gb), ptr(scratch), ptr(flat), _i64(flat.numel() if flat is not None else 0), _i64(ld_gout), _i64(M),
+             _i64(N), algo_bytes=3 * M * N * 4)
         def wgrad():
             call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(K), ptr(gw), _i64(K), _i64(M), _i64(K),
                  _i64(N), _i64(1), algo_bytes=(M * K + M * N + N * K) * 4)
@@ -964,7 +975,8 @@ class LinearBNActSplit(torch.autograd.Function):
         gw = flat[:N * Kt].view(N, Kt)
         call("mpc_bn_act_bwd_f32", ptr(grad_out), ptr(y), ptr(mean), ptr(var), ptr(gamma), ptr(beta),
              ctypes.c_float(eps), ctypes.c_float(slope), ctypes.c_int(1 if training else 0), ptr(gy), ptr(gg),
-             ptr(gb), ptr(scratch), ptr(flat), _i64(flat.numel()), _i64(M), _i64(N), algo_bytes=3 * M * N * 4)
+             ptr(gb), ptr(scratch), ptr(flat), _i64(flat.numel()), _i64(N), _i64(M), _i64(N),
+             algo_bytes=3 * M * N * 4)
 
         def wgrad():  # grad_w[:, :Ka] = gy^T x_a, written into the column slice of the full-width gradient
             call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(Ka), ptr(gw), _i64(Kt), _i64(M), _i64(Ka),

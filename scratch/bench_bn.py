@@ -45,7 +45,7 @@ def make(M, C, kind):
     else:
         def f(keep=keep):
             mpc._lib.call("mpc_bn_act_bwd_f32", P(go), P(y), P(mean), P(var), P(gamma), P(beta), F32(1e-5), F32(0.2),
-                          ctypes.c_int(1), P(out), P(gg), P(gb), P(scratch), P(None), I64(0), I64(M), I64(C))
+                          ctypes.c_int(1), P(out), P(gg), P(gb), P(scratch), P(None), I64(0), I64(C), I64(M), I64(C))
     return f
 
 

@@ -226,3 +226,31 @@ def test_split_projection_equals_concatenated_projection(mpc, train):
             torch.testing.assert_close(p.grad, q.grad, rtol=1e-3, atol=1e-4, msg=k)
     if train:
         torch.testing.assert_close(lin.norm2.running_var, ref.norm2.running_var, rtol=1e-5, atol=1e-6)
+
+
+def test_bn_backward_reads_strided_grad_rows(mpc):
+    """Three Linear+BN blocks feeding a concatenation: cat's backward hands each block a column slice of one wide
+    gradient, which the BatchNorm-backward kernels read in place (row stride 3C); gradients must equal the run in which
+    every slice is copied to a contiguous tensor first."""
+    torch.manual_seed(1)
+    lins = [mpc.pointnet2_utils.Linear(64, 64, bn=False).cuda().train() for _ in range(3)]
+    head = mpc.pointnet2_utils.Linear(192, 64, bn=False).cuda().train()
+    x = torch.randn(4, 512, 64, device="cuda")
+
+    def run(force_copy):
+        old = mpc.ops._grad_rows
+        if force_copy:
+            mpc.ops._grad_rows = lambda g, C: (g.contiguous(), C)
+        try:
+            for m in lins + [head]:
+                for p in m.parameters():
+                    p.grad = None
+            xi = x.clone().requires_grad_(True)
+            head(torch.cat([m(xi) for m in lins], 2)).square().sum().backward()
+            torch.cuda.synchronize()
+            return [xi.grad.clone()] + [p.grad.clone() for m in lins for p in m.parameters() if p.grad is not None]
+        finally:
+            mpc.ops._grad_rows = old
+
+    for a, b in zip(run(False), run(True)):
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4)

@@ -91,6 +91,14 @@ int mpc_gather_f32(const float* points, const int64_t* idx, float* out, int64_t 
                    int64_t C, mpc_stream_t stream);
 int mpc_gather_bwd_f32(const float* grad_out, const int64_t* idx, float* grad_points, int64_t B, int64_t N,
                        int64_t M, int64_t C, mpc_stream_t stream);
+/* bf16 payloads (half the HBM bytes): forward moves bf16 rows bit for bit, backward accumulates the scattered bf16
+ * gradient rows in an F32 buffer (cleared by the call; C % 2 == 0), which the host casts back. */
+int mpc_gather_bf16(const void* points, const int64_t* idx, void* out, int64_t B, int64_t N, int64_t M, int64_t C,
+                    mpc_stream_t stream);
+int mpc_gather_bwd_bf16(const void* grad_out, const int64_t* idx, float* grad_points, int64_t B, int64_t N, int64_t M,
+                        int64_t C, mpc_stream_t stream);
+/* Bytes of the reduction scratch (see the scratch contract) a layer of C channels needs: (2C + 2) doubles. */
+int mpc_reduction_scratch_bytes(int64_t C);
 int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* out, int64_t B, int64_t N, int64_t M,
                    mpc_stream_t stream);
 

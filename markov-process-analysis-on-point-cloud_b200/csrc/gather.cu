@@ -46,6 +46,25 @@ scatter_add_v4_kernel(const float4* __restrict__ grad_out, const int64_t* __rest
         red_add_f32x4(grad_points + (((size_t)b * N + n) * CV + v) * 4, __ldg(grad_out + t));
     }
 }
+// bf16 payloads (2-byte features, half the HBM bytes of the fp32 path): the forward gather is a byte mover and shares
+// gather_kernel; the backward converts on the fly and accumulates in an fp32 buffer (8 neighbours summed in bf16
+// would lose ~1 % of the gradient), two channels per thread.
+__global__ void __launch_bounds__(GT)
+scatter_add_bf16_kernel(const unsigned* __restrict__ grad_out, const int64_t* __restrict__ idx,
+                        float* __restrict__ grad_points, int N, int64_t M, int C2, int64_t total) {
+    pdl_prologue();
+    for (int64_t t = (int64_t)blockIdx.x * GT + threadIdx.x; t < total; t += (int64_t)gridDim.x * GT) {
+        const int64_t row = t / C2;
+        const int c2 = (int)(t - row * C2);
+        const int64_t b = row / M;
+        const int n = clamp_index(__ldg(idx + row), N);
+        const unsigned pr = __ldg(grad_out + t);  // two bf16: low half = even channel
+        float* dst = grad_points + ((size_t)b * N + n) * (2 * C2) + 2 * c2;
+        red_add_f32(dst, __uint_as_float(pr << 16));
+        red_add_f32(dst + 1, __uint_as_float(pr & 0xffff0000u));
+    }
+}
+
 __global__ void __launch_bounds__(GT)
 scatter_add_s_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
                      float* __restrict__ grad_points, int N, int64_t M, int C, int64_t total) {
@@ -474,6 +493,57 @@ MPC_API int mpc_gather_i64(const int64_t* values, const int64_t* idx, int64_t* o
         reinterpret_cast<const long long*>(values), idx, reinterpret_cast<long long*>(out), (int)N, M, 1, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
+}
+
+/* bf16 rows: [B,N,C] bf16 -> [B,M,C] bf16 (a byte mover: 16-byte, 4-byte or 2-byte vectors by alignment). */
+MPC_API int mpc_gather_bf16(const void* points, const int64_t* idx, void* out, int64_t B, int64_t N, int64_t M,
+                            int64_t C, mpc_stream_t stream) {
+    if (B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (B == 0 || M == 0) return MPC_OK;
+    if (!points || !idx || !out) return MPC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C % 8 == 0 && aligned16(points) && aligned16(out)) {
+        const int CV = (int)(C / 8);
+        const int64_t total = B * M * CV;
+        pdl_launch(gather_kernel<float4>, dim3(grid_for(total)), dim3(GT), 0, st, reinterpret_cast<const float4*>(points),
+                   idx, reinterpret_cast<float4*>(out), (int)N, M, CV, total);
+    } else if (C % 2 == 0) {
+        const int CV = (int)(C / 2);
+        const int64_t total = B * M * CV;
+        pdl_launch(gather_kernel<float>, dim3(grid_for(total)), dim3(GT), 0, st, reinterpret_cast<const float*>(points),
+                   idx, reinterpret_cast<float*>(out), (int)N, M, CV, total);
+    } else {
+        const int64_t total = B * M * C;
+        pdl_launch(gather_kernel<unsigned short>, dim3(grid_for(total)), dim3(GT), 0, st,
+                   reinterpret_cast<const unsigned short*>(points), idx, reinterpret_cast<unsigned short*>(out), (int)N, M,
+                   (int)C, total);
+    }
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+/* grad_points [B,N,C] F32 (cleared by the call) += grad_out [B,M,C] bf16 scattered by idx; C % 2 == 0. */
+MPC_API int mpc_gather_bwd_bf16(const void* grad_out, const int64_t* idx, float* grad_points, int64_t B, int64_t N,
+                                int64_t M, int64_t C, mpc_stream_t stream) {
+    if (B < 0 || N <= 0 || M < 0 || C <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (C % 2) return MPC_ERR_UNSUPPORTED;
+    if (B == 0) return MPC_OK;
+    if (!grad_points) return MPC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * N * C * sizeof(float), st));
+    if (M == 0) return MPC_OK;
+    if (!grad_out || !idx) return MPC_ERR_INVALID;
+    const int C2 = (int)(C / 2);
+    const int64_t total = B * M * C2;
+    pdl_launch(scatter_add_bf16_kernel, dim3(grid_for(total)), dim3(GT), 0, st, reinterpret_cast<const unsigned*>(grad_out),
+               idx, grad_points, (int)N, M, C2, total);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+/* Bytes of the reduction scratch a layer of C channels needs under the scratch contract (2C sums + 2 tickets). */
+MPC_API int mpc_reduction_scratch_bytes(int64_t C) {
+    return (C < 0 || C > (INT32_MAX / 16) - 2) ? MPC_ERR_INVALID : (int)((2 * C + 2) * sizeof(double));
 }
 
 MPC_API int mpc_gather_bwd_f32(const float* grad_out, const int64_t* idx, float* grad_points, int64_t B,

@@ -327,6 +327,36 @@ class _Gather(torch.autograd.Function):
         return grad_points, None
 
 
+class _GatherBF16(torch.autograd.Function):
+    """index_points for bf16 feature rows: half the HBM bytes of the fp32 path.  Forward moves the rows bit for bit;
+    backward scatters the bf16 gradient rows into an fp32 accumulator and casts the sum back."""
+
+    @staticmethod
+    def forward(ctx, points, idx):
+        B, N, C = points.shape
+        M = idx.numel() // B if B else 0
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.bfloat16, device=points.device)
+        call("mpc_gather_bf16", ptr(points), ptr(idx), ptr(out), _i64(B), _i64(N), _i64(M), _i64(C),
+             algo_bytes=B * M * (4 * C + 8))
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, N, M, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, N, M, C = ctx.dims
+        grad_out = grad_out.to(torch.bfloat16).contiguous()
+        acc = torch.empty(B, N, C, dtype=torch.float32, device=grad_out.device)
+        if C % 2 == 0:
+            call("mpc_gather_bwd_bf16", ptr(grad_out), ptr(idx), ptr(acc), _i64(B), _i64(N), _i64(M), _i64(C),
+                 algo_bytes=B * (M * (2 * C + 8) + N * C * 4))
+        else:
+            g32 = grad_out.float()
+            call("mpc_gather_bwd_f32", ptr(g32), ptr(idx), ptr(acc), _i64(B), _i64(N), _i64(M), _i64(C))
+        return acc.to(torch.bfloat16), None
+
+
 def index_points(points, idx, cuda=False, is_group=False):
     """R/modules/pointnet2_utils.py:64-81.  points [B,N,C], idx [B,S] or [B,S,K] (int64) ->
     [B,S,C] / [B,S,K,C].  float32 payloads are differentiable (backward = scatter-add); int64 payloads
@@ -337,6 +367,8 @@ def index_points(points, idx, cuda=False, is_group=False):
     _check_index(idx, N, "index_points")
     if points.dtype == torch.float32:
         return _Gather.apply(_f32c(points), idx)
+    if points.dtype == torch.bfloat16:
+        return _GatherBF16.apply(points.contiguous(), idx)
     if points.dtype == torch.int64:
         points = points.contiguous()
         M = idx.numel() // B if B else 0
@@ -346,7 +378,7 @@ def index_points(points, idx, cuda=False, is_group=False):
         else:  # an int64 row of C values is a float32 row of 2C values as far as a byte mover cares
             call("mpc_gather_f32", ptr(points), ptr(idx), ptr(out), _i64(B), _i64(N), _i64(M), _i64(2 * C))
         return out
-    raise TypeError("index_points supports float32 and int64 payloads, got %s" % points.dtype)
+    raise TypeError("index_points supports float32, bfloat16 and int64 payloads, got %s" % points.dtype)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -278,3 +278,29 @@ def test_sample_data_side_fps(mpc, orc):
     idx = orc.farthest_point_sample(feat[:, :3].permute(0, 2, 1).contiguous(), 64, start)
     ref = torch.gather(feat, 2, idx.unsqueeze(1).expand(-1, 6, -1))
     assert out.shape == (3, 6, 64) and torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("C", [1, 6, 64, 200])
+def test_index_points_bf16_fwd_bwd(mpc, C):
+    """bf16 payloads: the forward gather is bit-exact (a byte mover); the backward accumulates in fp32 and rounds once,
+    so it matches the fp32 scatter-add of the same bf16 gradient rows to one bf16 rounding (rtol 2e-2 stated in
+    SURVEY 8c for bf16 I/O; measured far below)."""
+    g = torch.Generator().manual_seed(C)
+    pts = torch.randn(3, 300, C, generator=g).to(torch.bfloat16).cuda()
+    idx = torch.randint(0, 300, (3, 70, 8), generator=g).cuda()
+    p1 = pts.clone().requires_grad_(True)
+    out = mpc.ops.index_points(p1, idx)
+    assert out.dtype == torch.bfloat16
+    ref = pts[torch.arange(3, device="cuda")[:, None, None], idx]
+    assert torch.equal(out, ref)
+    w = torch.randn(out.shape, generator=g).to(torch.bfloat16).cuda()
+    out.backward(w)
+    acc = torch.zeros(3, 300, C, device="cuda")
+    acc.view(3, 300, C).scatter_add_(1, idx.reshape(3, -1, 1).expand(-1, -1, C), w.float().reshape(3, -1, C))
+    torch.testing.assert_close(p1.grad.float(), acc, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(p1.grad, acc.to(torch.bfloat16), rtol=1e-2, atol=1e-2)
+
+
+def test_reduction_scratch_bytes(mpc):
+    lib = mpc._lib.load()
+    assert lib.mpc_reduction_scratch_bytes(64) == (2 * 64 + 2) * 8

@@ -756,11 +756,11 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
     if (al && C % 64 == 0 && C <= 256 && K <= 16 && g_knob[4] != 1 &&
         (C >= 128 || N <= 8192 || g_knob[4] == 2)) {
         // register-tiled variant.  C = 128 / 192 / 256: 2x the generic kernel below.  C = 64: alone it is no faster
-        // than the query-in-registers kernels (19-21 vs 23-28 TFLOP/s; 3-register FFMA issues at one warp
-        // instruction per 2 cycles per scheduler, ~37 TFLOP/s is the SIMT ceiling and both designs show "issue slots
-        // busy 50 %" in ncu), but inside the training step, where the search shares the GPU with the other two
-        // branches of its LocalMerge, it is worth 5 % of the step (12.97 vs 13.62 ms, A/B on one box); for the
-        // 24 000-point blocks the old kernels stay ahead (21.8 vs 28.2 ms per search).  (knob 4: 1 = never, 2 = always)
+        // than the query-in-registers kernels (19-21 vs 23-28 TFLOP/s; both are latency-bound at 2 warps per scheduler --
+        // ncu: no eligible warp on 50 % of the cycles -- far from the 72 TFLOP/s FFMA peak of scratch/ubench/ffma_peak.cu),
+        // but inside the training step, where the search shares the GPU with the other two branches of its LocalMerge,
+        // it is worth 5 % of the step (12.97 vs 13.62 ms, A/B on one box); for the 24 000-point blocks the old kernels
+        // stay ahead (21.8 vs 28.2 ms per search).  (knob 4: 1 = never, 2 = always)
         const size_t smem = ((size_t)C * KT_Q + KT_CK * KT_R + KT_Q * KT_DLD + KT_Q + KT_R) * sizeof(float);
         auto kern = knn_tiled_kernel<(K <= 16 ? K : 16)>;
         MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -293,7 +293,8 @@ int mpc_debug_trace_buffer(void* device_buffer);
 /* Debug facility: launch-geometry knobs of the streaming BatchNorm kernels (0 restores the built-in default).
  * id 0: elementwise CTAs per SM, 1: column-reduction CTAs per SM, 2: float4 per thread the elementwise grid is sized
  * for, 3: non-zero forces the grid-wide FPS variant for every cloud above 8192 points (parity tests of that variant
- * at sizes the CPU oracle finishes), 4: feature-space kNN variant (1 = never the register-tiled kernel, 2 = always).
+ * at sizes the CPU oracle finishes), 4: feature-space kNN variant (1 = never the register-tiled kernel), 5: KB of shared-memory padding of
+ * that kernel (occupancy experiments).
  * Process-global; used by scratch/bench_bn.py to pick the defaults. */
 int mpc_debug_set_knob(int id, int64_t value);
 

@@ -474,18 +474,19 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 constexpr int KT_THREADS = 128;
 constexpr int KT_Q = 128;   // queries per CTA
 constexpr int KT_R = 64;    // reference points per tile
-constexpr int KT_CK = 64;   // channels per shared-memory chunk of the reference tile
-constexpr int KT_DLD = KT_R + 1;  // distance tile row pitch (odd: conflict-free row scans)
+constexpr int KT_CK = 32;   // channels per shared-memory chunk of the reference tile
+constexpr int KT_DH = 32;   // reference points per selection pass: the distance tile is handed over in two halves
+                            // [128 queries][32], XOR-swizzled, so that a CTA needs 58 KB at C = 64 and THREE fit on an SM
 
 template <int K>
-__global__ void __launch_bounds__(KT_THREADS, 2)
+__global__ void __launch_bounds__(KT_THREADS, 3)
 knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
                  int64_t* __restrict__ idx_out, int N, int S, int C) {
     extern __shared__ __align__(16) float sm[];
     float* qt = sm;                              // [C][KT_Q]   queries, transposed
     float* rt = qt + (size_t)C * KT_Q;           // [KT_CK][KT_R] reference chunk, transposed
-    float* dt = rt + KT_CK * KT_R;               // [KT_Q][KT_DLD] distance tile
-    float* qn_s = dt + KT_Q * KT_DLD;            // [KT_Q]
+    float* dt = rt + KT_CK * KT_R;               // [KT_Q][KT_DH] half distance tile, column j of row i at j ^ (i & 31)
+    float* qn_s = dt + KT_Q * KT_DH;             // [KT_Q]
     float* rn_s = qn_s + KT_Q;                   // [KT_R]
     __shared__ CandQueue queue;
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -584,35 +585,43 @@ knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, f
         }
         if (tid < KT_R) rn_s[tid] = rnorm;
         __syncthreads();
-        // distance tile: d = ((-2 dot) + |q|^2) + |r|^2, the reference's order
+        // distance tile: d = ((-2 dot) + |q|^2) + |r|^2, the reference's order; handed to the selection phase in two
+        // halves of 32 reference points (ascending index order is preserved: points 0..31, then 32..63)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int qi = (i < 4 ? 0 : 60) + ty * 4 + i;  // rows ty*4+{0..3}, 64+ty*4+{0..3}
-            const float qn = qn_s[qi];
+        for (int half = 0; half < 2; ++half) {
+            if (half) __syncthreads();  // the first half has been scanned
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int rj = (j < 4 ? 0 : 28) + tx * 4 + j;  // cols tx*4+{0..3}, 32+tx*4+{0..3}
-                float lo, hi;
-                unpack2(acc2[i][j >> 1], lo, hi);
-                dt[qi * KT_DLD + rj] = sqdist_from_dot((j & 1) ? hi : lo, qn, rn_s[rj]);
-            }
-        }
-        __syncthreads();
-        // selection: thread = query, candidates in ascending index order
-        const float* row = dt + tid * KT_DLD;
-#pragma unroll 1
-        for (int j0 = 0; j0 < KT_R; j0 += 4) {
+            for (int i = 0; i < 8; ++i) {
+                const int qi = (i < 4 ? 0 : 60) + ty * 4 + i;  // rows ty*4+{0..3}, 64+ty*4+{0..3}
+                const float qn = qn_s[qi];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u;
-                const float d = row[j];
-                if (j < tn && d < thr) {
-                    queue.d[qcnt][tid] = d;
-                    queue.i[qcnt][tid] = t0 + j;
-                    ++qcnt;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = half * 4 + jj;      // accumulator column; reference point half*32 + tx*4 + jj
+                    const int col = tx * 4 + jj;      // column inside the half tile
+                    float lo, hi;
+                    unpack2(acc2[i][j >> 1], lo, hi);
+                    dt[qi * KT_DH + (col ^ (qi & 31))] =
+                        sqdist_from_dot((j & 1) ? hi : lo, qn, rn_s[half * KT_DH + col]);
                 }
             }
-            if (__any_sync(0xffffffffu, qcnt > KNN_QFLUSH)) drain_queue<K>(queue, qcnt, bd, bi, thr);
+            __syncthreads();
+            // selection: thread = query, candidates in ascending index order
+            const float* row = dt + tid * KT_DH;
+            const int sw = tid & 31;
+#pragma unroll 1
+            for (int j0 = 0; j0 < KT_DH; j0 += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u;
+                    const float d = row[j ^ sw];
+                    if (half * KT_DH + j < tn && d < thr) {
+                        queue.d[qcnt][tid] = d;
+                        queue.i[qcnt][tid] = t0 + half * KT_DH + j;
+                        ++qcnt;
+                    }
+                }
+                if (__any_sync(0xffffffffu, qcnt > KNN_QFLUSH)) drain_queue<K>(queue, qcnt, bd, bi, thr);
+            }
         }
     }
     drain_queue<K>(queue, qcnt, bd, bi, thr);
@@ -753,15 +762,22 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
         return MPC_OK;
     }
     const bool al = (reinterpret_cast<uintptr_t>(ref) & 15u) == 0 && (reinterpret_cast<uintptr_t>(qry) & 15u) == 0;
-    if (al && C % 64 == 0 && C <= 256 && K <= 16 && g_knob[4] != 1 &&
-        (C >= 128 || N <= 8192 || g_knob[4] == 2)) {
-        // register-tiled variant.  C = 128 / 192 / 256: 2x the generic kernel below.  C = 64: alone it is no faster
-        // than the query-in-registers kernels (19-21 vs 23-28 TFLOP/s; both are latency-bound at 2 warps per scheduler --
-        // ncu: no eligible warp on 50 % of the cycles -- far from the 72 TFLOP/s FFMA peak of scratch/ubench/ffma_peak.cu),
-        // but inside the training step, where the search shares the GPU with the other two branches of its LocalMerge,
-        // it is worth 5 % of the step (12.97 vs 13.62 ms, A/B on one box); for the 24 000-point blocks the old kernels
-        // stay ahead (21.8 vs 28.2 ms per search).  (knob 4: 1 = never, 2 = always)
-        const size_t smem = ((size_t)C * KT_Q + KT_CK * KT_R + KT_Q * KT_DLD + KT_Q + KT_R) * sizeof(float);
+    if (al && C % 64 == 0 && C <= 256 && K <= 16 && g_knob[4] != 1) {
+        // register-tiled variant (knob 4 = 1 forces the query-in-registers / generic kernels below).  Measured, k = 8:
+        // C = 128 / 256: 2x the generic kernel; C = 64, 24 000 x 24 000 x 8 clouds: 20.8 vs 21.8 ms, 12 000 x 24 000:
+        // 11.6 vs 14.4 ms, 2048 x 2048 x 32 clouds: 0.90 vs 0.79 ms alone but 5 % better for the training step, where
+        // the search shares the GPU with the other two branches of its LocalMerge (12.97 vs 13.62 ms, A/B on one box).
+        // Both designs are latency-bound (ncu: no eligible warp on ~50 % of the cycles) far below the 72 TFLOP/s FFMA
+        // peak of scratch/ubench/ffma_peak.cu; three resident CTAs (58 KB each at C = 64) are what lifted the large
+        // clouds from 19-21 to 24-29 TFLOP/s.
+        // Occupancy: three CTAs per SM pay off when the launch has many waves of CTAs (24 000-point blocks: +6 % on the
+        // fwd+bwd step); with ~1-2 waves (32 clouds x 2048 queries = 512 CTAs) two fatter-share CTAs per SM are as fast
+        // or slightly faster inside the training step (11.63 / 11.69 vs 11.70 / 11.74 ms, A/B), so small launches pad
+        // their shared-memory request.  knob 5 (KB of padding) overrides.
+        const int64_t ctas = (int64_t)B * ceil_div(S, KT_Q);
+        const int64_t pad_kb = g_knob[5] > 0 ? g_knob[5] : ((C == 64 && ctas <= 4 * kNumSMs) ? 22 : 0);
+        const size_t smem = ((size_t)C * KT_Q + KT_CK * KT_R + KT_Q * KT_DH + KT_Q + KT_R) * sizeof(float) +
+                            (size_t)pad_kb * 1024;
         auto kern = knn_tiled_kernel<(K <= 16 ? K : 16)>;
         MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)ceil_div(S, KT_Q), (unsigned)B);

@@ -13,8 +13,11 @@
  *   - float data is IEEE binary32, indices are int64 (the reference's API dtype);
  *   - the caller owns every buffer (outputs and scratch included); nothing is allocated, nothing
  *     synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*);
- *   - re-entrant, no global state: safe for one process per GPU under torchrun, and capturable into a
- *     CUDA graph;
+ *   - re-entrant and capturable into a CUDA graph; process-global state is limited to the tensor-map cache of
+ *     the GEMMs (mutex-protected), the barrier words of the grid-wide FPS variant (N > 262 144: one such call in flight
+ *     per device) and the debug knobs: safe for one process per GPU under torchrun;
+ *   - reduction scratch buffers follow the "zero on entry, zero on exit" contract stated with the BatchNorm entry
+ *     points: the caller allocates them zeroed once, no call memsets them;
  *   - returns 0 on success, a positive cudaError_t if a launch failed, or a negative MPC_ERR_* code if
  *     the arguments are rejected (nothing is launched in that case).
  *   - indices that are out of range are never dereferenced: gather-type kernels clamp them into range

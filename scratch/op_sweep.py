@@ -1,7 +1,13 @@
 """BASELINE config 4: op microbench sweep on single large clouds (B=1; B=8 at 16K), S = N/4 queries, C = 64 features.
-Prints one line per (op, N): device time (CUDA events, L2 flushed), algorithmic GB/s or TFLOP/s (SURVEY 8d formulas)."""
-import importlib, sys, torch
+Prints one line per (op, N): device time (CUDA events, L2 flushed), algorithmic GB/s or TFLOP/s (SURVEY 8d formulas).
+Under torchrun (N GPUs) every rank sweeps its own cloud -- the ops shard by cloud, FPS does not shard inside one -- and
+rank 0 prints the slowest rank's time and the aggregate rate (weak scaling)."""
+import importlib, os, sys, torch
 sys.path.insert(0, '.')
+RANK, WORLD = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+if WORLD > 1:
+    torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
 mpc = importlib.import_module("markov-process-analysis-on-point-cloud_b200")
 ops = mpc.ops
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -12,13 +18,19 @@ def timeit(fn, n=3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    ts.sort(); return ts[len(ts) // 2]
+    ts.sort(); t = ts[len(ts) // 2]
+    if WORLD > 1:  # slowest rank
+        tt = torch.tensor([t], device="cuda"); torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX); t = float(tt)
+    return t / WORLD  # aggregate rate = WORLD clouds per t
 sizes = [int(a) for a in sys.argv[1:]] or [16384, 65536, 262144, 1048576]
+_print = print
+print = lambda *a, **k: _print(*a, **k) if RANK == 0 else None
+if WORLD > 1: print("# %d GPUs, one cloud set per GPU; ms = slowest rank / %d (time per GPU-cloud in aggregate)" % (WORLD, WORLD))
 print("%-22s %8s %3s %10s %12s" % ("op", "N", "B", "ms", "rate"))
 for N in sizes:
     B = 8 if N <= 16384 else 1
     S, C = N // 4, 64
-    g = torch.Generator().manual_seed(N)
+    g = torch.Generator().manual_seed(N + RANK)
     xyz = (torch.rand(B, N, 3, generator=g) * 2 - 1).cuda()
     feat = torch.randn(B, N, C, generator=g).cuda()
     start = torch.zeros(B, dtype=torch.long, device="cuda")

@@ -4,6 +4,7 @@ There is no CPU fallback: if the library is missing, or no CUDA device is presen
 the call raises.
 """
 import ctypes
+import functools
 import os
 
 import torch
@@ -126,6 +127,8 @@ def call(name, *args, algo_bytes=0):
     if timed:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        if prof.get("keep_args"):
+            prof.setdefault("args", {}).setdefault(name, []).append(args)
     rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         kind = {-1: "invalid arguments", -2: "unsupported shape"}.get(rc, "CUDA error %d" % rc)
@@ -152,7 +155,39 @@ def replay(calls):
 
 
 def require_cuda(*tensors):
+    """Every operand on a CUDA device, and all of them on the same one."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise MpcError("mpc_b200 ops run on a CUDA device only (got a %s tensor); there is no CPU fallback"
                            % t.device.type)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise MpcError("mpc_b200 ops need all operands on one device (got %s and %s)" % (dev, t.device))
+
+
+def _first_cuda_tensor(args, kwargs):
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a
+    for a in kwargs.values():
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a
+    return None
+
+
+def on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first CUDA tensor argument current.  Kernels are launched on torch's
+    current stream, which belongs to torch's current device: a model on cuda:1 called while cuda:0 is current would
+    otherwise be launched on device 0 with device-1 pointers.  A no-op (one comparison) when the devices agree."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(args, kwargs)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper

@@ -617,10 +617,14 @@ static void pick_pipeline(int stage_bytes, int* stages, int* epi_bufs) {
 }
 
 static cudaError_t ensure_smem_optin() {
-    static bool done = false;  // idempotent attribute; a benign race at worst sets it twice
-    if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + ~10 KB static <= 227 KB
-    done = e == cudaSuccess;
+    // the attribute is per device (and idempotent: a benign race at worst sets it twice)
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + ~10 KB static <= 227 KB
+    if (dev >= 0 && dev < 64) done[dev] = e == cudaSuccess;
     return e;
 }
 

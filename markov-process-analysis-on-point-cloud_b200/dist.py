@@ -1,7 +1,14 @@
 """Data-parallel plumbing for the one exchange step of the path: batches of clouds are sharded across ranks
-(one process per GPU), nothing is exchanged in forward, and after backward the gradients are averaged with one
-coalesced all-reduce (NCCL over NVLink on GPUs; gloo in the CPU tests).  BatchNorm statistics stay per replica --
-the reference is single-GPU, so a replica reproduces the reference on its shard (plain DDP semantics).
+(one process per GPU), nothing is exchanged in forward, and after backward the gradients are averaged (NCCL over
+NVLink on GPUs; gloo in the CPU tests).  BatchNorm statistics stay per replica -- the reference is single-GPU, so a
+replica reproduces the reference on its shard (plain DDP semantics).
+
+Two forms of the exchange:
+  * GradBucket: every gradient is packed into ONE contiguous fp32 buffer (a handful of multi-tensor copy launches,
+    capturable in the step's CUDA graph), one all-reduce with the 1/world folded into the reduction (ReduceOp.AVG on
+    NCCL), and `p.grad` then points at views of that buffer, so an optimiser reads the averaged gradients in place.
+    16.5 MB (part-seg) / 34.1 MB (classifier) cross NVLink in one collective instead of ~1300 coalesced ones.
+  * allreduce_mean_grads: the per-tensor coalesced form (kept for callers that hold no bucket).
 """
 import torch
 import torch.distributed as dist
@@ -12,6 +19,51 @@ def shard_batch(batch_size, rank, world):
     base, rem = divmod(batch_size, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradBucket:
+    """One flat fp32 gradient buffer for the parameters that receive a gradient (decided once, after a warm-up
+    backward: which parameters are used does not depend on the data, so every rank builds the same layout; the
+    reference's constructed-but-unused sub-modules are left out on every rank alike)."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.grad is not None]
+        if not self.params:
+            raise ValueError("GradBucket needs parameters that already hold a gradient (run one backward first)")
+        dev = self.params[0].device
+        self.group = group
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def pack(self):
+        """Copy the freshly written gradients into the bucket (multi-tensor copy: ~1 launch per 100 tensors)."""
+        torch._foreach_copy_(self.views, [p.grad for p in self.params])
+
+    def all_reduce(self, world=None):
+        """Mean over the ranks, in place in the bucket.  No-op for a single rank."""
+        if world is None:
+            world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world <= 1:
+            return
+        if self.flat.is_cuda:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:  # gloo has no AVG
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(float(world))
+
+    def attach(self):
+        """Point every p.grad at its slice of the (averaged) bucket."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def exchange(self, world=None):
+        self.pack()
+        self.all_reduce(world)
+        self.attach()
 
 
 def allreduce_mean_grads(params, world=None, group=None):

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import call, ptr, require_cuda
+from ._lib import call, on_tensor_device, ptr, require_cuda
 
 _i64 = ctypes.c_int64
 _CHECK_INDEX = os.environ.get("MPC_CHECK_INDEX", "0") == "1"
@@ -43,24 +43,29 @@ class _IndexTape:
         self.inject = None  # list of index tensors consumed in call order
         self.record = None  # list that receives (kind, idx) in call order
         self.fps_starts = None  # list of [B] int64 start tensors consumed in call order
+        self.audit = None  # list receiving (kind, own idx, own dist, injected idx, reference set, queries) per search
 
 
 _tape = _IndexTape()
 
 
 @contextlib.contextmanager
-def index_tape(inject=None, record=None, fps_starts=None):
+def index_tape(inject=None, record=None, fps_starts=None, audit=None):
     """inject: iterable of index tensors returned (in call order) by farthest_point_sample / knn_point
     instead of computing them; record: list receiving ("fps"|"knn"|"knnf", idx); fps_starts: iterable of [B] start
-    indices used instead of drawing them from the CPU generator."""
-    old = (_tape.inject, _tape.record, _tape.fps_starts)
+    indices used instead of drawing them from the CPU generator; audit: list receiving, for every neighbour search
+    (with or without injection), (kind, own idx, own dist, injected idx or None, reference set, queries) -- the search
+    itself always runs, so a test can compare this path's neighbours with the injected ones on the very operands this
+    path saw ("teacher forcing": the tie audit of SURVEY.md 8c)."""
+    old = (_tape.inject, _tape.record, _tape.fps_starts, _tape.audit)
     _tape.inject = list(inject) if inject is not None else None
     _tape.record = record
     _tape.fps_starts = list(fps_starts) if fps_starts is not None else None
+    _tape.audit = audit
     try:
         yield
     finally:
-        _tape.inject, _tape.record, _tape.fps_starts = old
+        _tape.inject, _tape.record, _tape.fps_starts, _tape.audit = old
 
 
 def _taped(kind, device):
@@ -86,6 +91,7 @@ def draw_fps_start(B, N, device):
     return torch.randint(0, N, (B,), dtype=torch.long).to(device)
 
 
+@on_tensor_device
 @torch.no_grad()
 def farthest_point_sample(xyz, npoint, cuda=False, start=None):
     """R/modules/pointnet2_utils.py:84-109.  xyz [B,N,C] -> int64 [B,npoint]; bit-exact with the reference
@@ -107,6 +113,10 @@ def _fps_launch(xyz, npoint, start):
     B, N, C = xyz.shape
     xyz = _f32c(xyz.detach())
     start = _i64c(start.to(xyz.device))
+    if start.shape != (B,):
+        raise ValueError("farthest_point_sample: start must hold one index per cloud, got shape %s" % (tuple(start.shape),))
+    if _CHECK_INDEX and B:  # (the kernel clamps an out-of-range start into [0, N); the reference would raise)
+        _check_index(start, N, "farthest_point_sample start")
     out = torch.empty(B, npoint, dtype=torch.int64, device=xyz.device)
     call("mpc_fps_f32", ptr(xyz), ptr(start), ptr(out), _i64(B), _i64(N), _i64(C), _i64(npoint),
          algo_bytes=B * (N * C * 4 + npoint * 8))
@@ -119,6 +129,7 @@ def _fps_compute(xyz, npoint):
     return _fps_launch(xyz, npoint, draw_fps_start(B, N, xyz.device))
 
 
+@on_tensor_device
 def sample(nsample, feature, cuda=False):
     """Data-side FPS of the reference's training scripts (`sample(args.num_point, points, cuda=...)`,
     R/tool/train_cls_scanobjectnn.py:244 -- called there, defined nowhere in the shipped tree; upstream RepSurf
@@ -130,13 +141,17 @@ def sample(nsample, feature, cuda=False):
     return index_points(feature.permute(0, 2, 1).contiguous(), idx).permute(0, 2, 1).contiguous()
 
 
-def _list_length(k):
+def _list_length(k, N):
+    """The kernels keep sorted neighbour lists of these compiled lengths; a longer list is computed and sliced (when
+    the compiled length exceeds the number of reference points, _knn_compute pads the reference set)."""
+    if k > _KNN_LIST_LENGTHS[-1]:
+        raise ValueError("knn_point supports nsample <= %d, got %d" % (_KNN_LIST_LENGTHS[-1], k))
     for L in _KNN_LIST_LENGTHS:
         if k <= L:
             return L
-    raise ValueError("knn_point supports nsample <= %d, got %d" % (_KNN_LIST_LENGTHS[-1], k))
 
 
+@on_tensor_device
 @torch.no_grad()
 def knn_point(nsample, xyz, new_xyz):
     """R/modules/pointnet2_utils.py:211-222.  NOTE the reference's argument order: (k, reference set
@@ -151,6 +166,8 @@ def knn_point(nsample, xyz, new_xyz):
     # inside one forward the same coordinate search can be asked for twice (la0 and la1_up both search the full
     # cloud in itself) or be prefetched: the geometry scope remembers coordinate-space results by operand identity
     dist, idx = _knn_compute(nsample, xyz, new_xyz)
+    if _tape.audit is not None:
+        _tape.audit.append(("knn" if C == 3 else "knnf", idx, dist, taped, xyz, new_xyz))
     if taped is not None:
         idx = taped
     _record("knn" if C == 3 else "knnf", idx)  # "knnf": feature-space search (tie-prone, see tests)
@@ -163,21 +180,27 @@ def _knn_compute(nsample, xyz, new_xyz):
     B, N, C = xyz.shape
     S = new_xyz.shape[1]
     cache = _geo.cache if (_geo is not None and C == 3) else None
-    key = (xyz.data_ptr(), new_xyz.data_ptr(), tuple(xyz.shape), tuple(new_xyz.shape), nsample)
+    key = (xyz.data_ptr(), new_xyz.data_ptr(), tuple(xyz.shape), tuple(new_xyz.shape), xyz.stride(), new_xyz.stride(),
+           nsample)
     if cache is not None and key in cache:
-        return cache[key]
+        return cache[key][:2]
     xyz, new_xyz = _f32c(xyz.detach()), _f32c(new_xyz.detach())
-    L = _list_length(nsample)  # the kernels keep sorted lists of these lengths; a longer list is sliced
+    L = _list_length(nsample, N)
     if L > N:
-        raise ValueError("knn_point: k=%d with only N=%d reference points is not supported" % (nsample, N))
+        # k <= N < L (a handful of reference points): pad the reference set with L - N points far outside any cloud;
+        # their distances exceed every real one, so they never enter the first k <= N entries that are returned
+        pad = torch.full((B, L - N, C), 1e18, dtype=torch.float32, device=xyz.device)
+        xyz_run, N_run = torch.cat((xyz, pad), 1), L
+    else:
+        xyz_run, N_run = xyz, N
     dist = torch.empty(B, S, L, dtype=torch.float32, device=xyz.device)
     idx = torch.empty(B, S, L, dtype=torch.int64, device=xyz.device)
-    call("mpc_knn_f32", ptr(xyz), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N), _i64(S), _i64(C), _i64(L),
-         algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
+    call("mpc_knn_f32", ptr(xyz_run), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N_run), _i64(S), _i64(C),
+         _i64(L), algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
     if L != nsample:
         dist, idx = dist[:, :, :nsample].contiguous(), idx[:, :, :nsample].contiguous()
     if cache is not None:
-        cache[key] = (dist, idx)
+        cache[key] = (dist, idx, xyz, new_xyz)  # the operands stay alive with the entry: their addresses are the key
     return dist, idx
 
 
@@ -200,6 +223,7 @@ def square_distance(src, dst):
     return dist
 
 
+@on_tensor_device
 @torch.no_grad()
 def query_ball_point(radius, nsample, xyz, new_xyz, cuda=False):
     """R/modules/pointnet2_utils.py:112-134 -> int64 [B,S,nsample] (ascending index order, padded with the
@@ -256,6 +280,7 @@ def _ce_scratch(device):
     return buf
 
 
+@on_tensor_device
 def smooth_cross_entropy(pred, target, eps=0.1):
     """mean_rows( -sum_c smooth_one_hot(target)[c] * log_softmax(pred)[c] ), pred [M,C] f32 on the device."""
     require_cuda(pred)
@@ -275,6 +300,7 @@ def xyz2sphere(xyz, normalize=True):
     return torch.cat([rho, theta, phi], dim=-1)
 
 
+@on_tensor_device
 @torch.no_grad()
 def umbrella_features(center, k=9, return_dist=True, sign=None):
     """The umbrella feature UmbrellaSurfaceConstructor feeds to its MLP (R/modules/pointnet2_utils.py:360-378):
@@ -357,6 +383,7 @@ class _GatherBF16(torch.autograd.Function):
         return acc.to(torch.bfloat16), None
 
 
+@on_tensor_device
 def index_points(points, idx, cuda=False, is_group=False):
     """R/modules/pointnet2_utils.py:64-81.  points [B,N,C], idx [B,S] or [B,S,K] (int64) ->
     [B,S,C] / [B,S,K,C].  float32 payloads are differentiable (backward = scatter-add); int64 payloads
@@ -413,6 +440,7 @@ class _Transition(torch.autograd.Function):
         return g, None, None
 
 
+@on_tensor_device
 def upsample(points, knn_idx, scale_ratio=2, dist=None, n_out=None):
     """The Markov state transition, R/modules/pointnet2_utils.py:13-50: out = D^-1 A^T points with A the
     S x N kNN incidence (K ones per row) and D the count-normalisation of :44-48.  points [B,S,C], knn_idx
@@ -464,6 +492,7 @@ class ThreeInterpolate(torch.autograd.Function):
         return g, None, None
 
 
+@on_tensor_device
 def three_interpolate(points2, dist, idx):
     require_cuda(points2, dist, idx)
     return ThreeInterpolate.apply(_f32c(points2), _f32c(dist.detach()), _i64c(idx))
@@ -538,6 +567,7 @@ class FeatAttention(torch.autograd.Function):
              algo_bytes=B * ((2 * N * C + 2 * S * C) * 4 + S * K * 8))
         ctx.save_for_backward(c2d, f2d, idx, wq, wkv, q, kv)
         ctx.shapes = (B, S, N, Cin, C, K, center.data_ptr() == features.data_ptr() and S == N)
+        ctx.wparams = (wq, wk, wv)  # the parameter objects (the saved wkv is a concatenated copy)
         return out
 
     @staticmethod
@@ -567,7 +597,7 @@ class FeatAttention(torch.autograd.Function):
                  _i64(B * N), _i64(Cin), _i64(2 * C), _i64(1 if zeroed else 0),
                  algo_bytes=(B * N * (Cin + 2 * C) + 2 * C * Cin) * 4)
 
-        if zeroed and _DEFER_WGRAD and _STREAMS_ENABLED:
+        if zeroed and _DEFER_WGRAD and _STREAMS_ENABLED and _wgrad_deferrable(*ctx.wparams):
             _defer_wgrad(wgrads, (gq, c2d, gkv, f2d, gwq, gwkv))  # off the critical path, see _defer_wgrad
         else:
             wgrads()
@@ -705,6 +735,7 @@ class BNAct(torch.autograd.Function):
         return gy, gg, gb, None, None, None, None, None, None, None
 
 
+@on_tensor_device
 def bn_act(y2d, gamma, beta, running_mean, running_var, num_batches_tracked, training, momentum=0.1, eps=1e-5,
            slope=0.2):
     """slope = 1.0 means no activation (Linear(..., act=False))."""
@@ -731,7 +762,28 @@ def set_defer_wgrad(on):
 
 
 _wgrad_streams = {}
-_wgrad_pending = set()
+_wgrad_pending = {}  # device -> id of the backward pass (autograd graph task) whose join callback is queued
+
+
+def _wgrad_deferrable(*params):
+    """Deferring is only sound when AccumulateGrad will STEAL the gradient buffer (p.grad is None: nothing reads
+    the buffer before the end-of-backward join) and nothing observes the gradient earlier (tensor hooks /
+    post-accumulate hooks, e.g. a DDP-style reducer).  With gradient accumulation (p.grad already set),
+    zero_grad(set_to_none=False) or a weight used twice in one backward, autograd reads the buffer on the backward
+    stream right away: those launches run inline -- after joining whatever the weight-gradient stream still has in
+    flight for this device, because p.grad may be a buffer it is still writing."""
+    ok = True
+    for p in params:
+        if p is None:
+            continue
+        if p.grad is not None or getattr(p, "_backward_hooks", None) or getattr(p, "_post_accumulate_grad_hooks", None):
+            ok = False
+    if not ok:
+        cur = torch.cuda.current_stream()
+        st = _wgrad_streams.get(cur.device)
+        if st is not None:
+            cur.wait_stream(st)
+    return ok
 
 
 def _defer_wgrad(fn, tensors):
@@ -745,15 +797,21 @@ def _defer_wgrad(fn, tensors):
     for t in tensors:
         if t is not None:
             t.record_stream(st)
-    if cur.device not in _wgrad_pending:
-        _wgrad_pending.add(cur.device)
+    # one join per backward pass: keyed by the autograd graph task, so a backward that raised (its callback never ran)
+    # cannot leave the device marked as pending for the next one
+    task = torch._C._current_graph_task_id()
+    if _wgrad_pending.get(cur.device) != task or task < 0:
         dev = cur.device
+        _wgrad_pending[dev] = task
 
         def join():
-            _wgrad_pending.discard(dev)
+            _wgrad_pending.pop(dev, None)
             torch.cuda.current_stream(dev).wait_stream(st)
 
-        torch.autograd.Variable._execution_engine.queue_callback(join)
+        if task >= 0:
+            torch.autograd.Variable._execution_engine.queue_callback(join)
+        else:  # not inside a backward pass (direct call of a Function's backward): join at once
+            join()
 
 
 # dgrad || wgrad of a Linear+BN block on two streams: measured 2 % SLOWER on the part-seg step (both GEMMs want every
@@ -937,7 +995,8 @@ class LinearBNAct(torch.autograd.Function):
         if ctx.needs_input_grad[0] and tc_wgrad and _BWD_PAIR:
             # grad-input and grad-weight only share their input: side by side (two graph branches)
             gx, _ = parallel(lambda: _tc_dgrad(gy, w, x2d), wgrad)
-        elif ctx.needs_input_grad[0] and tc_wgrad and _DEFER_WGRAD and _STREAMS_ENABLED:
+        elif (ctx.needs_input_grad[0] and tc_wgrad and _DEFER_WGRAD and _STREAMS_ENABLED
+              and _wgrad_deferrable(w)):
             # nothing upstream waits for a weight gradient: it runs on the weight-gradient stream, ordered after the
             # BatchNorm backward above, and rejoins at the end of the backward pass (see _defer_wgrad)
             _defer_wgrad(wgrad, (gy, x2d, flat))
@@ -1014,7 +1073,8 @@ class LinearBNActSplit(torch.autograd.Function):
             call("mpc_linear_wgrad_f32", ptr(gy), _i64(N), ptr(x2d), _i64(Ka), ptr(gw), _i64(Kt), _i64(M), _i64(Ka),
                  _i64(N), _i64(1), algo_bytes=(M * Ka + M * N + N * Ka) * 4)
 
-        if _DEFER_WGRAD and _STREAMS_ENABLED:
+        deferred = _DEFER_WGRAD and _STREAMS_ENABLED and _wgrad_deferrable(w)
+        if deferred:
             _defer_wgrad(wgrad, (gy, x2d, flat))
         else:
             wgrad()
@@ -1026,7 +1086,7 @@ class LinearBNActSplit(torch.autograd.Function):
         colsum = gy.view(-1, rows, N).sum(1)  # [G,N]: per-cloud column sums of grad_y
         gg_ = colsum.mm(w[:, Ka:]) if ctx.needs_input_grad[1] else None
         gwb = colsum.t().mm(g)  # [N,Kb]
-        if _DEFER_WGRAD and _STREAMS_ENABLED:
+        if deferred:
             # the deferred wgrad owns `flat` on its stream: the Wb slice is written there too, after it
             st = _wgrad_streams[dev]
             st.wait_stream(torch.cuda.current_stream())
@@ -1041,6 +1101,7 @@ class LinearBNActSplit(torch.autograd.Function):
         return gx, gg_, gw, gbias, gg, gb, None, None, None, None, None, None, None, None
 
 
+@on_tensor_device
 def linear_bn_act_split(x_a, g, weight, bias, bn, training, slope):
     """x_a [B,Np,Ka] (per-point channels), g [B,Kb] (per-cloud channels) -> act(BN(Linear(cat(x_a, broadcast g)))),
     [B,Np,N]; see LinearBNActSplit.  Caller guarantees Np % 128 == 0 and Ka % 32 == 0."""
@@ -1049,8 +1110,16 @@ def linear_bn_act_split(x_a, g, weight, bias, bn, training, slope):
     N = weight.shape[0]
     out = LinearBNActSplit.apply(_f32c(x_a.reshape(-1, Ka)), _f32c(g), weight.contiguous(), bias, bn.weight, bn.bias,
                                  bn.running_mean, bn.running_var, bn.num_batches_tracked, bool(training),
-                                 float(bn.momentum), float(bn.eps), float(slope), int(Np))
+                                 _momentum(bn), float(bn.eps), float(slope), int(Np))
     return out.view(B, Np, N)
+
+
+def _momentum(bn):
+    """nn.BatchNorm's momentum=None means a cumulative moving average: factor 1 / num_batches_tracked (after the
+    increment this forward performs)."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    return 1.0 / float(int(bn.num_batches_tracked) + 1)
 
 
 def split_supported(n_points, Ka, N):
@@ -1058,6 +1127,7 @@ def split_supported(n_points, Ka, N):
             and 1024 % N == 0)
 
 
+@on_tensor_device
 def linear_bn_act(x, weight, bias, bn, training, slope, residual=None):
     """Linear -> BatchNorm1d(channels) -> LeakyReLU(slope) [+ residual] on any [..., K] input (slope = 1: no
     activation).  `bn` is the nn.BatchNorm1d holding gamma / beta / running statistics.  `residual` ([..., N]) is
@@ -1069,17 +1139,18 @@ def linear_bn_act(x, weight, bias, bn, training, slope, residual=None):
     if _tc_ok(x2d, weight):
         res2d = _f32c(residual.reshape(-1, N)) if residual is not None else None
         out = LinearBNAct.apply(_f32c(x2d), weight.contiguous(), bias, bn.weight, bn.bias, bn.running_mean,
-                                bn.running_var, bn.num_batches_tracked, bool(training), float(bn.momentum),
+                                bn.running_var, bn.num_batches_tracked, bool(training), _momentum(bn),
                                 float(bn.eps), float(slope), res2d)
     else:
         y = torch.nn.functional.linear(x2d, weight, bias)
         out = bn_act(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, training,
-                     momentum=bn.momentum, eps=bn.eps, slope=slope)
+                     momentum=_momentum(bn), eps=bn.eps, slope=slope)
         if residual is not None:
             out = out + residual.reshape(-1, N)
     return out.view(*shape[:-1], N)
 
 
+@on_tensor_device
 def linear(x, weight, bias=None):
     """nn.Linear's arithmetic on any [..., K] input: the tcgen05 3xTF32 kernel when K % 32 == 0, else the
     library GEMM (K = 3 / 16 layers: a few kFLOP per point)."""
@@ -1237,10 +1308,10 @@ def fps_and_gather(points, npoint):
     """One sampling step of the encoders (R/modules/pointnet2_utils.py:771-772 and the like): FPS indices and the
     sampled coordinates.  Inside a geometry scope a prefetched result (geo_prefetch_pyramid) is returned."""
     if _geo is not None:
-        hit = _geo.fps_cache.get((points.data_ptr(), tuple(points.shape), npoint))
+        hit = _geo.fps_cache.get((points.data_ptr(), tuple(points.shape), points.stride(), npoint))
         if hit is not None:
             _record("fps", hit[0])
-            return hit
+            return hit[0], hit[1]
     idx = farthest_point_sample(points, npoint)
     return idx, index_points(points, idx)
 
@@ -1273,7 +1344,7 @@ def geo_prefetch_pyramid(xyz, npoints, k, self_levels=(0,), cross=()):
         def sample(base=base, npoint=npoint):
             idx = _fps_compute(base, npoint)
             sub = index_points(base, idx)
-            geo.fps_cache[(base.data_ptr(), tuple(base.shape), npoint)] = (idx, sub)
+            geo.fps_cache[(base.data_ptr(), tuple(base.shape), base.stride(), npoint)] = (idx, sub, base)
             return idx, sub
 
         _, sub = geo.call(sample, "fps", deps=(base,))

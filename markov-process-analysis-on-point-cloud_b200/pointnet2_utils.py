@@ -17,6 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from ._lib import on_tensor_device
 from .ops import (farthest_point_sample, index_points, knn_point, query_ball_point, query_knn_point,  # noqa: F401
                   sample, square_distance, three_interpolate, three_nn, upsample)
 
@@ -68,6 +69,7 @@ class LocalTrans(nn.Module):
         self.ffn = Linear(out_c, out_c, bn=False)
         self.tanh = nn.Tanh()
 
+    @on_tensor_device
     def forward(self, features, idx, pos, FPS_idx=None, xyz=False):
         if self.usetanh is True:
             # the reference's tanh branch (:535-537) multiplies [B,S,K,C] by [B,S,K,C] with matmul, which
@@ -87,7 +89,7 @@ class LocalTrans(nn.Module):
                 n = self.conv_res.norm2
                 shape = res.shape
                 residual = ops.bn_act(res.view(-1, shape[-1]), n.weight, n.bias, n.running_mean, n.running_var,
-                                      n.num_batches_tracked, self.training, momentum=n.momentum, eps=n.eps,
+                                      n.num_batches_tracked, self.training, momentum=ops._momentum(n), eps=n.eps,
                                       slope=0.2 if self.conv_res.act_flag is True else 1.0).view(shape)
             else:
                 center = index_points(features, FPS_idx) if FPS_idx is not None else features
@@ -121,6 +123,7 @@ class LocalMerge(nn.Module):
         self.feature_Trans1 = LocalTrans(in_channels, out_channels, knn, usetanh=self.usetanh, residual=self.residual)
         self.feature_Trans2 = LocalTrans(in_channels, out_channels, knn, usetanh=self.usetanh, residual=self.residual)
 
+    @on_tensor_device
     def forward(self, xyz, base_xyz, normal=None, feature=None, FPS_idx=None, xyz_flag=True):
         # coordinate-space neighbour search: geometry stream (it only depends on the cloud), joined here
         dist, idx = ops.geo_join(ops.geo_call(lambda: knn_point(self.knn, base_xyz, xyz)))
@@ -234,12 +237,14 @@ class KeepHighResolutionModulePartSeg(nn.Module):
         self.fuse5 = Fuse(64, 64, 64, 128, 256)
         self.lrelu = nn.LeakyReLU(negative_slope=0.2)
 
+    @on_tensor_device
     def forward(self, xyz, normal, label):
         xyz = xyz.permute(0, 2, 1).contiguous()
         normal = normal.permute(0, 2, 1).contiguous()
         with ops.geometry_scope():
             return self._forward(xyz, normal, label)
 
+    @on_tensor_device
     def forward_parts(self, xyz, normal, label):
         """Same computation as forward, but the 896-channel head input is returned in its two parts instead of
         concatenated: (xyz [B,N,3], per-point channels [B,N,256], per-cloud channels [B,640] = global max pools + label
@@ -323,6 +328,7 @@ class UmbrellaSurfaceConstructor(nn.Module):
             nn.Conv2d(in_channel, in_channel, 1, bias=True),
         )
 
+    @on_tensor_device
     def forward(self, center):
         center = center.permute(0, 2, 1).contiguous()
         sign = None
@@ -338,7 +344,7 @@ class UmbrellaSurfaceConstructor(nn.Module):
         for conv, bn in ((conv0, bn1), (conv3, bn4)):
             x = F.linear(x, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
             x = ops.bn_act(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                           bn.training, momentum=bn.momentum, eps=bn.eps, slope=0.0)
+                           bn.training, momentum=ops._momentum(bn), eps=bn.eps, slope=0.0)
         x = F.linear(x, conv6.weight.view(conv6.out_channels, conv6.in_channels), conv6.bias).view(B, N, G, -1)
         if self.aggr_type == 'max':
             x = torch.max(x, 2)[0]
@@ -366,6 +372,7 @@ class PointNetFeaturePropagation(nn.Module):
         self.act = act
         self.conv = Linear(in_channel, out_channel, bn=False, act=self.act)
 
+    @on_tensor_device
     def forward(self, xyz1, xyz2, points1, points2):
         B, N, C = xyz1.shape
         S = xyz2.shape[1]

@@ -9,6 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from ._lib import on_tensor_device
 from .ops import (farthest_point_sample, index_points, knn_point, query_ball_point, query_knn_point,  # noqa: F401
                   square_distance, xyz2sphere)
 from .pointnet2_utils import Linear, LocalTrans, UmbrellaSurfaceConstructor  # noqa: F401
@@ -95,6 +96,7 @@ class SurfaceAbstraction(nn.Module):
         return sample_and_group(self.npoint, self.radius, self.nsample, center, normal, feature,
                                 return_polar=self.return_polar, return_normal=self.return_normal, cuda=self.cuda_ops)
 
+    @on_tensor_device
     def forward(self, center, normal, feature):
         new_center, new_normal, x = self._group(center, normal, feature)  # x [B,S,K,C] channel-last
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
@@ -130,6 +132,7 @@ class SurfaceAbstractionCD(SurfaceAbstraction):
             self.mlp_bns.append(nn.BatchNorm2d(out_channel))
             last_channel = out_channel
 
+    @on_tensor_device
     def forward(self, center, normal, feature):
         new_center, new_normal, x = self._group(center, normal, feature)
         loc = _conv_bn(x[..., :self.pos_channel].contiguous(), self.mlp_l0, self.bn_l0, 1.0)
@@ -157,6 +160,7 @@ class LocalMerge(nn.Module):
         self.feature_Trans = LocalTrans(in_channels, out_channels, knn, usetanh=self.usetanh, residual=self.residual)
         self.feature_Trans2 = LocalTrans(in_channels, out_channels, knn, usetanh=self.usetanh, residual=self.residual)
 
+    @on_tensor_device
     def forward(self, xyz, base_xyz, normal=None, feature=None, FPS_idx=None, xyz_flag=True):
         dist, idx = ops.geo_join(ops.geo_call(lambda: knn_point(self.knn, base_xyz, xyz)))
         if feature is None:
@@ -200,6 +204,7 @@ class KeepHighResolutionModule(nn.Module):
         self.bn = nn.BatchNorm1d(1024)
         self.lrelu = nn.LeakyReLU(negative_slope=0.2)
 
+    @on_tensor_device
     def forward(self, xyz, normal):
         xyz = xyz.permute(0, 2, 1).contiguous()
         normal = normal.permute(0, 2, 1).contiguous()

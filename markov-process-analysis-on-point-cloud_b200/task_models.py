@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from ._lib import on_tensor_device
 from .pointnet2_utils import KeepHighResolutionModulePartSeg, Linear
 from .repsurface_utils import KeepHighResolutionModule, SurfaceAbstractionCD, UmbrellaSurfaceConstructor
 
@@ -33,6 +34,7 @@ class Model(nn.Module):
         self.fc3 = nn.Linear(256, args.num_class)
         self.lrelu = nn.LeakyReLU(negative_slope=0.2)
 
+    @on_tensor_device
     def forward(self, points):
         center = points[:, :3, :]
         normal = center  # the shipped model feeds the coordinates as `normal` (:59); it is never consumed
@@ -74,6 +76,7 @@ class Model2x(nn.Module):
             nn.Linear(512, 256), nn.BatchNorm1d(256), nn.ReLU(True), nn.Dropout(0.4),
             nn.Linear(256, args.num_class))
 
+    @on_tensor_device
     def forward(self, points):
         center = points[:, :3, :]
         normal = self.surface_constructor(center)
@@ -102,6 +105,7 @@ class get_model(nn.Module):
         self.drop1 = nn.Dropout(0.5)
         self.drop2 = nn.Dropout(0.5)
 
+    @on_tensor_device
     def forward(self, xyz, cls_label):
         if xyz.is_cuda and ops.split_supported(xyz.shape[2], 256, self.conv8.linear.out_features):
             # 640 of conv8's 896 input channels are constant over a cloud's points (global pools, label embedding):

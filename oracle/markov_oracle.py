@@ -197,8 +197,9 @@ class Ctx:
     """Evaluation context: train/eval, which kNN implementation ranks neighbours, and the index tape
     (every FPS / kNN result in call order) used for index injection into the CUDA path."""
 
-    def __init__(self, train=False, knn_impl="c", fps_starts=None):
+    def __init__(self, train=False, knn_impl="c", fps_starts=None, eval_blocks=()):
         self.train = train
+        self.eval_blocks = tuple(eval_blocks)  # Linear blocks (key prefixes) whose BatchNorm uses running statistics
         self.knn_impl = knn_impl
         self.fps_starts = list(fps_starts) if fps_starts is not None else None
         self.tape = []
@@ -230,10 +231,11 @@ def linear_block(P, pre, x, ctx, act=True):
     y = F.linear(x, P[pre + "linear.weight"], P[pre + "linear.bias"])
     shp = y.shape
     y2 = y.reshape(-1, shp[-1])
+    train = ctx.train and pre not in ctx.eval_blocks
     y2 = F.batch_norm(y2, P[pre + "norm2.running_mean"], P[pre + "norm2.running_var"],
-                      P[pre + "norm2.weight"], P[pre + "norm2.bias"], training=ctx.train,
+                      P[pre + "norm2.weight"], P[pre + "norm2.bias"], training=train,
                       momentum=0.1, eps=1e-5)
-    if ctx.train and (pre + "norm2.num_batches_tracked") in P:
+    if train and (pre + "norm2.num_batches_tracked") in P:
         P[pre + "norm2.num_batches_tracked"] += 1
     y = y2.reshape(shp)
     if act:

@@ -46,33 +46,55 @@ ORC_API int orc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, in
     for (int64_t b = 0; b < B; ++b) {
         const float* p = xyz + b * N * C;
         float* mind = (float*)malloc(sizeof(float) * (size_t)N);
-        for (int64_t n = 0; n < N; ++n) mind[n] = 1e10f;
+        float* pt = (float*)malloc(sizeof(float) * (size_t)(N * C)); /* channel-major copy: unit-stride inner loops */
+        for (int64_t n = 0; n < N; ++n) {
+            mind[n] = 1e10f;
+            for (int64_t k = 0; k < C; ++k) pt[k * N + n] = p[n * C + k];
+        }
+        float* acc = (float*)malloc(sizeof(float) * (size_t)N);
         int64_t far = start[b];
         for (int64_t i = 0; i < npoint; ++i) {
             out[b * npoint + i] = far;
             const float* c = p + far * C;
+            /* the per-point arithmetic is the same scalar sequence as before (sub, mul, add: no fma), evaluated for
+             * all points channel by channel so that the compiler can use SIMD lanes: lane-wise IEEE ops, same bits */
+            {
+                const float c0 = c[0];
+                const float* x = pt;
+#pragma omp simd
+                for (int64_t n = 0; n < N; ++n) {
+                    float d0 = x[n] - c0;
+                    acc[n] = d0 * d0;
+                }
+            }
+            for (int64_t k = 1; k < C; ++k) {
+                const float ck = c[k];
+                const float* x = pt + k * N;
+#pragma omp simd
+                for (int64_t n = 0; n < N; ++n) {
+                    float dk = x[n] - ck;
+                    acc[n] = acc[n] + dk * dk; /* -ffp-contract=off: mul then add, two roundings */
+                }
+            }
             float best = -INFINITY;
-            int64_t besti = 0;
+#pragma omp simd reduction(max : best)
             for (int64_t n = 0; n < N; ++n) {
-                const float* q = p + n * C;
-                float d0 = q[0] - c[0];
-                float acc = d0 * d0;
-                for (int64_t k = 1; k < C; ++k) {
-                    float dk = q[k] - c[k];
-                    acc = acc + dk * dk; /* -ffp-contract=off: mul then add, two roundings */
-                }
                 float m = mind[n];
-                if (acc < m) {
-                    m = acc;
-                    mind[n] = m;
-                }
-                if (m > best) { /* strict: lowest index wins ties */
-                    best = m;
+                m = acc[n] < m ? acc[n] : m;
+                mind[n] = m;
+                best = m > best ? m : best;
+            }
+            int64_t besti = 0;
+            for (int64_t n = 0; n < N; ++n) { /* first (lowest) index attaining the maximum: torch.max's tie rule */
+                if (mind[n] == best) {
                     besti = n;
+                    break;
                 }
             }
             far = besti;
         }
+        free(acc);
+        free(pt);
         free(mind);
     }
     return 0;
@@ -106,12 +128,26 @@ static inline float sqdist_expanded(const float* q, float qn, const float* r, fl
  * idx_out [B,S,K] int64.  torch.topk's order among exactly equal distances is implementation
  * defined; this restatement (and the CUDA kernel) fix it to ascending index.  K <= N required.
  * ---------------------------------------------------------------------------------------------- */
+#define ORC_KNN_LANES 32
 ORC_API int orc_knn_f32(const float* ref, const float* qry, float* dist_out, int64_t* idx_out,
                         int64_t B, int64_t N, int64_t S, int64_t C, int64_t K) {
     if (K <= 0 || K > N || C <= 0) return 1;
-    float* rnorm = (float*)malloc(sizeof(float) * (size_t)(B * N));
+    /* channel-major, lane-padded copy of the reference set, so that ORC_KNN_LANES pairs run their fma chains side
+     * by side in SIMD lanes: every pair still sees exactly the scalar sequence of sqdist_expanded (same bits) */
+    const int64_t Np = (N + ORC_KNN_LANES - 1) / ORC_KNN_LANES * ORC_KNN_LANES;
+    float* rnorm = (float*)malloc(sizeof(float) * (size_t)(B * Np));
+    float* rt = (float*)malloc(sizeof(float) * (size_t)(B * C * Np));
 #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < B * N; ++i) rnorm[i] = sqnorm_seq(ref + i * C, C);
+    for (int64_t i = 0; i < B * Np; ++i) {
+        int64_t b = i / Np, n = i % Np;
+        if (n < N) {
+            rnorm[i] = sqnorm_seq(ref + (b * N + n) * C, C);
+            for (int64_t k = 0; k < C; ++k) rt[(b * C + k) * Np + n] = ref[(b * N + n) * C + k];
+        } else {
+            rnorm[i] = 0.0f;
+            for (int64_t k = 0; k < C; ++k) rt[(b * C + k) * Np + n] = 0.0f;
+        }
+    }
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t bs = 0; bs < B * S; ++bs) {
         int64_t b = bs / S;
@@ -120,20 +156,41 @@ ORC_API int orc_knn_f32(const float* ref, const float* qry, float* dist_out, int
         float* bd = dist_out + bs * K;
         int64_t* bi = idx_out + bs * K;
         int64_t cnt = 0;
-        for (int64_t n = 0; n < N; ++n) {
-            float d = sqdist_expanded(q, qn, ref + (b * N + n) * C, rnorm[b * N + n], C);
-            if (cnt == K && !(d < bd[K - 1])) continue;
-            int64_t pos = cnt < K ? cnt : K - 1;
-            while (pos > 0 && d < bd[pos - 1]) { /* strict <: equal distances keep ascending index */
-                bd[pos] = bd[pos - 1];
-                bi[pos] = bi[pos - 1];
-                --pos;
+        const float* rtb = rt + b * C * Np;
+        const float* rnb = rnorm + b * Np;
+        for (int64_t n0 = 0; n0 < N; n0 += ORC_KNN_LANES) {
+            float dot[ORC_KNN_LANES], dd[ORC_KNN_LANES];
+#pragma omp simd
+            for (int j = 0; j < ORC_KNN_LANES; ++j) dot[j] = 0.0f;
+            for (int64_t k = 0; k < C; ++k) {
+                const float qk = q[k];
+                const float* col = rtb + k * Np + n0;
+#pragma omp simd
+                for (int j = 0; j < ORC_KNN_LANES; ++j) dot[j] = fmaf(qk, col[j], dot[j]);
             }
-            bd[pos] = d;
-            bi[pos] = n;
-            if (cnt < K) ++cnt;
+#pragma omp simd
+            for (int j = 0; j < ORC_KNN_LANES; ++j) {
+                float d = -2.0f * dot[j];
+                d = d + qn;
+                dd[j] = d + rnb[n0 + j];
+            }
+            const int64_t lim = N - n0 < ORC_KNN_LANES ? N - n0 : ORC_KNN_LANES;
+            for (int64_t j = 0; j < lim; ++j) {
+                const float d = dd[j];
+                if (cnt == K && !(d < bd[K - 1])) continue;
+                int64_t pos = cnt < K ? cnt : K - 1;
+                while (pos > 0 && d < bd[pos - 1]) { /* strict <: equal distances keep ascending index */
+                    bd[pos] = bd[pos - 1];
+                    bi[pos] = bi[pos - 1];
+                    --pos;
+                }
+                bd[pos] = d;
+                bi[pos] = n0 + j;
+                if (cnt < K) ++cnt;
+            }
         }
     }
+    free(rt);
     free(rnorm);
     return 0;
 }

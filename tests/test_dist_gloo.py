@@ -24,8 +24,18 @@ def _worker(rank, world, port, out_dir):
     lo, hi = mpc.dist.shard_batch(8, rank, world)
     lin(data[lo:hi]).pow(2).sum().backward()
     local = [p.grad.clone() for p in lin.parameters()]
+    # flat-bucket form of the exchange, on clones of the same gradients
+    twin = torch.nn.Linear(5, 3)
+    twin_unused = torch.nn.Linear(2, 2)
+    for p, g in zip(twin.parameters(), local):
+        p.grad = g.clone()
+    bucket = mpc.dist.GradBucket(list(twin.parameters()) + list(twin_unused.parameters()))
+    bucket.exchange(world)
     n = mpc.dist.allreduce_mean_grads(list(lin.parameters()) + list(unused.parameters()), world)
-    torch.save({"n": n, "local": local, "avg": [p.grad.clone() for p in lin.parameters()], "shard": (lo, hi)},
+    torch.save({"n": n, "local": local, "avg": [p.grad.clone() for p in lin.parameters()], "shard": (lo, hi),
+                "bucket": [p.grad.clone() for p in twin.parameters()], "bucket_numel": bucket.numel,
+                "bucket_views": all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views)),
+                "bucket_skipped_unused": all(p.grad is None for p in twin_unused.parameters())},
                os.path.join(out_dir, "r%d.pt" % rank))
     dist.destroy_process_group()
 
@@ -49,3 +59,8 @@ def test_gradient_exchange_gloo_world2(tmp_path):
     for a0, a1, l0, l1 in zip(r0["avg"], r1["avg"], r0["local"], r1["local"]):
         assert torch.equal(a0, a1)  # every rank ends with the same averaged gradient ...
         torch.testing.assert_close(a0, (l0 + l1) / 2)  # ... the mean of the per-shard gradients
+    # the flat bucket gives the same averaged gradients, as views of ONE buffer, unused parameters left out
+    for r in (r0, r1):
+        assert r["bucket_numel"] == 5 * 3 + 3 and r["bucket_views"] and r["bucket_skipped_unused"]
+        for b, a in zip(r["bucket"], r0["avg"]):
+            torch.testing.assert_close(b, a)

@@ -158,21 +158,21 @@ class Workload:
             self.kind, self.cfg_index = "seg", 1
             self.title = ("ShapeNetPart-shaped part segmentation, 32 x 2048 points per GPU, full Markov encoder + "
                           "transition decoder, fwd+bwd (BASELINE configs[1])")
-            self.cpu_B, self.cpu_steps = 8, 2
+            self.cpu_B, self.cpu_steps = 16, 2
         elif key == "cls1024_train":
             self.B, self.N, self.classes, self.scaling = 32, 1024, 40, "weak"
             self.kind, self.cfg_index = "cls", 4
             self.adam = True
             self.title = ("data-parallel training step of the ModelNet40-shaped classifier, 32 x 1024 points per GPU "
                           "(256 at 8 GPUs), fwd + smoothed loss + bwd + gradient all-reduce + Adam (BASELINE configs[4])")
-            self.cpu_B, self.cpu_steps = 16, 2
+            self.cpu_B, self.cpu_steps = 32, 3
         elif key == "cls_fwd":
             self.B, self.N, self.classes, self.scaling = 16, 1024, 40, "weak"
             self.kind, self.cfg_index = "cls", 0
             self.train = False
             self.title = ("ModelNet40-shaped classification forward, batch 16 x 1024 points per GPU, eval() "
                           "(BASELINE configs[0])")
-            self.cpu_B, self.cpu_steps = 16, 3
+            self.cpu_B, self.cpu_steps = 16, 5
         else:
             raise SystemExit("bench.py: unknown workload %r" % key)
         self.total_clouds = self.B * world
@@ -288,7 +288,8 @@ def cpu_reference_run(wl, steps, warmup):
 
 def reference_record(wl, steps, warmup, args):
     r = cpu_reference_run(wl, steps, warmup)
-    return {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+    return {"impl": "reference", "metric": METRIC if wl.key == HEADLINE else "point clouds/s (%s)" % wl.key,
+            "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -410,8 +411,9 @@ class GraphedStep:
 GEMM_ENTRIES = ("mpc_linear_fwd_f32", "mpc_linear_dgrad_f32", "mpc_linear_wgrad_f32")
 # C-ABI entry point -> the CUDA kernel that does its work (the three GEMM entry points share one kernel)
 KERNEL_OF = {n: "linear_3xtf32_kernel" for n in GEMM_ENTRIES}
-KERNEL_OF.update({"mpc_knn_f32": "knn kernels (knn3 / knn_tiled / knn64 / knn_tc by shape)", "mpc_fps_f32": "fps kernels "
-                  "(cta / cluster / grid by size)"})
+KERNEL_OF.update({"mpc_knn_f32": "knn3 / knn_tiled / knn64 kernels (FP32 SIMT, by shape)",
+                  "mpc_knn_tc_f32": "knn_tc_kernel (tcgen05 filter + exact refinement)",
+                  "mpc_fps_f32": "fps kernels (cta / cluster / grid by size)"})
 
 
 def kernel_table(rows):
@@ -481,6 +483,13 @@ def knn_flops(args):
     """mpc_knn_f32(ref, qry, dist, idx, B, N, S, C, L): B*S*N*(2C+3) flop."""
     B, N, S, C = (a.value for a in args[4:8])
     return B * S * N * (2 * C + 3)
+
+
+def knn_tc_flops(args):
+    """mpc_knn_tc_f32(ref, qry, dist, idx, ws, ws_bytes, B, N, S, C, K): (brute-force flops B*S*N*(2C+3) of the
+    reference algorithm, tensor-core flops actually issued = 3 split terms x 2*B*S*N*C)."""
+    B, N, S, C = (a.value for a in args[6:10])
+    return B * S * N * (2 * C + 3), 3 * 2 * B * S * N * C
 
 
 def measure_roofline(wl, step, mpc, device, inputs, starts_fn, flush, full, dev_ms_per_step):
@@ -553,6 +562,7 @@ def measure_roofline(wl, step, mpc, device, inputs, starts_fn, flush, full, dev_
             ms += sum(a.elapsed_time(b) for v in recs.values() for a, b, _ in v)
             by = sum(c for v in recs.values() for _, _, c in v)
             flops = sum(knn_flops(a) for a in argl.get("mpc_knn_f32", []))
+            tc = [knn_tc_flops(a) for a in argl.get("mpc_knn_tc_f32", [])]
         ms /= reps
     finally:
         ops._STREAMS_ENABLED = streams_were
@@ -561,8 +571,22 @@ def measure_roofline(wl, step, mpc, device, inputs, starts_fn, flush, full, dev_
     common = {"kernel": name, "entry_points": entries, "launches_per_step": n, "avg_launch_us": 1e3 * ms / max(n, 1),
               "kernel_ms_per_step": ms, "share_of_step": ms / dev_ms_per_step, "how": how,
               "traffic": committed_traffic(name, wl.key)}
+    if entries == ["mpc_knn_tc_f32"]:
+        issued = sum(t[1] for t in tc)
+        tf32_peak = pk["bf16_tflops"] / 2
+        achieved = issued / 1e12 / (ms / 1e3)
+        rec = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+               "frac": achieved / tf32_peak, "algo_flops_per_launch": issued / max(n, 1),
+               "peak_kind": pk_kind + " bf16 dense rate / 2 (kind::tf32 runs at half the bf16 rate)",
+               "reference_algorithm_tflops": sum(t[0] for t in tc) / 1e12 / (ms / 1e3),
+               "note": "issued tensor-core flops = 3 split terms x 2*B*S*N*C (3xTF32: fp32-level products so that the "
+                       "exact refinement only has to look at ~K candidates); the launch also contains the operand "
+                       "split pre-pass, the FP32 refinement and the exact fallback for near-tie queries; "
+                       "reference_algorithm_tflops counts the reference's brute-force flops B*S*N*(2C+3) instead"}
+        rec.update(common)
+        return rec
     if entries == ["mpc_knn_f32"]:
-        tc = os.environ.get("MPC_KNN_TC", "1") == "1" and getattr(ops, "knn_tc_available", lambda: False)()
+        tc = False
         simt_peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         achieved = flops / 1e12 / (ms / 1e3)
         rec = {"bound": "fp32-simt", "achieved": achieved, "peak": simt_peak, "unit": "TFLOP/s",

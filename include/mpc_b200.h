@@ -73,6 +73,27 @@ int mpc_knn_f32(const float* ref, const float* qry, float* dist_out, int64_t* id
                 int64_t N, int64_t S, int64_t C, int64_t K, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * k nearest neighbours in feature space with the distance GEMM on the tensor cores.  Same operands, same outputs
+ * and the SAME bit-exact contract as mpc_knn_f32 (it replaces the same reference lines, R/modules/pointnet2_utils.py:
+ * 190-222, whose square_distance is a torch.matmul): filter-and-refine.  The 128 x 128 dot products of a (query tile,
+ * reference tile) pair are tcgen05 kind::tf32 MMAs with the 3xTF32 operand split (fp32-level products, fp32
+ * accumulation in TMEM, operands by TMA); the epilogue thread of a query keeps its 16 best approximate distances;
+ * every true neighbour provably lies within 2 eps of the K-th best approximate distance (eps = 2^-14 (|q|^2 +
+ * max|r|^2)), so when the 16th entry is beyond that bound the candidates' EXACT distances (the contract's FP32 fma
+ * chain) are evaluated and ranked by (distance, index); queries with more near-ties than the list holds (identical
+ * feature vectors after a Markov transition) go through the exact brute-force kernel.  Results are therefore
+ * bit-identical to mpc_knn_f32 for any input.
+ *   C == 64, K == 8, N >= 16, operands 16-byte aligned; else MPC_ERR_UNSUPPORTED (callers fall back to mpc_knn_f32).
+ *   workspace: mpc_knn_tc_workspace_bytes(...) bytes, 256-byte aligned, caller-owned, no initialisation needed.
+ *   After the call its first words hold diagnostics: uint32[B] bit patterns of max|r|^2 per cloud, int32[B] queries
+ *   per cloud that took the exact fallback, then one uint32 = bit pattern of the worst observed
+ *   |approximate - exact| / (|q|^2 + max|r|^2) over all refined candidates (to be compared with eps' 2^-14).
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_knn_tc_workspace_bytes(int64_t B, int64_t N, int64_t S, int64_t C, int64_t K, int64_t* bytes_out);
+int mpc_knn_tc_f32(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, void* workspace,
+                   int64_t workspace_bytes, int64_t B, int64_t N, int64_t S, int64_t C, int64_t K, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Ball query.  Replaces query_ball_point, R/modules/pointnet2_utils.py:112-134.
  *   xyz [B,N,C], new_xyz [B,S,C], idx_out [B,S,nsample] i64; r2 = radius^2 rounded to f32.
  * First `nsample` indices n (ascending) with NOT(d > r2), d as in mpc_knn_f32; padded with the first hit;

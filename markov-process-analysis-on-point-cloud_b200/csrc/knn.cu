@@ -481,7 +481,13 @@ constexpr int KT_DH = 32;   // reference points per selection pass: the distance
 template <int K>
 __global__ void __launch_bounds__(KT_THREADS, 3)
 knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
-                 int64_t* __restrict__ idx_out, int N, int S, int C) {
+                 int64_t* __restrict__ idx_out, int N, int S, int C, const int* __restrict__ qlist,
+                 const int* __restrict__ qcount) {
+    // Indirect mode (qlist != null): the CTA grid covers all S query slots of a cloud, but only the first qcount[b]
+    // slots are live and slot i stands for query row qlist[b*S + i] (the rows mpc_knn_tc_f32's filter could not decide);
+    // CTAs beyond the live range leave at once.
+    const int S_live = qcount ? qcount[blockIdx.y] : S;
+    if ((int)(blockIdx.x * KT_Q) >= S_live) return;
     extern __shared__ __align__(16) float sm[];
     float* qt = sm;                              // [C][KT_Q]   queries, transposed
     float* rt = qt + (size_t)C * KT_Q;           // [KT_CK][KT_R] reference chunk, transposed
@@ -502,7 +508,10 @@ knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, f
     for (int i = tid; i < KT_Q * (C / 4); i += KT_THREADS) {
         const int c4 = (i % (C / 4)) * 4, q = i / (C / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q0 + q < S) v = __ldg(reinterpret_cast<const float4*>(qb + (size_t)(q0 + q) * C + c4));
+        if (q0 + q < S_live) {
+            const int qrow = qlist ? qlist[(size_t)b * S + q0 + q] : q0 + q;
+            v = __ldg(reinterpret_cast<const float4*>(qb + (size_t)qrow * C + c4));
+        }
         const int col = swz(c4, q, KT_Q / 4);
         qt[(c4 + 0) * KT_Q + col] = v.x;
         qt[(c4 + 1) * KT_Q + col] = v.y;
@@ -518,8 +527,8 @@ knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, f
         }
         qn_s[tid] = a;
     }
-    const int s = q0 + tid;
-    const bool active = s < S;
+    const bool active = q0 + tid < S_live;
+    const int s = !active ? 0 : (qlist ? qlist[(size_t)b * S + q0 + tid] : q0 + tid);
     float bd[K];
     int bi[K];
 #pragma unroll
@@ -781,7 +790,7 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
         auto kern = knn_tiled_kernel<(K <= 16 ? K : 16)>;
         MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)ceil_div(S, KT_Q), (unsigned)B);
-        kern<<<grid, KT_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C);
+        kern<<<grid, KT_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C, nullptr, nullptr);
         MPC_LAUNCH_CHECK();
         return MPC_OK;
     }
@@ -805,6 +814,19 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
     if (smem > 36 * 1024) MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(S, KNNG_THREADS), (unsigned)B);
     kern<<<grid, KNNG_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C);
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+// Exact search for an indirect list of queries (see knn_tiled_kernel): the fallback pass of mpc_knn_tc_f32.
+int launch_knn_tiled_indirect8(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, const int* qlist,
+                               const int* qcount, int B, int N, int S, int C, cudaStream_t st) {
+    if (C % 64 != 0 || C > 256) return MPC_ERR_UNSUPPORTED;
+    const size_t smem = ((size_t)C * KT_Q + KT_CK * KT_R + KT_Q * KT_DH + KT_Q + KT_R) * sizeof(float);
+    auto kern = knn_tiled_kernel<8>;
+    MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(S, KT_Q), (unsigned)B);
+    kern<<<grid, KT_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C, qlist, qcount);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

@@ -1,0 +1,480 @@
+// Feature-space k nearest neighbours with the distance GEMM on the 5th-generation tensor cores (tcgen05 + TMEM +
+// TMA), bit-exact with the FP32 brute-force contract of mpc_knn_f32.  See include/mpc_b200.h (mpc_knn_tc_f32).
+//
+// The reference computes -2 * (queries x reference^T) with torch.matmul (pointnet2_utils.py:204-208): the distance
+// matrix IS a dense contraction, 131 flop per pair at C = 64, and on the 24 000-point blocks it is 80 % of the
+// training step when evaluated on the FP32 SIMT pipe (18 TFLOP/s of a 74 TFLOP/s peak).  Indices must nevertheless
+// come out exactly as the oracle's FP32 fma chain ranks them.  Filter-and-refine:
+//
+//   1. filter (tensor cores).  Per CTA 128 queries stay resident in shared memory; the reference set streams through
+//      in tiles of 128 points (TMA, 128B swizzle); the 128 x 128 dot products of a tile are three kind::tf32 MMAs per
+//      K step -- q_lo r_hi + q_hi r_lo + q_hi r_hi, hi = the top 19 bits (what the tensor core reads of an fp32
+//      word), lo = x - hi precomputed once per call -- i.e. ~fp32-accurate products, fp32 accumulation in TMEM.
+//      Epilogue thread = query (tcgen05.ld 32x32b gives every lane its own row): approximate distance
+//      d~ = |r|^2 - 2 dot~, compared against the thread's 16th best; a sorted list of the 16 best (d~, index) is kept in
+//      registers.  Two TMEM accumulator stages: the selection of tile j overlaps the MMAs of tile j + 1.
+//   2. refine (FP32 SIMT, same kernel).  |d~ - d| <= eps for every pair, eps = 2^-14 (|q|^2 + max|r|^2) (rigorous
+//      for an fma chain of 64 terms, the 3xTF32 split and <= 1 ulp per tensor-core accumulation step; the measured
+//      worst deviation is recorded in the workspace and reported by the tests: ~1e-7).  With T = the K-th smallest d~,
+//      every true neighbour has d~ <= T + 2 eps.  If the list's 16th entry lies beyond that bound the list provably
+//      contains all of them: their EXACT distances (the oracle's arithmetic: fma chain over c from 0, sequential
+//      norms, ((-2 dot) + |q|^2) + |r|^2) are evaluated and the K best by (distance, index) are written.
+//   3. fallback.  Otherwise (more than 16 - K near-ties: after a Markov transition every unreached point carries the
+//      same feature vector) the query is appended to a per-cloud list and the exact brute-force kernel (knn.cu) runs
+//      on the listed queries only.
+//
+// Warp roles (192 threads, one CTA per SM by shared memory): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2-5 selection / refinement (TMEM lane quadrant = warp % 4).
+#include "tc_common.cuh"
+
+namespace mpc {
+namespace knntc {
+using namespace tc;
+
+constexpr int BM = 128;                          // queries per CTA
+constexpr int BN = 128;                          // reference points per tile
+constexpr int CH = 64;                           // channels
+constexpr int KCH = CH / BLOCK_K;                // K chunks of 32 channels (one 128-byte swizzle row each)
+constexpr int CHUNK_BYTES = 128 * BLOCK_K * 4;   // 128 rows x 128 B
+constexpr int A_BYTES = 2 * KCH * CHUNK_BYTES;   // hi + lo of the query tile: 64 KB
+constexpr int B_STAGE_BYTES = 2 * KCH * CHUNK_BYTES;  // hi + lo of one reference tile: 64 KB
+constexpr int STAGES = 2;
+constexpr int LIST = 16;                         // candidates kept per query
+constexpr int DROW = 36;                         // floats per row of the per-thread distance scratch (16 B aligned)
+constexpr int THREADS = 192;
+constexpr int DYN_SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 1024;
+
+struct Params {
+    const float* ref;     // [B,N,64]
+    const float* qry;     // [B,S,64]
+    const float* rn;      // [B,Npad] exact |r|^2, +inf beyond N
+    const float* qn;      // exact |q|^2, row b*qn_stride + s
+    const unsigned* rnmax;  // [B] max |r|^2 of the cloud (float bits)
+    unsigned* maxdev;     // worst observed |(d~ + |q|^2) - d| / (|q|^2 + max|r|^2) (float bits), diagnostic
+    int* qcount;          // [B] queries handed to the exact fallback
+    int* qlist;           // [B,S]
+    float* dist_out;      // [B,S,K] or null
+    int64_t* idx_out;     // [B,S,K]
+    int N, S, Npad, qn_stride, ntiles;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// ascending list, strict <: candidates arrive in ascending index order, so equal keys keep the lower index first
+__device__ __forceinline__ void list_insert(float (&ld)[LIST], int (&li)[LIST], float d, int n) {
+    ld[LIST - 1] = d;
+    li[LIST - 1] = n;
+#pragma unroll
+    for (int p = LIST - 1; p > 0; --p) {
+        if (ld[p] < ld[p - 1]) {
+            const float td = ld[p];
+            ld[p] = ld[p - 1];
+            ld[p - 1] = td;
+            const int ti = li[p];
+            li[p] = li[p - 1];
+            li[p - 1] = ti;
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+              const __grid_constant__ CUtensorMap map_rhi, const __grid_constant__ CUtensorMap map_rlo, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_tmem_full[2], bar_tmem_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float rn_s[4][2][BN];       // [selection warp][buffer][column]: |r|^2 of a tile
+    __shared__ __align__(16) float drow[BM * DROW];      // per-thread scratch: the 32 distances of one TMEM slab
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a_s = smem;                 // [hi k0][hi k1][lo k0][lo k1], 16 KB each
+    uint8_t* b_s = smem + A_BYTES;       // STAGES x the same layout
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * BM;
+    const int ntiles = p.ntiles;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_a, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tmem_full[a], 1);
+            mbar_init(&bar_tmem_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qlo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rlo) : "memory");
+    }
+    if (warp == 1) {  // TMEM: 2 accumulator stages x 128 fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int qrow = b * p.S + q0;  // rows past the cloud / the tensor are masked by the consumers / zero-filled
+            mbar_arrive_expect_tx(&bar_a, A_BYTES);
+            for (int kc = 0; kc < KCH; ++kc) {
+                tma_load_2d(&map_qhi, &bar_a, a_s + kc * CHUNK_BYTES, kc * BLOCK_K, qrow);
+                tma_load_2d(&map_qlo, &bar_a, a_s + (KCH + kc) * CHUNK_BYTES, kc * BLOCK_K, qrow);
+            }
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                uint8_t* st = b_s + (size_t)s * B_STAGE_BYTES;
+                const int rrow = b * p.N + j * BN;
+                mbar_arrive_expect_tx(&bar_full[s], B_STAGE_BYTES);
+                for (int kc = 0; kc < KCH; ++kc) {
+                    tma_load_2d(&map_rhi, &bar_full[s], st + kc * CHUNK_BYTES, kc * BLOCK_K, rrow);
+                    tma_load_2d(&map_rlo, &bar_full[s], st + (KCH + kc) * CHUNK_BYTES, kc * BLOCK_K, rrow);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 (cute::UMMA::InstrDescriptor)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            mbar_wait(&bar_a, 0);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(a_s);
+            for (int j = 0; j < ntiles; ++j) {
+                const int as = j & 1;
+                const uint32_t aph = (j >> 1) & 1;
+                mbar_wait(&bar_tmem_empty[as], aph ^ 1);
+                const int s = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                mbar_wait(&bar_full[s], ph);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                const uint32_t b0 = smem_u32(b_s + (size_t)s * B_STAGE_BYTES);
+#pragma unroll
+                for (int kc = 0; kc < KCH; ++kc) {
+                    const uint64_t a_hi = make_desc(a0 + kc * CHUNK_BYTES), a_lo = make_desc(a0 + (KCH + kc) * CHUNK_BYTES);
+                    const uint64_t b_hi = make_desc(b0 + kc * CHUNK_BYTES), b_lo = make_desc(b0 + (KCH + kc) * CHUNK_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                        const uint64_t adv = (uint64_t)((UMMA_K * 4) >> 4) * kk;  // +32 B inside the swizzle row
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kc != 0 || kk != 0) ? 1u : 0u);
+                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                    }
+                }
+                umma_commit(&bar_empty[s]);        // the stage may be refilled once these MMAs have read it
+                umma_commit(&bar_tmem_full[as]);   // accumulator complete
+            }
+        }
+    } else {
+        // ===== selection + refinement: thread = query =====
+        const int ew = warp - 2;          // private |r|^2 staging slab
+        const int quad = warp & 3;        // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane; // query row inside the tile = TMEM lane
+        const int s_idx = q0 + row;
+        const bool active = s_idx < p.S;
+        const float* rnb = p.rn + (size_t)b * p.Npad;
+        float* my_d = drow + row * DROW;
+        float ld[LIST];
+        int li[LIST];
+#pragma unroll
+        for (int e = 0; e < LIST; ++e) {
+            ld[e] = __int_as_float(0x7f800000);
+            li[e] = 0;
+        }
+        float thr = __int_as_float(0x7f800000);
+        float4 pre = __ldg(reinterpret_cast<const float4*>(rnb) + lane);  // |r|^2 of tile 0, 4 columns per lane
+        for (int j = 0; j < ntiles; ++j) {
+            const int as = j & 1;
+            const uint32_t aph = (j >> 1) & 1;
+            float* rns = rn_s[ew][j & 1];
+            __syncwarp();  // every lane is done with this buffer (tile j - 2)
+            reinterpret_cast<float4*>(rns)[lane] = pre;
+            __syncwarp();
+            if (j + 1 < ntiles) pre = __ldg(reinterpret_cast<const float4*>(rnb + (size_t)(j + 1) * BN) + lane);
+            mbar_wait(&bar_tmem_full[as], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quad * 32) << 16);
+            const int n0 = j * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                unsigned mask = 0u;
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(rns + c0 + i4 * 4);  // broadcast
+                    float4 d4;
+                    d4.x = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 0]), r4.x);
+                    d4.y = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 1]), r4.y);
+                    d4.z = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 2]), r4.z);
+                    d4.w = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 3]), r4.w);
+                    mask |= (d4.x < thr ? 1u : 0u) << (i4 * 4 + 0);
+                    mask |= (d4.y < thr ? 1u : 0u) << (i4 * 4 + 1);
+                    mask |= (d4.z < thr ? 1u : 0u) << (i4 * 4 + 2);
+                    mask |= (d4.w < thr ? 1u : 0u) << (i4 * 4 + 3);
+                    *reinterpret_cast<float4*>(my_d + i4 * 4) = d4;  // own row: read back by this thread only
+                }
+                while (mask) {  // ascending column = ascending reference index
+                    const int i = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float d = my_d[i];
+                    if (d < thr) {
+                        list_insert(ld, li, d, n0 + c0 + i);
+                        thr = ld[LIST - 1];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_tmem_empty[as]);
+        }
+        // ---- refinement
+        const float qn = active ? __ldg(p.qn + (size_t)b * p.qn_stride + s_idx) : 0.f;
+        const float scale = qn + __uint_as_float(__ldg(p.rnmax + b));
+        const float eps = scale * 6.103515625e-05f;  // 2^-14
+        const float bound = ld[K - 1] + 2.5f * eps;  // (2 eps, and the rounding of this very sum)
+        const bool overflow = !(ld[LIST - 1] > bound);
+        float dev = 0.f;
+        if (active && overflow) {
+            const int pos = atomicAdd(p.qcount + b, 1);
+            p.qlist[(size_t)b * p.S + pos] = s_idx;
+        } else if (active) {
+            const float* q = p.qry + ((size_t)b * p.S + s_idx) * CH;
+            const float* rb = p.ref + (size_t)b * p.N * CH;
+            float dot[LIST];
+#pragma unroll
+            for (int e = 0; e < LIST; ++e) dot[e] = 0.f;
+            for (int c4 = 0; c4 < CH / 4; ++c4) {
+                const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + c4);
+#pragma unroll
+                for (int e = 0; e < LIST; ++e) {
+                    if (ld[e] <= bound) {  // (the list is sorted: a prefix)
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rb + (size_t)li[e] * CH) + c4);
+                        dot[e] = __fmaf_rn(qv.x, rv.x, dot[e]);
+                        dot[e] = __fmaf_rn(qv.y, rv.y, dot[e]);
+                        dot[e] = __fmaf_rn(qv.z, rv.z, dot[e]);
+                        dot[e] = __fmaf_rn(qv.w, rv.w, dot[e]);
+                    }
+                }
+            }
+            float bd[K];
+            int bi[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                bd[k] = __int_as_float(0x7f800000);
+                bi[k] = 0x7fffffff;
+            }
+#pragma unroll
+            for (int e = 0; e < LIST; ++e) {
+                if (ld[e] <= bound) {
+                    const float d = sqdist_from_dot(dot[e], qn, __ldg(rnb + li[e]));
+                    dev = fmaxf(dev, fabsf((ld[e] + qn) - d));
+                    const int n = li[e];
+                    if (d < bd[K - 1] || (d == bd[K - 1] && n < bi[K - 1])) {
+                        bd[K - 1] = d;
+                        bi[K - 1] = n;
+#pragma unroll
+                        for (int q2 = K - 1; q2 > 0; --q2) {
+                            if (bd[q2] < bd[q2 - 1] || (bd[q2] == bd[q2 - 1] && bi[q2] < bi[q2 - 1])) {
+                                const float td = bd[q2];
+                                bd[q2] = bd[q2 - 1];
+                                bd[q2 - 1] = td;
+                                const int ti = bi[q2];
+                                bi[q2] = bi[q2 - 1];
+                                bi[q2 - 1] = ti;
+                            }
+                        }
+                    }
+                }
+            }
+            const size_t o = ((size_t)b * p.S + s_idx) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (p.dist_out) p.dist_out[o + k] = bd[k];
+                p.idx_out[o + k] = bi[k];
+            }
+            dev = scale > 0.f ? dev / scale : 0.f;
+        }
+        dev = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(dev)));  // non-negative floats order as uints
+        if (lane == 0 && dev > 0.f) atomicMax(p.maxdev, __float_as_uint(dev));
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+// lo = x - trunc_tf32(x) and the exact sequential squared norm of every row; thread = row.  `npad` > n: the norm
+// array is [B][npad] and the padding gets +inf (such a column can never pass a threshold).
+__global__ void __launch_bounds__(128)
+knn_tc_prep_kernel(const float* __restrict__ x, float* __restrict__ lo, float* __restrict__ norm, unsigned* __restrict__ nmax,
+                   int B, int n, int npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= npad) return;
+    float acc = __int_as_float(0x7f800000);
+    if (i < n) {
+        const float4* src = reinterpret_cast<const float4*>(x + ((size_t)b * n + i) * CH);
+        float4* dst = reinterpret_cast<float4*>(lo + ((size_t)b * n + i) * CH);
+#pragma unroll 4
+        for (int c4 = 0; c4 < CH / 4; ++c4) {
+            const float4 v = __ldg(src + c4);
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & TF32_MASK);
+            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & TF32_MASK);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & TF32_MASK);
+            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & TF32_MASK);
+            dst[c4] = l;
+            if (c4 == 0)
+                acc = __fmul_rn(v.x, v.x);
+            else
+                acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
+            acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
+            acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
+            acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+        }
+        if (nmax) {  // one atomic per warp: non-negative floats order like their bit patterns
+            const unsigned act = __activemask();
+            const unsigned m = __reduce_max_sync(act, __float_as_uint(acc));
+            if ((int)(threadIdx.x & 31) == __ffs(act) - 1) atomicMax(nmax + b, m);
+        }
+    }
+    norm[(size_t)b * npad + i] = acc;
+}
+
+static cudaError_t ensure_attr() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(knn_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM);
+    if (dev >= 0 && dev < 64) done[dev] = e == cudaSuccess;
+    return e;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Layout {
+    size_t head, rn, qn, qlist, rlo, qlo, total;
+};
+static Layout layout(int64_t B, int64_t N, int64_t S, bool self) {
+    const int64_t npad = ceil_div(N, BN) * BN;
+    Layout l;
+    l.head = 0;                                             // [B] rnmax | [B] qcount | maxdev
+    l.rn = align256((size_t)(2 * B + 1) * 4);
+    l.qn = l.rn + align256((size_t)B * npad * 4);
+    l.qlist = l.qn + (self ? 0 : align256((size_t)B * S * 4));
+    l.rlo = l.qlist + align256((size_t)B * S * 4);
+    l.qlo = l.rlo + align256((size_t)B * N * CH * 4);
+    l.total = l.qlo + (self ? 0 : align256((size_t)B * S * CH * 4));
+    return l;
+}
+
+}  // namespace knntc
+
+// knn.cu: the exact register-tiled kernel on an indirect query list (K = 8, C % 64 == 0)
+int launch_knn_tiled_indirect8(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, const int* qlist,
+                               const int* qcount, int B, int N, int S, int C, cudaStream_t st);
+}  // namespace mpc
+
+MPC_API int mpc_knn_tc_workspace_bytes(int64_t B, int64_t N, int64_t S, int64_t C, int64_t K, int64_t* bytes_out) {
+    using namespace mpc;
+    if (!bytes_out || B < 0 || N <= 0 || S < 0) return MPC_ERR_INVALID;
+    if (C != knntc::CH || K != 8) return MPC_ERR_UNSUPPORTED;
+    *bytes_out = (int64_t)knntc::layout(B, N, S, false).total;
+    return MPC_OK;
+}
+
+MPC_API int mpc_knn_tc_f32(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, void* workspace,
+                           int64_t workspace_bytes, int64_t B, int64_t N, int64_t S, int64_t C, int64_t K,
+                           mpc_stream_t stream) {
+    using namespace mpc;
+    using namespace mpc::knntc;
+    if (B < 0 || N <= 0 || S < 0 || C <= 0 || K <= 0 || K > N) return MPC_ERR_INVALID;
+    if (B == 0 || S == 0) return MPC_OK;
+    if (!ref || !qry || !idx_out || !workspace) return MPC_ERR_INVALID;
+    if (C != CH || K != 8 || N < LIST || B > 65535 || (int64_t)B * N > INT32_MAX || (int64_t)B * S > INT32_MAX)
+        return MPC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(ref) & 15u) || (reinterpret_cast<uintptr_t>(qry) & 15u) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255u))
+        return MPC_ERR_UNSUPPORTED;
+    const bool self = (ref == qry) && (N == S);
+    const Layout l = layout(B, N, S, self);
+    if ((int64_t)l.total > workspace_bytes) return MPC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const int npad = (int)(ceil_div(N, BN) * BN);
+    unsigned* rnmax = reinterpret_cast<unsigned*>(ws);
+    int* qcount = reinterpret_cast<int*>(ws) + B;
+    unsigned* maxdev = reinterpret_cast<unsigned*>(ws) + 2 * B;
+    float* rn = reinterpret_cast<float*>(ws + l.rn);
+    float* qn = self ? rn : reinterpret_cast<float*>(ws + l.qn);
+    int* qlist = reinterpret_cast<int*>(ws + l.qlist);
+    float* rlo = reinterpret_cast<float*>(ws + l.rlo);
+    float* qlo = self ? rlo : reinterpret_cast<float*>(ws + l.qlo);
+
+    MPC_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * B + 1) * 4, st));
+    knn_tc_prep_kernel<<<dim3((unsigned)ceil_div(npad, 128), (unsigned)B), 128, 0, st>>>(ref, rlo, rn, rnmax, (int)B, (int)N,
+                                                                                          npad);
+    MPC_LAUNCH_CHECK();
+    if (!self) {
+        knn_tc_prep_kernel<<<dim3((unsigned)ceil_div(S, 128), (unsigned)B), 128, 0, st>>>(qry, qlo, qn, nullptr, (int)B,
+                                                                                          (int)S, (int)S);
+        MPC_LAUNCH_CHECK();
+    }
+    CUtensorMap m_qhi, m_qlo, m_rhi, m_rlo;
+    int rc;
+    if ((rc = make_map(&m_qhi, qry, B * S, CH, CH, BM)) != MPC_OK) return rc;
+    if ((rc = make_map(&m_qlo, qlo, B * S, CH, CH, BM)) != MPC_OK) return rc;
+    if ((rc = make_map(&m_rhi, ref, B * N, CH, CH, BN)) != MPC_OK) return rc;
+    if ((rc = make_map(&m_rlo, rlo, B * N, CH, CH, BN)) != MPC_OK) return rc;
+    MPC_CUDA(ensure_attr());
+    Params p;
+    p.ref = ref;
+    p.qry = qry;
+    p.rn = rn;
+    p.qn = qn;
+    p.rnmax = rnmax;
+    p.maxdev = maxdev;
+    p.qcount = qcount;
+    p.qlist = qlist;
+    p.dist_out = dist_out;
+    p.idx_out = idx_out;
+    p.N = (int)N;
+    p.S = (int)S;
+    p.Npad = npad;
+    p.qn_stride = self ? npad : (int)S;
+    p.ntiles = npad / BN;
+    knn_tc_kernel<8><<<dim3((unsigned)ceil_div(S, BM), (unsigned)B), THREADS, DYN_SMEM, st>>>(m_qhi, m_qlo, m_rhi, m_rlo, p);
+    MPC_LAUNCH_CHECK();
+    // exact brute force for the queries the filter could not decide (near-tie groups larger than the candidate list)
+    return launch_knn_tiled_indirect8(ref, qry, dist_out, idx_out, qlist, qcount, (int)B, (int)N, (int)S, (int)C, st);
+}

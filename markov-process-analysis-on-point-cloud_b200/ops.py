@@ -22,6 +22,20 @@ _i64 = ctypes.c_int64
 _CHECK_INDEX = os.environ.get("MPC_CHECK_INDEX", "0") == "1"
 _KNN_LIST_LENGTHS = (1, 3, 8, 9, 16, 32)
 _TRANSITION_IMPL = os.environ.get("MPC_TRANSITION", "csr")  # "atomic": red.global scatter form
+# Feature-space searches (C = 64, k = 8) run their distance GEMM on the tensor cores (mpc_knn_tc_f32: filter on
+# tcgen05, exact FP32 refinement, bit-identical results); MPC_KNN_TC=0 forces the FP32-SIMT brute-force kernels.
+_KNN_TC = os.environ.get("MPC_KNN_TC", "1") == "1"
+_KNN_TC_MIN_N = int(os.environ.get("MPC_KNN_TC_MIN_N", "512"))
+knn_tc_debug = None  # set to a list to collect (workspace, B) of every tensor-core search (tests read the diagnostics)
+
+
+def knn_tc_available():
+    return _KNN_TC
+
+
+def set_knn_tc(on):
+    global _KNN_TC
+    _KNN_TC = bool(on)
 
 
 def _f32c(t):
@@ -195,6 +209,18 @@ def _knn_compute(nsample, xyz, new_xyz):
         xyz_run, N_run = xyz, N
     dist = torch.empty(B, S, L, dtype=torch.float32, device=xyz.device)
     idx = torch.empty(B, S, L, dtype=torch.int64, device=xyz.device)
+    if (_KNN_TC and C == 64 and L == 8 and N_run >= _KNN_TC_MIN_N and xyz_run.data_ptr() % 16 == 0
+            and new_xyz.data_ptr() % 16 == 0 and B * max(N_run, S) < 2 ** 31):
+        need = ctypes.c_int64(0)
+        _lib.load().mpc_knn_tc_workspace_bytes(_i64(B), _i64(N_run), _i64(S), _i64(C), _i64(L), ctypes.byref(need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=xyz.device)
+        call("mpc_knn_tc_f32", ptr(xyz_run), ptr(new_xyz), ptr(dist), ptr(idx), ptr(ws), _i64(need.value), _i64(B),
+             _i64(N_run), _i64(S), _i64(C), _i64(L), algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
+        if knn_tc_debug is not None:
+            knn_tc_debug.append((ws, B, N_run, S))
+        if cache is not None:
+            cache[key] = (dist, idx, xyz, new_xyz)
+        return dist, idx
     call("mpc_knn_f32", ptr(xyz_run), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N_run), _i64(S), _i64(C),
          _i64(L), algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
     if L != nsample:

@@ -170,6 +170,21 @@ class _TransitionC(torch.autograd.Function):
         return g, None, None
 
 
+def upsample_torch(points, knn_idx, n_out):
+    """The same sparse restatement in ATen ops of any float dtype (the float64 "exact" runs that the full-size
+    gradient tests measure both fp32 implementations against): out = D^-1 A^T points, D counting the sources
+    whose channel-0 value is non-zero (:44), zero counts replaced by one (:45-46)."""
+    B, S, C = points.shape
+    K = knn_idx.shape[2]
+    flat = (knn_idx + n_out * torch.arange(B).view(B, 1, 1)).reshape(-1)
+    src = points.unsqueeze(2).expand(B, S, K, C).reshape(-1, C)
+    out = torch.zeros(B * n_out, C, dtype=points.dtype).index_add(0, flat, src)
+    cnt = torch.zeros(B * n_out, dtype=points.dtype).index_add(
+        0, flat, (src[:, 0] != 0).to(points.dtype).detach())
+    cnt = torch.where(cnt == 0, torch.ones_like(cnt), cnt)
+    return (out / cnt.unsqueeze(1)).view(B, n_out, C)
+
+
 def upsample(points, knn_idx, scale_ratio=2, dist=None, n_out=None):
     """The Markov state transition, R/modules/pointnet2_utils.py:13-50, restated sparsely (see
     pointset_oracle.c).  `dist` is accepted and ignored like the reference does (:30-34)."""
@@ -178,6 +193,8 @@ def upsample(points, knn_idx, scale_ratio=2, dist=None, n_out=None):
         n_out = S * scale_ratio
     if int(knn_idx.max()) >= n_out or int(knn_idx.min()) < 0:
         raise RuntimeError("index out of range in transition")  # ATen's scatter_ raises here too
+    if points.dtype != torch.float32:
+        return upsample_torch(points, knn_idx, int(n_out))
     return _TransitionC.apply(points, knn_idx, int(n_out))
 
 
@@ -197,8 +214,11 @@ class Ctx:
     """Evaluation context: train/eval, which kNN implementation ranks neighbours, and the index tape
     (every FPS / kNN result in call order) used for index injection into the CUDA path."""
 
-    def __init__(self, train=False, knn_impl="c", fps_starts=None, eval_blocks=()):
+    def __init__(self, train=False, knn_impl="c", fps_starts=None, eval_blocks=(), inject=None):
         self.train = train
+        # index tensors returned (in call order) instead of searching / sampling: a float64 run of the same network
+        # on the fp32 run's neighbourhoods (tests/test_gpu_fullsize.py)
+        self.inject = list(inject) if inject is not None else None
         self.eval_blocks = tuple(eval_blocks)  # Linear blocks (key prefixes) whose BatchNorm uses running statistics
         self.knn_impl = knn_impl
         self.fps_starts = list(fps_starts) if fps_starts is not None else None
@@ -208,6 +228,10 @@ class Ctx:
         """space: "xyz" (coordinates; tie-free on real clouds) or "feat" (feature space, where the
         transition leaves many points with IDENTICAL features and the reference's topk order among the
         exact ties is arbitrary -- taped as "knnf" so tests can audit instead of demanding equality)."""
+        if self.inject is not None:
+            i = self.inject.pop(0)
+            self.tape.append(("knn" if space == "xyz" else "knnf", i))
+            return None, i
         with torch.no_grad():
             if self.knn_impl == "torch":
                 d, i = knn_point_torch(k, xyz.detach(), new_xyz.detach())
@@ -219,7 +243,7 @@ class Ctx:
     def fps(self, xyz, npoint):
         B, N, _ = xyz.shape
         start = self.fps_starts.pop(0) if self.fps_starts is not None else draw_fps_start(B, N)
-        i = farthest_point_sample(xyz, npoint, start)
+        i = self.inject.pop(0) if self.inject is not None else farthest_point_sample(xyz, npoint, start)
         self.tape.append(("fps", i))
         return i
 

@@ -94,6 +94,23 @@ int mpc_knn_tc_f32(const float* ref, const float* qry, float* dist_out, int64_t*
                    int64_t workspace_bytes, int64_t B, int64_t N, int64_t S, int64_t C, int64_t K, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * k nearest neighbours of 3-D coordinates through a uniform grid.  Same operands (C = 3 implied), same outputs and the
+ * SAME bit-exact contract as mpc_knn_f32 (it replaces the same reference lines, R/modules/pointnet2_utils.py:190-222,
+ * for the coordinate searches of LocalMerge :448, Fuse :667-704 and three_nn :899-901): the reference set of each
+ * cloud is counting-sorted into grid cells (about K/4 points per cell), a query evaluates only the cells its
+ * neighbourhood can reach -- every candidate with the contract's fp32 expression, ranked by (distance, index) -- and
+ * stops once every cell intersecting the ball of radius sqrt(d_K + eps) has been visited, eps = 64 * 2^-24 *
+ * (|q|^2 + max|r|^2) bounding how far the expanded form can lie below the true squared distance.  Results are
+ * therefore bit-identical to mpc_knn_f32 for any input; the work drops from B*S*N to about B*S*7K distance
+ * evaluations.  K in {1, 3, 8, 9, 16, 32}, K <= N, N <= 2^30; else MPC_ERR_INVALID / UNSUPPORTED.
+ *   workspace: mpc_knn3_grid_workspace_bytes(...) bytes, 256-byte aligned, caller-owned, no initialisation needed
+ *   (cell table, counting-sort cursors, sorted copy of the reference set).
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_knn3_grid_workspace_bytes(int64_t B, int64_t N, int64_t S, int64_t K, int64_t* bytes_out);
+int mpc_knn3_grid_f32(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, void* workspace,
+                      int64_t workspace_bytes, int64_t B, int64_t N, int64_t S, int64_t K, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Ball query.  Replaces query_ball_point, R/modules/pointnet2_utils.py:112-134.
  *   xyz [B,N,C], new_xyz [B,S,C], idx_out [B,S,nsample] i64; r2 = radius^2 rounded to f32.
  * First `nsample` indices n (ascending) with NOT(d > r2), d as in mpc_knn_f32; padded with the first hit;

@@ -26,6 +26,10 @@ _TRANSITION_IMPL = os.environ.get("MPC_TRANSITION", "csr")  # "atomic": red.glob
 # tcgen05, exact FP32 refinement, bit-identical results); MPC_KNN_TC=0 forces the FP32-SIMT brute-force kernels.
 _KNN_TC = os.environ.get("MPC_KNN_TC", "1") == "1"
 _KNN_TC_MIN_N = int(os.environ.get("MPC_KNN_TC_MIN_N", "512"))
+# Coordinate searches (C = 3) in large clouds go through the uniform-grid kernel (mpc_knn3_grid_f32: bit-identical
+# results, ~7K instead of N distance evaluations per query); MPC_KNN_GRID=0 forces brute force.
+_KNN_GRID = os.environ.get("MPC_KNN_GRID", "1") == "1"
+_KNN_GRID_MIN_N = int(os.environ.get("MPC_KNN_GRID_MIN_N", "2048"))
 knn_tc_debug = None  # set to a list to collect (workspace, B) of every tensor-core search (tests read the diagnostics)
 
 
@@ -36,6 +40,13 @@ def knn_tc_available():
 def set_knn_tc(on):
     global _KNN_TC
     _KNN_TC = bool(on)
+
+
+def set_knn_grid(on, min_n=None):
+    global _KNN_GRID, _KNN_GRID_MIN_N
+    _KNN_GRID = bool(on)
+    if min_n is not None:
+        _KNN_GRID_MIN_N = int(min_n)
 
 
 def _f32c(t):
@@ -221,8 +232,15 @@ def _knn_compute(nsample, xyz, new_xyz):
         if cache is not None:
             cache[key] = (dist, idx, xyz, new_xyz)
         return dist, idx
-    call("mpc_knn_f32", ptr(xyz_run), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N_run), _i64(S), _i64(C),
-         _i64(L), algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
+    if _KNN_GRID and C == 3 and N_run >= _KNN_GRID_MIN_N:
+        need = ctypes.c_int64(0)
+        _lib.load().mpc_knn3_grid_workspace_bytes(_i64(B), _i64(N_run), _i64(S), _i64(L), ctypes.byref(need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=xyz.device)
+        call("mpc_knn3_grid_f32", ptr(xyz_run), ptr(new_xyz), ptr(dist), ptr(idx), ptr(ws), _i64(need.value), _i64(B),
+             _i64(N_run), _i64(S), _i64(L), algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
+    else:
+        call("mpc_knn_f32", ptr(xyz_run), ptr(new_xyz), ptr(dist), ptr(idx), _i64(B), _i64(N_run), _i64(S), _i64(C),
+             _i64(L), algo_bytes=B * ((N + S) * C * 4 + S * L * 12))
     if L != nsample:
         dist, idx = dist[:, :, :nsample].contiguous(), idx[:, :, :nsample].contiguous()
     if cache is not None:

@@ -11,7 +11,7 @@ namespace mpc {
 
 // tuning knobs (mpc_debug_set_knob; 0 = built-in default): 0 = elementwise CTAs per SM, 1 = column-reduction CTAs
 // per SM, 2 = elementwise float4 per thread the grid is sized for
-int64_t g_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 3 = force the grid-wide FPS variant for N > 8192 (tests)
+int64_t g_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 3 = force the grid-wide FPS variant for N > 8192 (tests); 6 = smallest N for the pruned FPS variant (< 0: never)
 static inline int64_t knob(int i, int64_t dflt) { return g_knob[i] > 0 ? g_knob[i] : dflt; }
 
 constexpr int BN_TX = 32;  // lanes along channels (float4 each => 128 channels per CTA column)

@@ -404,6 +404,10 @@ static int launch_grid(const float* xyz, const int64_t* start, int64_t* out, int
     return MPC_OK;
 }
 
+// fps_pruned.cu: exact bucket-pruned variant for mid-sized clouds
+int fps_pruned_dispatch(const float* xyz, const int64_t* start, int64_t* out, int B, int N, int npoint,
+                        cudaStream_t st);
+
 }  // namespace mpc
 
 MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, int64_t B, int64_t N, int64_t C,
@@ -424,6 +428,12 @@ MPC_API int mpc_fps_f32(const float* xyz, const int64_t* start, int64_t* out, in
     }
     const int b = (int)B, n = (int)N, np = (int)npoint;
     if (n > 8192 && g_knob[3] > 0) return launch_grid<8, 1024>(xyz, start, out, b, n, np, st);  // debug: force variant D
+    // mid-sized clouds: exact bucket pruning (fps_pruned.cu).  knob 6: 0 = default threshold, < 0 = plain kernels
+    // only (A/B runs and the tests that compare the two), > 0 = smallest N that takes the pruned variant
+    {
+        const int64_t min_n = g_knob[6] == 0 ? 8193 : g_knob[6];
+        if (min_n > 0 && n >= min_n && n <= 24576 && np > 1) return fps_pruned_dispatch(xyz, start, out, b, n, np, st);
+    }
     // single CTA: THREADS * PPT >= N, xyz copy N*12 bytes of shared memory (<= 192 KB at N = 16384)
     if (n <= 128) return launch_cta<1, 128>(xyz, start, out, b, n, np, st);
     if (n <= 256) return launch_cta<2, 128>(xyz, start, out, b, n, np, st);

@@ -159,6 +159,13 @@ int mpc_transition_fwd_f32(const float* points, const int64_t* idx, float* out, 
  * zero-fill / normalise passes, deterministic summation order (ascending s).  workspace: B*(2N+1) + B*S*K int32. */
 int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, float* out, float* cnt, int32_t* workspace,
                                int64_t B, int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
+/* The two halves of mpc_transition_fwd_csr_f32, for callers that apply the SAME neighbour table to several feature
+ * tensors (Fuse.forward reuses the encoder's kNN indices in every stage, R/modules/pointnet2_utils.py:663-704): build
+ * the reverse-neighbour lists once (depends on idx only), then apply them to any points [B,S,C]. */
+int mpc_transition_csr_build(const int64_t* idx, int32_t* workspace, int64_t B, int64_t S, int64_t K, int64_t N,
+                             mpc_stream_t stream);
+int mpc_transition_csr_apply_f32(const float* points, const int32_t* workspace, float* out, float* cnt, int64_t B,
+                                 int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
 int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, const float* cnt, float* grad_points,
                            int64_t B, int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream);
 
@@ -190,6 +197,11 @@ int mpc_three_interpolate_bwd_f32(const float* grad_out, const float* weight, co
 int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, const float* vf, int64_t ldkv,
                           const int64_t* idx, float* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K,
                           int64_t C, mpc_stream_t stream);
+/* bf16-I/O forward of the same core (inference path): q, kf, vf, ctx_out are bf16 (strides in elements, 8-byte
+ * aligned rows), arithmetic in fp32, one rounding at the store. */
+int mpc_attn_feat_fwd_bf16(const void* q, int64_t ldq, const void* kf, const void* vf, int64_t ldkv,
+                           const int64_t* idx, void* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K, int64_t C,
+                           mpc_stream_t stream);
 int mpc_attn_feat_bwd_f32(const float* grad_ctx, const float* q, int64_t ldq, const float* kf,
                           const float* vf, int64_t ldkv, const int64_t* idx, float* grad_q, int64_t ldgq,
                           float* grad_kf, float* grad_vf, int64_t ldgkv, float* grad_bias, int64_t B, int64_t S,
@@ -291,6 +303,23 @@ int mpc_bn_finalize_f32(double* sums, float* stats, float* running_mean, float* 
  * 16-byte aligned, count % 4 == 0) is cleared by the same launch on behalf of the mpc_linear_wgrad_f32 that follows. */
 int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t ldw, float* gx, int64_t ldx,
                          int64_t M, int64_t K, int64_t N, float* zero_buf, int64_t zero_count, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * bf16-I/O shared-MLP block for inference: the reference's whole `Linear` block in eval() -- nn.Linear -> BatchNorm1d
+ * with running statistics -> LeakyReLU, R/modules/pointnet2_utils.py:413-425 -- plus the residual that LocalTrans /
+ * Fuse add to it (:515,574,640-709), as ONE tcgen05 kernel (kind::f16, bf16 operands, fp32 accumulation in TMEM):
+ *     out[m,n] = act(acc[m,n] * scale[n] + shift[n]) (+ residual[m,n]),  acc = x[m,:] . w[n,:],  act = LeakyReLU(slope)
+ *   x [M,K] bf16 (row stride ldx elements), w [N,K] bf16 (ldw), scale / shift [N] f32 (NULL = 1 / 0; for a BatchNorm
+ *   in eval(): scale = gamma / sqrt(var + eps), shift = beta + (bias - mean) * scale), slope = 1 for no activation,
+ *   residual [M,N] bf16 (ldr) or NULL, out [M,N] bf16 or (out_is_f32 != 0) f32 with row stride ldo.
+ *   K % 64 == 0, ldx / ldw % 8 == 0, x / w 16-byte aligned; else MPC_ERR_UNSUPPORTED (callers use the fp32 path).
+ * mpc_f32_to_bf16: row-wise conversion x [rows, cols] f32 (ldx) -> y bf16 (ldy >= cols; pad columns are zeroed), used
+ * for weights (once per layer) and for the first activation of a bf16 forward.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* scale, const float* shift,
+                    float slope, const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t out_is_f32,
+                    int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+int mpc_f32_to_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t cols, mpc_stream_t stream);
 /* Weight gradient of the same layer (what autograd derives for nn.Linear):  gw[N,K] = gy[M,N]^T x[M,K].
  * Same 3xTF32 tcgen05 pipeline with MN-major operand descriptors (no transposed copies), the reduction over the M
  * points split across the SMs and combined with TMA reduce-add into gw.  gw_is_zero = 1: an earlier call in the

@@ -7,6 +7,8 @@
 // writes only the [B,S,C] context; the backward recomputes the softmax instead of saving it.  Both are
 // gather-bound: per centre point they read K rows of k and v (L2-resident at the live sizes) with 128-bit
 // loads, so the roofline that applies is HBM/L2 bandwidth, not the tensor pipe.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mpc {
@@ -116,6 +118,52 @@ attn_feat_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __re
         MPC_CH(x) MPC_CH(y) MPC_CH(z) MPC_CH(w)
 #undef MPC_CH
         *reinterpret_cast<float4*>(ctx + row * (int64_t)CV * 4 + c4) = out;
+    }
+}
+
+// bf16-I/O forward (inference path): rows travel as bf16 (half the gathered bytes), the arithmetic is the fp32
+// expression of the kernel above, one rounding at the store.
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+}
+
+template <int K>
+__global__ void __launch_bounds__(AT)
+attn_feat_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ kf,
+                          const __nv_bfloat16* __restrict__ vf, int64_t ldkv, const int64_t* __restrict__ idx,
+                          __nv_bfloat16* __restrict__ ctx, int S, int N, int CV, float sqrtc, int64_t total) {
+    pdl_prologue();
+    for (int64_t t = (int64_t)blockIdx.x * AT + threadIdx.x; t < total; t += (int64_t)gridDim.x * AT) {
+        const int64_t row = t / CV;
+        const int c4 = (int)(t - row * CV) * 4;
+        const int64_t b = row < 0xffffffffll ? (int64_t)((unsigned)row / (unsigned)S) : row / S;
+        const int64_t* irow = idx + row * K;
+        float4 kk[K], vv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const size_t src = ((size_t)b * N + clamp_index(__ldg(irow + j), N)) * ldkv + c4;
+            kk[j] = ld_bf16x4(kf + src);
+            vv[j] = ld_bf16x4(vf + src);
+        }
+        const float4 qq = ld_bf16x4(q + row * ldq + c4);
+        float4 out;
+        float e[K], v[K], a[K], O;
+        int js;
+#define MPC_CH(comp)                                              \
+    _Pragma("unroll") for (int j = 0; j < K; ++j) {               \
+        e[j] = qq.comp - kk[j].comp;                              \
+        v[j] = vv[j].comp;                                        \
+    }                                                             \
+    out.comp = attn_channel<K>(e, v, sqrtc, a, O, js);
+        MPC_CH(x) MPC_CH(y) MPC_CH(z) MPC_CH(w)
+#undef MPC_CH
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(out.x, out.y), h1 = __floats2bfloat162_rn(out.z, out.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&h0);
+        o.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(ctx + row * (int64_t)CV * 4 + c4) = o;
     }
 }
 
@@ -466,6 +514,26 @@ MPC_API int mpc_attn_feat_fwd_f32(const float* q, int64_t ldq, const float* kf, 
     cudaStream_t st = (cudaStream_t)stream;
     MPC_DISPATCH_K(K, (pdl_launch(attn_feat_fwd_kernel<KK>, dim3(attn_grid(total, AT)), dim3(AT), 0, st, 
                           q, ldq, kf, vf, ldkv, idx, ctx_out, (int)S, (int)N, CV, sqrtc, total)));
+    MPC_LAUNCH_CHECK();
+    return MPC_OK;
+}
+
+MPC_API int mpc_attn_feat_fwd_bf16(const void* q, int64_t ldq, const void* kf, const void* vf, int64_t ldkv,
+                                   const int64_t* idx, void* ctx_out, int64_t B, int64_t S, int64_t N, int64_t K,
+                                   int64_t C, mpc_stream_t stream) {
+    if (!q || !kf || !vf || !idx || !ctx_out || B < 0 || S < 0 || N <= 0 || K <= 0 || C <= 0) return MPC_ERR_INVALID;
+    if (C % 4 || ldq % 4 || ldkv % 4 || ldq < C || ldkv < C || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (((uintptr_t)q | (uintptr_t)kf | (uintptr_t)vf | (uintptr_t)ctx_out) & 7u) return MPC_ERR_INVALID;
+    if (K > KMAX || C > 1024) return MPC_ERR_UNSUPPORTED;
+    if (B == 0 || S == 0) return MPC_OK;
+    const int CV = (int)(C / 4);
+    const int64_t total = B * S * CV;
+    const float sqrtc = 1.0f / sqrtf((float)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    MPC_DISPATCH_K(K, (pdl_launch(attn_feat_fwd_bf16_kernel<KK>, dim3(attn_grid(total, AT)), dim3(AT), 0, st,
+                          static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(kf),
+                          static_cast<const __nv_bfloat16*>(vf), ldkv, idx, static_cast<__nv_bfloat16*>(ctx_out), (int)S,
+                          (int)N, CV, sqrtc, total)));
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

@@ -340,6 +340,107 @@ transition_gather_kernel(const float* __restrict__ points, const int* __restrict
     }
 }
 
+// Same product, G = min(C/4, 32) lanes per output row (C/4 a power of two): the lanes load the row's reverse-neighbour
+// list together (one entry per lane), rank-sort it with shuffles (ascending s: the oracle's summation order) and then
+// stream the source rows in that order, one float4 per lane and row -- each list entry is loaded once per row instead
+// of L times per thread, and the channel-0 count is taken by the lane that holds channel 0.  Rows whose list is
+// longer than G fall back to the selection walk.
+template <int G>
+__global__ void __launch_bounds__(GT)
+transition_gather_group_kernel(const float* __restrict__ points, const int* __restrict__ offs,
+                               const int* __restrict__ list, float* __restrict__ out, float* __restrict__ cnt, int S,
+                               int K, int C, int N, int64_t rows_total) {
+    pdl_prologue();
+    const int CV = C / 4;
+    const int slices = CV / G;  // 32-lane slices of one row when C/4 > 32
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int64_t groups_total = rows_total * slices;
+    const int64_t gstride = (int64_t)gridDim.x * (GT / G);
+    // all lanes of a warp run the same number of iterations (the shuffles are group-wide, the loop bound warp-wide)
+    const int64_t g0 = (int64_t)blockIdx.x * (GT / G) + threadIdx.x / G;
+    const int64_t w0 = g0 - (lane / G);  // first group of this warp
+    for (int64_t wg = w0; wg < groups_total; wg += gstride) {
+        const int64_t g = wg + lane / G;
+        const bool live = g < groups_total;
+        const int64_t row = live ? g / slices : 0;  // (b, n)
+        const int v = (int)(live ? g - row * slices : 0) * G + gl;
+        const int64_t b = row / N;
+        const int n = (int)(row - b * N);
+        const int* o = offs + b * (int64_t)(N + 1) + n;
+        const int lo = live ? __ldg(o) : 0, hi = live ? __ldg(o + 1) : 0;
+        const int L = hi - lo;
+        const int* lst = list + b * (int64_t)S * K;
+        const float* pb = points + (size_t)b * S * C;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float nz = 0.f;
+        const int Lmax = __reduce_max_sync(0xffffffffu, L <= G ? L : 0);
+        // sorted list in registers: lane p of the group ends up with the p-th smallest source
+        const int mine = (gl < L && L <= G) ? __ldg(lst + lo + gl) : 0x7fffffff;
+        int rank = 0;
+        for (int e = 0; e < Lmax; ++e) {
+            const int other = __shfl_sync(gmask, mine, (lane & ~(G - 1)) + e);
+            rank += (other < mine) ? 1 : 0;  // sources of one list are distinct
+        }
+        int sorted = 0x7fffffff;
+        for (int e = 0; e < Lmax; ++e) {
+            const int val = __shfl_sync(gmask, mine, (lane & ~(G - 1)) + e);
+            const int r = __shfl_sync(gmask, rank, (lane & ~(G - 1)) + e);
+            if (r == gl) sorted = val;
+        }
+        for (int e0 = 0; e0 < Lmax; e0 += 4) {  // four source rows in flight per lane, summed in list order
+            float4 pr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = __shfl_sync(gmask, sorted, (lane & ~(G - 1)) + ((e0 + u) & (G - 1)));
+                pr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e0 + u < L && L <= G) pr[u] = __ldg(reinterpret_cast<const float4*>(pb + (size_t)s * C) + v);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e0 + u < L && L <= G) {
+                    if (v == 0 && pr[u].x != 0.0f) nz += 1.0f;  // count_nonzero of channel 0 (reference :44)
+                    acc.x += pr[u].x; acc.y += pr[u].y; acc.z += pr[u].z; acc.w += pr[u].w;
+                }
+            }
+        }
+        if (L > G) {  // long list: selection walk (rare)
+            int prev = -1;
+            for (int e = lo; e < hi; ++e) {
+                int s = 0x7fffffff;
+                for (int f = lo; f < hi; ++f) {
+                    const int c = __ldg(lst + f);
+                    if (c > prev && c < s) s = c;
+                }
+                prev = s;
+                const float* src = pb + (size_t)s * C;
+                if (v == 0 && __ldg(src) != 0.0f) nz += 1.0f;
+                const float4 p = __ldg(reinterpret_cast<const float4*>(src) + v);
+                acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+            }
+        }
+        // the count lives in the lane that holds channel 0 (slice 0, group lane 0); other slices of the row recount
+        float dv;
+        if (slices == 1) {
+            nz = __shfl_sync(gmask, nz, lane & ~(G - 1));
+            dv = nz == 0.0f ? 1.0f : nz;
+        } else {
+            float c0 = 0.f;  // (C/4 > 32: the row spans several warps; every slice counts channel 0 itself)
+            if (gl == 0 && live) {
+                for (int e = lo; e < hi; ++e)
+                    if (__ldg(pb + (size_t)__ldg(lst + e) * C) != 0.0f) c0 += 1.0f;
+            }
+            c0 = __shfl_sync(gmask, c0, lane & ~(G - 1));
+            dv = c0 == 0.0f ? 1.0f : c0;
+        }
+        if (live) {
+            reinterpret_cast<float4*>(out)[row * CV + v] = make_float4(__fdiv_rn(acc.x, dv), __fdiv_rn(acc.y, dv),
+                                                                       __fdiv_rn(acc.z, dv), __fdiv_rn(acc.w, dv));
+            if (v == 0) cnt[row] = dv;
+        }
+    }
+}
+
 // backward: a pure gather (no atomics): grad_points[row,:] = sum_k grad_out[b, idx[row,k], :] / cnt[b, idx[row,k]]
 template <bool VEC4>
 __global__ void __launch_bounds__(GT)
@@ -600,13 +701,12 @@ MPC_API int mpc_transition_fwd_f32(const float* points, const int64_t* idx, floa
     return MPC_OK;
 }
 
-MPC_API int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, float* out, float* cnt,
-                                       int32_t* workspace, int64_t B, int64_t S, int64_t K, int64_t C, int64_t N,
-                                       mpc_stream_t stream) {
-    if (B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+MPC_API int mpc_transition_csr_build(const int64_t* idx, int32_t* workspace, int64_t B, int64_t S, int64_t K,
+                                     int64_t N, mpc_stream_t stream) {
+    if (B < 0 || S < 0 || K <= 0 || N <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
     if (K > 32 || S * K > INT32_MAX) return MPC_ERR_UNSUPPORTED;
     if (B == 0) return MPC_OK;
-    if (!out || !cnt || !workspace || (S > 0 && (!points || !idx))) return MPC_ERR_INVALID;
+    if (!workspace || (S > 0 && !idx)) return MPC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     // workspace: offsets [B, N+1] | cursor [B, N] | lists [B, S*K]
     int* offs = workspace;
@@ -637,8 +737,36 @@ MPC_API int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, 
         pdl_launch(csr_fill_kernel, dim3(grid_for(total)), dim3(GT), 0, st, idx, cursor, list, (int)S, (int)K, (int)N, total);
         MPC_LAUNCH_CHECK();
     }
+    return MPC_OK;
+}
+
+MPC_API int mpc_transition_csr_apply_f32(const float* points, const int32_t* workspace, float* out, float* cnt,
+                                         int64_t B, int64_t S, int64_t K, int64_t C, int64_t N, mpc_stream_t stream) {
+    if (B < 0 || S < 0 || K <= 0 || C <= 0 || N <= 0 || N > INT32_MAX) return MPC_ERR_INVALID;
+    if (K > 32 || S * K > INT32_MAX) return MPC_ERR_UNSUPPORTED;
+    if (B == 0) return MPC_OK;
+    if (!out || !cnt || !workspace || (S > 0 && !points)) return MPC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int* offs = workspace;
+    const int* list = offs + B * (N + 1) + B * N;
     const bool v4 = C % 4 == 0 && aligned16(points) && aligned16(out);
-    const int64_t total = B * N * (v4 ? C / 4 : C);
+    const int64_t CV = v4 ? C / 4 : C;
+    if (v4 && (CV & (CV - 1)) == 0 && g_knob[7] == 0) {
+        // G lanes per output row; grid: enough warps in flight to cover the gather latency, whole waves of SMs
+        const int G = (int)(CV < 32 ? CV : 32);
+        const int64_t groups = B * N * (CV / G);
+        const int64_t want = ceil_div(groups * G, GT);
+        const int64_t cap = (int64_t)kNumSMs * (g_knob[5] > 0 ? g_knob[5] : 16);
+        const unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+        switch (G) {
+#define MPC_TG(GG) case GG: pdl_launch(transition_gather_group_kernel<GG>, dim3(grid), dim3(GT), 0, st, points, offs, list, out, cnt, (int)S, (int)K, (int)C, (int)N, B * N); break;
+            MPC_TG(1) MPC_TG(2) MPC_TG(4) MPC_TG(8) MPC_TG(16) MPC_TG(32)
+#undef MPC_TG
+        }
+        MPC_LAUNCH_CHECK();
+        return MPC_OK;
+    }
+    const int64_t total = B * N * CV;
     if (v4)
         pdl_launch(transition_gather_kernel<true>, dim3(grid_for(total)), dim3(GT), 0, st, points, offs, list, out, cnt, (int)S, (int)K, (int)C,
                                                                       (int)N, total);
@@ -647,6 +775,15 @@ MPC_API int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, 
                                                                        (int)C, (int)N, total);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
+}
+
+MPC_API int mpc_transition_fwd_csr_f32(const float* points, const int64_t* idx, float* out, float* cnt,
+                                       int32_t* workspace, int64_t B, int64_t S, int64_t K, int64_t C, int64_t N,
+                                       mpc_stream_t stream) {
+    if (!out || !cnt) return B == 0 ? MPC_OK : MPC_ERR_INVALID;
+    const int rc = mpc_transition_csr_build(idx, workspace, B, S, K, N, stream);
+    if (rc != MPC_OK) return rc;
+    return mpc_transition_csr_apply_f32(points, workspace, out, cnt, B, S, K, C, N, stream);
 }
 
 MPC_API int mpc_transition_bwd_f32(const float* grad_out, const int64_t* idx, const float* cnt,

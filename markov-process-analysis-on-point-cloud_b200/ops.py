@@ -209,6 +209,10 @@ def _knn_compute(nsample, xyz, new_xyz):
            nsample)
     if cache is not None and key in cache:
         return cache[key][:2]
+    if xyz.dtype == torch.bfloat16 or new_xyz.dtype == torch.bfloat16:  # bf16 inference: indices from fp32 arithmetic
+        same = new_xyz is xyz
+        xyz = xyz.float()
+        new_xyz = xyz if same else new_xyz.float()
     xyz, new_xyz = _f32c(xyz.detach()), _f32c(new_xyz.detach())
     L = _list_length(nsample, N)
     if L > N:
@@ -281,6 +285,126 @@ def query_ball_point(radius, nsample, xyz, new_xyz, cuda=False):
     call("mpc_ball_query_f32", ptr(xyz), ptr(new_xyz), ptr(out), r2, _i64(B), _i64(N), _i64(S), _i64(C),
          _i64(nsample))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# bf16 inference path (activations travel as bf16, arithmetic in fp32: mpc_linear_bf16 / mpc_attn_feat_fwd_bf16 /
+# mpc_gather_bf16).  Indices still come from fp32 arithmetic: coordinate searches see the fp32 cloud, feature-space
+# searches see the bf16 features widened to fp32.
+# ------------------------------------------------------------------------------------------------------
+_INFER_BF16 = False
+
+
+@contextlib.contextmanager
+def bf16_inference():
+    """Inside this context the drop-in modules, when in eval(), run their bf16-I/O kernels: every `Linear` block
+    (nn.Linear -> BatchNorm1d(running statistics) -> LeakyReLU [+ residual]) is ONE tcgen05 GEMM with the affine map
+    and the activation in its epilogue, the attention core and the gathers move bf16 rows.  No autograd."""
+    global _INFER_BF16
+    old = _INFER_BF16
+    _INFER_BF16 = True
+    try:
+        with torch.no_grad():
+            yield
+    finally:
+        _INFER_BF16 = old
+
+
+def bf16_active():
+    return _INFER_BF16
+
+
+def to_bf16_rows(x2d):
+    """[M,K] f32 -> bf16 (one pass, mpc_f32_to_bf16); bf16 input is returned as is."""
+    if x2d.dtype == torch.bfloat16:
+        return x2d if x2d.stride(1) == 1 else x2d.contiguous()
+    x2d = _f32c(x2d)
+    M, K = x2d.shape
+    out = torch.empty(M, K, dtype=torch.bfloat16, device=x2d.device)
+    call("mpc_f32_to_bf16", ptr(x2d), _i64(K), ptr(out), _i64(K), _i64(M), _i64(K), algo_bytes=M * K * 6)
+    return out
+
+
+def _bf16_weight(*ws):
+    """bf16 copy of a weight matrix (or of several stacked along the output dimension), rounded once and cached on
+    the first parameter, keyed by the parameters' versions."""
+    key = tuple((w.data_ptr(), w._version) for w in ws)
+    hit = getattr(ws[0], "_mpc_bf16", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    w = ws[0].detach() if len(ws) == 1 else torch.cat([w.detach() for w in ws], 0)
+    w16 = to_bf16_rows(w.contiguous())
+    ws[0]._mpc_bf16 = (key, w16)
+    return w16
+
+
+def _bn_affine(bias, bn):
+    """BatchNorm1d in eval() after a Linear bias is the per-channel affine map y * scale + shift."""
+    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bias._version if bias is not None else -1, bn.weight.data_ptr())
+    hit = getattr(bn, "_mpc_affine", None)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    scale = (bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)).float().contiguous()
+    b = bias.detach() if bias is not None else 0.0
+    shift = (bn.bias.detach() + (b - bn.running_mean) * scale).float().contiguous()
+    bn._mpc_affine = (key, scale, shift)
+    return scale, shift
+
+
+def linear_bf16(x2d, w16, scale, shift, slope=1.0, residual2d=None, out_f32=False):
+    """out = LeakyReLU_slope(x2d @ w16^T * scale + shift) (+ residual2d): mpc_linear_bf16.  x2d [M,K] bf16 with
+    K % 64 == 0; returns bf16 [M,N] (rows padded to 16 bytes when N % 8 != 0) or f32."""
+    M, K = x2d.shape
+    N = w16.shape[0]
+    if out_f32:
+        out = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
+        ldo = N
+    else:
+        Np = (N + 7) & ~7
+        out = torch.empty(M, Np, dtype=torch.bfloat16, device=x2d.device)
+        ldo = Np
+        if Np != N:
+            out = out[:, :N]
+    if residual2d is not None:
+        residual2d = to_bf16_rows(residual2d)
+    call("mpc_linear_bf16", ptr(x2d), _i64(x2d.stride(0)), ptr(w16), _i64(w16.stride(0)), ptr(scale), ptr(shift),
+         ctypes.c_float(slope), ptr(residual2d), _i64(residual2d.stride(0) if residual2d is not None else 0), ptr(out),
+         _i64(ldo), _i64(1 if out_f32 else 0), _i64(M), _i64(K), _i64(N),
+         algo_bytes=(M * K + N * K) * 2 + M * N * (4 if out_f32 else 2) * (2 if residual2d is not None else 1))
+    return out
+
+
+def _bf16_gemm_ok(x2d):
+    return (x2d.is_cuda and x2d.shape[1] % 64 == 0 and x2d.shape[0] > 0
+            and (x2d.dtype == torch.float32 or (x2d.stride(0) % 8 == 0 and x2d.data_ptr() % 16 == 0)))
+
+
+def feat_attention_bf16(center, features, idx, wq, bq, wk, bk, wv, bv):
+    """Feature branch of LocalTrans for the bf16 inference path: q projection, fused k|v projection (two
+    mpc_linear_bf16 launches, biases in the epilogue) and the bf16 attention core."""
+    B, S, Cin = center.shape
+    N = features.shape[1]
+    C = wq.shape[0]
+    K = idx.shape[2]
+    c2d, f2d = to_bf16_rows(center.reshape(-1, Cin)), to_bf16_rows(features.reshape(-1, Cin))
+    q = linear_bf16(c2d, _bf16_weight(wq), None, bq.detach())
+    kv = linear_bf16(f2d, _bf16_weight(wk, wv), None, _cat_cached(bk, bv))
+    out = torch.empty(B, S, C, dtype=torch.bfloat16, device=center.device)
+    call("mpc_attn_feat_fwd_bf16", ptr(q), _i64(q.stride(0)), ptr(kv), ctypes.c_void_p(kv.data_ptr() + 2 * C),
+         _i64(kv.stride(0)), ptr(_i64c(idx)), ptr(out), _i64(B), _i64(S), _i64(N), _i64(K), _i64(C),
+         algo_bytes=B * ((2 * N * C + 2 * S * C) * 2 + S * K * 8))
+    return out
+
+
+def _cat_cached(a, b):
+    key = (a._version, b._version, a.data_ptr(), b.data_ptr())
+    hit = getattr(a, "_mpc_cat", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    c = torch.cat((a.detach(), b.detach()), 0).float().contiguous()
+    a._mpc_cat = (key, c)
+    return c
 
 
 class SmoothCE(torch.autograd.Function):
@@ -455,6 +579,30 @@ def index_points(points, idx, cuda=False, is_group=False):
 # ------------------------------------------------------------------------------------------------------
 # Markov state transition
 # ------------------------------------------------------------------------------------------------------
+def _csr_lists(idx, B, S, K, n_out):
+    """Reverse-neighbour lists (CSR) of a kNN index tensor: workspace of mpc_transition_csr_build.  They depend on the
+    indices only, and Fuse applies the same encoder kNN tensors in every decoder stage (R/modules/pointnet2_utils.py:
+    663-704: 14 transitions over 9 distinct index tensors per forward), so inside a geometry scope they are built once
+    per (index tensor, target size) and shared -- across streams through the event recorded after the build."""
+    geo = _geo
+    key = (idx.data_ptr(), idx._version, tuple(idx.shape), idx.stride(), n_out)
+    if geo is not None:
+        hit = geo.csr.get(key)
+        if hit is not None:
+            ws, ev, _ = hit
+            torch.cuda.current_stream().wait_event(ev)
+            ws.record_stream(torch.cuda.current_stream())
+            return ws
+    ws = torch.empty(B * (2 * n_out + 1) + B * S * K, dtype=torch.int32, device=idx.device)
+    call("mpc_transition_csr_build", ptr(idx), ptr(ws), _i64(B), _i64(S), _i64(K), _i64(n_out),
+         algo_bytes=B * S * K * 8)
+    if geo is not None:
+        ev = torch.cuda.Event()
+        ev.record()
+        geo.csr[key] = (ws, ev, idx)  # idx stays alive with the entry: its address is the key
+    return ws
+
+
 class _Transition(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, idx, n_out):
@@ -463,9 +611,9 @@ class _Transition(torch.autograd.Function):
         out = torch.empty(B, n_out, C, dtype=torch.float32, device=points.device)
         cnt = torch.empty(B, n_out, dtype=torch.float32, device=points.device)
         if _TRANSITION_IMPL == "csr":  # gather form over reverse-neighbour lists (deterministic, no float atomics)
-            ws = torch.empty(B * (2 * n_out + 1) + B * S * K, dtype=torch.int32, device=points.device)
-            call("mpc_transition_fwd_csr_f32", ptr(points), ptr(idx), ptr(out), ptr(cnt), ptr(ws), _i64(B), _i64(S),
-                 _i64(K), _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8))
+            ws = _csr_lists(idx, B, S, K, n_out)
+            call("mpc_transition_csr_apply_f32", ptr(points), ptr(ws), ptr(out), ptr(cnt), _i64(B), _i64(S), _i64(K),
+                 _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8))
         else:
             call("mpc_transition_fwd_f32", ptr(points), ptr(idx), ptr(out), ptr(cnt), _i64(B), _i64(S), _i64(K),
                  _i64(C), _i64(n_out), algo_bytes=B * ((S + n_out) * C * 4 + S * K * 8))
@@ -496,6 +644,8 @@ def upsample(points, knn_idx, scale_ratio=2, dist=None, n_out=None):
         n_out = S * scale_ratio
     knn_idx = _i64c(knn_idx)
     _check_index(knn_idx, n_out, "upsample")
+    if points.dtype == torch.bfloat16:  # bf16 inference path: the sparse product accumulates in fp32
+        return _Transition.apply(points.float().contiguous(), knn_idx, int(n_out)).to(torch.bfloat16)
     return _Transition.apply(_f32c(points), knn_idx, int(n_out))
 
 
@@ -1180,6 +1330,16 @@ def linear_bn_act(x, weight, bias, bn, training, slope, residual=None):
     shape = x.shape
     x2d = x.reshape(-1, shape[-1])
     N = weight.shape[0]
+    if _INFER_BF16 and not training:
+        scale, shift = _bn_affine(bias, bn)
+        res2d = residual.reshape(-1, N) if residual is not None else None
+        if _bf16_gemm_ok(x2d):
+            out = linear_bf16(to_bf16_rows(x2d), _bf16_weight(weight), scale, shift, float(slope), res2d)
+        else:  # K = 3 / 16 layers: a few kFLOP per point, library GEMM in fp32, one rounding at the end
+            y = torch.nn.functional.linear(x2d.float(), weight) * scale + shift
+            y = torch.nn.functional.leaky_relu(y, float(slope))
+            out = (y if res2d is None else y + res2d.float()).to(torch.bfloat16)
+        return out.view(*shape[:-1], N)
     if _tc_ok(x2d, weight):
         res2d = _f32c(residual.reshape(-1, N)) if residual is not None else None
         out = LinearBNAct.apply(_f32c(x2d), weight.contiguous(), bias, bn.weight, bn.bias, bn.running_mean,
@@ -1201,6 +1361,9 @@ def linear(x, weight, bias=None):
     require_cuda(x)
     shape = x.shape
     x2d = x.reshape(-1, shape[-1])
+    if _INFER_BF16 and not torch.is_grad_enabled() and _bf16_gemm_ok(x2d):
+        y = linear_bf16(to_bf16_rows(x2d), _bf16_weight(weight), None, bias.detach() if bias is not None else None)
+        return y.view(*shape[:-1], weight.shape[0])
     if _tc_ok(x2d, weight):
         x2d = _f32c(x2d)
         y = LinearTC.apply(x2d, weight.contiguous(), bias)
@@ -1278,6 +1441,7 @@ class _GeoScope:
         self.stream.wait_stream(cur)  # fork: everything issued so far (the input cloud) is visible
         self.fps_stream.wait_stream(cur)
         self.cache = {}      # coordinate-space kNN results of this forward, by operand identity
+        self.csr = {}        # reverse-neighbour lists of the transitions of this forward, by index-tensor identity
         self.fps_cache = {}  # prefetched (FPS indices, sampled coordinates), by operand identity
         self.events = {}     # tensor storage address -> event recorded after its producer
         self.keep = []       # keeps those tensors (hence their addresses) alive for the scope

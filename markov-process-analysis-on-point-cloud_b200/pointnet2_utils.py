@@ -80,7 +80,7 @@ class LocalTrans(nn.Module):
             # conv_res.linear(centre) are computed inside one kernel; BatchNorm + LeakyReLU of conv_res follow
             fused_res = self.residual is True and self.conv_res.bn_flag is not True
             lin = self.conv_res.linear
-            context, res = ops.AttnXyz.apply(features.contiguous(),
+            context, res = ops.AttnXyz.apply(features.float().contiguous(),
                                              FPS_idx.contiguous() if FPS_idx is not None else None,
                                              idx.contiguous(), self.q.weight, self.q.bias, self.k.weight, self.k.bias,
                                              self.v.weight, self.v.bias, lin.weight if fused_res else None,
@@ -97,6 +97,10 @@ class LocalTrans(nn.Module):
             return self.ffn(context, residual=residual)
         center = index_points(features, FPS_idx) if FPS_idx is not None else features
         residual = self.conv_res(center) if self.residual is True else center
+        if ops.bf16_active() and not self.training and center.shape[-1] % 64 == 0 and self.out_c % 8 == 0:
+            context = ops.feat_attention_bf16(center, features, idx, self.q.weight, self.q.bias, self.k.weight,
+                                              self.k.bias, self.v.weight, self.v.bias)
+            return self.ffn(context, residual=residual)
         if ops.feat_attention_fusable(center, self.q.weight):
             context = ops.FeatAttention.apply(center.contiguous(), features.contiguous(), idx.contiguous(),
                                               self.q.weight, self.q.bias, self.k.weight, self.k.bias,

@@ -218,5 +218,6 @@ class KeepHighResolutionModule(nn.Module):
                                                         FPS_idx=fps_idx)
                 base = sub
         final = self.conv4(self.conv3(feat))  # [B,32,1024]
-        pooled = torch.cat((final.max(dim=1)[0], final.mean(dim=1)), 1)  # adaptive max / avg pool (:632-634)
+        pooled = torch.cat((final.max(dim=1)[0], final.float().mean(dim=1).to(final.dtype)), 1)  # max / avg pool (:632-634)
+        pooled = pooled.float()  # (bf16 inference path: the small head runs in fp32)
         return self.lrelu(self.bn(self.final_class(pooled)))

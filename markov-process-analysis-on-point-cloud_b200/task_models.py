@@ -107,7 +107,8 @@ class get_model(nn.Module):
 
     @on_tensor_device
     def forward(self, xyz, cls_label):
-        if xyz.is_cuda and ops.split_supported(xyz.shape[2], 256, self.conv8.linear.out_features):
+        if (xyz.is_cuda and ops.split_supported(xyz.shape[2], 256, self.conv8.linear.out_features)
+                and not (ops.bf16_active() and not self.training)):
             # 640 of conv8's 896 input channels are constant over a cloud's points (global pools, label embedding):
             # project them once per cloud instead of once per point (ops.LinearBNActSplit) -- same arithmetic
             branch1_xyz, per_point, per_cloud = self.keepHigh.forward_parts(xyz, normal=xyz, label=cls_label)

@@ -180,6 +180,33 @@ def test_transition_vs_oracle(mpc, orc, B, S, ratio, C, K):
     assert (o0.detach().abs().sum(-1) == 0).any()  # the case includes unreached rows (-> 0)
 
 
+@pytest.mark.parametrize("C", [4, 8, 12, 32, 64, 128, 256, 512])
+def test_transition_group_kernel_shapes(mpc, orc, C):
+    """Every lane grouping of the cooperative gather kernel (C/4 = 1 .. 128 lanes per row; C = 12 takes the per-thread
+    kernel), lists longer than a lane group (many sources pointing at one target), empty lists, bit-identical to the
+    oracle's ascending-source summation; and the reverse-neighbour lists shared between two feature tensors."""
+    g = torch.Generator().manual_seed(C)
+    B, S, K, N = 2, 300, 8, 640
+    pts = torch.randn(B, S, C, generator=g)
+    pts[1, 7, 0] = 0.0
+    idx = torch.randint(0, N, (B, S, K), generator=g)
+    idx[0, :150, 0] = 17          # a list of 150 sources: longer than any lane group
+    idx[1, :40, 3] = 5            # and one of 40
+    idx[:, :, 1] = idx[:, :, 0]   # duplicates inside a row count once
+    o0 = orc.upsample(pts, idx, n_out=N)
+    o1 = mpc.ops.upsample(pts.cuda(), idx.cuda(), n_out=N)
+    assert torch.equal(o1.cpu(), o0)
+    # one neighbour table, two feature tensors: the lists are built once inside a geometry scope
+    pts2 = torch.randn(B, S, C, generator=g)
+    idx_g = idx.cuda()
+    n0 = mpc.ops.launches()
+    with mpc.ops.geometry_scope():
+        a = mpc.ops.upsample(pts.cuda(), idx_g, n_out=N)
+        b = mpc.ops.upsample(pts2.cuda(), idx_g, n_out=N)
+    assert mpc.ops.launches() - n0 == 3  # build + apply + apply
+    assert torch.equal(a.cpu(), o0) and torch.equal(b.cpu(), orc.upsample(pts2, idx, n_out=N))
+
+
 # ---------------------------------------------------------------------------------------------- three_interpolate
 @pytest.mark.parametrize("C", [5, 64])
 def test_three_interpolate(mpc, orc, C):

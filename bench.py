@@ -12,6 +12,8 @@ cpu_baseline / clocks:
   cls1024_train   configs[4]: data-parallel TRAINING STEP of the ModelNet40-shaped classifier, 32 clouds x 1024 points
                   per GPU (256 at 8 GPUs: weak), forward, label-smoothed loss, backward, gradient all-reduce, Adam.
   cls_fwd         configs[0]: classifier forward, 16 x 1024, eval() -- the reference's own CPU-runnable case.
+  cls_fwd_bf16    the same forward through the bf16 inference path (ops.bf16_inference(): a separate dtype "bf16"
+                  record; the headline and every other record stay fp32, the reference's precision).
   partseg2048     configs[1]: ShapeNetPart-shaped part segmentation, 32 x 2048 per GPU, forward + backward.
 
 (configs[3], the op sweep, is scratch/op_sweep.py -> profiles/.)
@@ -39,6 +41,7 @@ BatchNorm over a per-GPU batch of ONE block is undefined (nn.BatchNorm1d raises,
 workload must be the same network at 8, 4, 2 and 1 blocks per GPU.  Everything else runs in train mode.
 """
 import argparse
+import contextlib
 import ctypes
 import importlib
 import json
@@ -56,7 +59,7 @@ if ROOT not in sys.path:
 PKG = "markov-process-analysis-on-point-cloud_b200"
 UNIT = "clouds/s"
 HEADLINE = "sem24k"
-ORDER = ("sem24k", "cls1024_train", "cls_fwd", "partseg2048")
+ORDER = ("sem24k", "cls1024_train", "cls_fwd", "cls_fwd_bf16", "partseg2048")
 METRIC = ("point clouds/s (24 000-point blocks fwd+bwd, 8 blocks sharded over the GPUs; sub-records: 1024-point "
           "classifier training step and forward, 2048-point part segmentation fwd+bwd)")
 
@@ -143,6 +146,7 @@ class Workload:
         self.adam = False
         self.train = True
         self.eval_blocks = ()
+        self.bf16 = False
         if key == "sem24k":
             self.total = 8
             if self.total % world:
@@ -166,12 +170,14 @@ class Workload:
             self.title = ("data-parallel training step of the ModelNet40-shaped classifier, 32 x 1024 points per GPU "
                           "(256 at 8 GPUs), fwd + smoothed loss + bwd + gradient all-reduce + Adam (BASELINE configs[4])")
             self.cpu_B, self.cpu_steps = 32, 3
-        elif key == "cls_fwd":
+        elif key in ("cls_fwd", "cls_fwd_bf16"):
             self.B, self.N, self.classes, self.scaling = 16, 1024, 40, "weak"
             self.kind, self.cfg_index = "cls", 0
             self.train = False
+            self.bf16 = key.endswith("bf16")
             self.title = ("ModelNet40-shaped classification forward, batch 16 x 1024 points per GPU, eval() "
-                          "(BASELINE configs[0])")
+                          "(BASELINE configs[0])" + (", bf16 inference path (activations in bf16, fp32 accumulation, "
+                                                     "indices from fp32 arithmetic)" if self.bf16 else ""))
             self.cpu_B, self.cpu_steps = 16, 5
         else:
             raise SystemExit("bench.py: unknown workload %r" % key)
@@ -341,7 +347,8 @@ class Step:
             if pack and self.bucket is not None and self.world > 1:
                 self.bucket.pack()
             return res
-        with torch.no_grad(), self.mpc.ops.index_tape(fps_starts=starts):
+        mode = self.mpc.ops.bf16_inference() if wl.bf16 else contextlib.nullcontext()
+        with torch.no_grad(), mode, self.mpc.ops.index_tape(fps_starts=starts):
             return wl.forward(self.model, inputs)
 
     def ensure_bucket(self):
@@ -411,7 +418,9 @@ class GraphedStep:
 GEMM_ENTRIES = ("mpc_linear_fwd_f32", "mpc_linear_dgrad_f32", "mpc_linear_wgrad_f32")
 # C-ABI entry point -> the CUDA kernel that does its work (the three GEMM entry points share one kernel)
 KERNEL_OF = {n: "linear_3xtf32_kernel" for n in GEMM_ENTRIES}
-KERNEL_OF.update({"mpc_knn_f32": "knn3 / knn_tiled / knn64 kernels (FP32 SIMT, by shape)",
+KERNEL_OF.update({"mpc_linear_bf16": "linear_bf16_kernel (tcgen05 kind::f16, fused BatchNorm affine + LeakyReLU + residual)",
+                  "mpc_knn3_grid_f32": "knn3_grid_kernel (uniform-grid coordinate search) + grid build",
+                  "mpc_knn_f32": "knn3 / knn_tiled / knn64 kernels (FP32 SIMT, by shape)",
                   "mpc_knn_tc_f32": "knn_tc_kernel (tcgen05 filter + exact refinement)",
                   "mpc_fps_f32": "fps kernels (cta / cluster / grid by size)"})
 
@@ -746,7 +755,7 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
             "metric": METRIC if wl.key == HEADLINE else "point clouds/s (%s)" % wl.key,
             "value": clouds / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": wl.config(),
+            "dtype": "bf16" if wl.bf16 else "f32", "data": "synthetic", "config": wl.config(),
             "method": {"clouds_per_gpu": B, "parallelism": par,
                        "l2": "256 MiB flush buffer written between timed steps; step working set >> 126 MB L2",
                        "launch": "CUDA graph replay" if graphed else "eager launches",

@@ -305,6 +305,17 @@ int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, int64_t l
                          int64_t M, int64_t K, int64_t N, float* zero_buf, int64_t zero_count, mpc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * fp32 inference form of the shared-MLP block (the reference's `Linear` in eval(), R/modules/pointnet2_utils.py:413-425
+ * + the residual of :515,574,640-709): the 3xTF32 tcgen05 GEMM of mpc_linear_fwd_f32 with the BatchNorm (running
+ * statistics) affine map, the LeakyReLU and the residual add in its epilogue -- no separate normalise pass:
+ *     y[m,n] = LeakyReLU_slope(acc[m,n] * scale[n] + shift[n]) (+ residual[m,n])
+ * Operand constraints as mpc_linear_fwd_f32; y rows 16-byte aligned (ldy % 4 == 0); residual [M,N] f32 (ldr) or NULL.
+ * ------------------------------------------------------------------------------------------------- */
+int mpc_linear_affine_act_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* scale,
+                              const float* shift, float slope, const float* residual, int64_t ldr, float* y,
+                              int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * bf16-I/O shared-MLP block for inference: the reference's whole `Linear` block in eval() -- nn.Linear -> BatchNorm1d
  * with running statistics -> LeakyReLU, R/modules/pointnet2_utils.py:413-425 -- plus the residual that LocalTrans /
  * Fuse add to it (:515,574,640-709), as ONE tcgen05 kernel (kind::f16, bf16 operands, fp32 accumulation in TMEM):

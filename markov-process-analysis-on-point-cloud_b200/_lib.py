@@ -54,6 +54,7 @@ SIGNATURES = {
     "mpc_bn_act_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
                            _i64, _i64, _i64, _ptr],
     "mpc_linear_fwd_f32": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr],
+    "mpc_linear_affine_act_f32": [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _f32, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr],
     "mpc_bn_finalize_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i64, _i64, _ptr],
     "mpc_linear_wgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr],
     "mpc_linear_dgrad_f32": [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
@@ -70,7 +71,7 @@ KERNELS_PER_CALL = {
     "mpc_gather_i64": 1, "mpc_gather_bf16": 1, "mpc_gather_bwd_bf16": 1, "mpc_reduction_scratch_bytes": 0, "mpc_transition_fwd_f32": 3, "mpc_transition_bwd_f32": 1, "mpc_transition_fwd_csr_f32": 4, "mpc_transition_csr_build": 3, "mpc_transition_csr_apply_f32": 1,
     "mpc_three_interpolate_fwd_f32": 2, "mpc_three_interpolate_bwd_f32": 1, "mpc_attn_feat_fwd_f32": 1, "mpc_attn_feat_fwd_bf16": 1, "mpc_linear_bf16": 1, "mpc_f32_to_bf16": 1,
     "mpc_attn_feat_bwd_f32": 1, "mpc_attn_xyz_fwd_f32": 1, "mpc_attn_xyz_bwd_f32": 1, "mpc_bn_stats_f32": 1, "mpc_col_sum_f32": 1, "mpc_bn_finalize_f32": 1, "mpc_bn_act_fwd_sums_f32": 1,
-    "mpc_bn_act_fwd_f32": 1, "mpc_bn_act_bwd_f32": 2, "mpc_linear_fwd_f32": 1,
+    "mpc_bn_act_fwd_f32": 1, "mpc_bn_act_bwd_f32": 2, "mpc_linear_fwd_f32": 1, "mpc_linear_affine_act_f32": 1,
     "mpc_linear_wgrad_f32": 1,
     "mpc_linear_dgrad_f32": 1,
     "mpc_smooth_ce_fwd_f32": 1, "mpc_smooth_ce_bwd_f32": 1,

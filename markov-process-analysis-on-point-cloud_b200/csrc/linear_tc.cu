@@ -32,7 +32,7 @@ constexpr int SPLIT_THREADS = 256;
 constexpr int MAX_STAGES = 6;
 
 constexpr int STAGING_BYTES = BLOCK_M * 128;  // one 32-column slab of a tile: 128 rows x 128 B
-constexpr int EPI_BIAS_BYTES = 1024;  // bias for up to 256 columns
+constexpr int EPI_BIAS_BYTES = 2048;  // bias (shift) and scale for up to 256 columns
 
 struct Params {
     int M, N, K;
@@ -56,6 +56,12 @@ struct Params {
                       // accumulated from the staged tile while it is still in shared memory (must be zero on entry)
     float4* zero_ptr; // optional: buffer this launch clears on behalf of a LATER launch in the same stream (the
     long long zero_n4;//   split-reduction target of the weight-gradient GEMM that follows a dgrad), in float4 units
+    // inference epilogue (mpc_linear_affine_act_f32): y = LeakyReLU_slope(acc * scale[n] + bias[n]) (+ residual[m,n]) --
+    // BatchNorm with running statistics folded to a per-channel affine map, activation and residual add in registers
+    const float* scale;     // [N] or null (null: the plain y = acc + bias epilogue)
+    float slope;
+    const float* residual;  // [M, ldr] or null
+    int ldr;
 };
 
 // debug timeline: role r in [0,4) records up to 255 timestamps
@@ -311,6 +317,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     float v = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
                     if (p.bias2 && n0 + i < p.N) v += __ldg(p.bias2 + (size_t)grp * p.N + n0 + i);
                     bias_s[i] = v;
+                    if (p.scale) bias_s[256 + i] = n0 + i < p.N ? __ldg(p.scale + n0 + i) : 1.0f;
                 }
                 epi_barrier();
                 bias_n0 = n0;
@@ -338,6 +345,34 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             bulk_wait_read0();
                     }
                     __syncwarp();
+                    if (p.scale) {
+                        // inference epilogue: affine (BatchNorm with running statistics) + LeakyReLU + residual
+                        const bool row_ok = lane < rows_valid;
+                        const float* rrow = p.residual ? p.residual + (size_t)row * p.ldr + n0 + c : nullptr;
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const uint32_t* src = q4 < 4 ? &r0[q4 * 4] : &r1[(q4 - 4) * 4];
+                            float v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float t = fmaf(__uint_as_float(src[u]), bias_s[256 + c + q4 * 4 + u],
+                                                     bias_s[c + q4 * 4 + u]);
+                                v[u] = t > 0.f ? t : t * p.slope;
+                            }
+                            if (rrow && row_ok) {
+                                if (n0 + c + q4 * 4 + 4 <= p.N && (p.ldr & 3) == 0) {
+                                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow) + q4);
+                                    v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+                                } else {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u)
+                                        if (n0 + c + q4 * 4 + u < p.N) v[u] += __ldg(rrow + q4 * 4 + u);
+                                }
+                            }
+                            srow[q4 ^ (lane & 7)] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]),
+                                                               __float_as_uint(v[2]), __float_as_uint(v[3]));
+                        }
+                    } else {
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {  // 8 x 16 B of this row, 128B-swizzled like the TMA box expects
                         const uint32_t* src = q4 < 4 ? &r0[q4 * 4] : &r1[(q4 - 4) * 4];
@@ -347,6 +382,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         o.z = __float_as_uint(__uint_as_float(src[2]) + bias_s[c + q4 * 4 + 2]);
                         o.w = __float_as_uint(__uint_as_float(src[3]) + bias_s[c + q4 * 4 + 3]);
                         srow[q4 ^ (lane & 7)] = o;
+                    }
                     }
                     fence_async_proxy();
                     __syncwarp();
@@ -477,9 +513,10 @@ static cudaError_t launch_pdl(int grid, size_t smem, cudaStream_t st, const CUte
 }  // namespace tc
 }  // namespace mpc
 
-MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
-                               int64_t ldy, double* stat_scratch, const float* group_bias, int64_t rows_per_group,
-                               int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+static int linear_fwd_impl(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                           int64_t ldy, double* stat_scratch, const float* group_bias, int64_t rows_per_group,
+                           int64_t M, int64_t K, int64_t N, const float* scale, float slope, const float* residual,
+                           int64_t ldr, mpc_stream_t stream) {
     using namespace mpc;
     using namespace mpc::tc;
     if (!x || !w || !y || M <= 0 || K <= 0 || N <= 0) return MPC_ERR_INVALID;
@@ -521,6 +558,11 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     p.splits = 1;
     p.k_chunks = (int)(K / BLOCK_K);
     p.trace = g_trace;
+    p.scale = scale;
+    p.slope = slope;
+    p.residual = residual;
+    p.ldr = (int)ldr;
+    if (scale && !tma_out) return MPC_ERR_UNSUPPORTED;
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, x, M, K, ldx, BLOCK_M);
     if (rc) return rc;
@@ -537,6 +579,21 @@ MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
     const int grid = total_tiles < kNumSMs ? total_tiles : kNumSMs;
     MPC_CUDA(launch_pdl(grid, smem, (cudaStream_t)stream, map_a, map_b, map_y, p));
     return MPC_OK;
+}
+
+MPC_API int mpc_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                               int64_t ldy, double* stat_scratch, const float* group_bias, int64_t rows_per_group,
+                               int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+    return linear_fwd_impl(x, ldx, w, ldw, bias, y, ldy, stat_scratch, group_bias, rows_per_group, M, K, N, nullptr,
+                           1.0f, nullptr, 0, stream);
+}
+
+MPC_API int mpc_linear_affine_act_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* scale,
+                                      const float* shift, float slope, const float* residual, int64_t ldr, float* y,
+                                      int64_t ldy, int64_t M, int64_t K, int64_t N, mpc_stream_t stream) {
+    if (!scale || !shift || (residual && ldr < N)) return MPC_ERR_INVALID;
+    return linear_fwd_impl(x, ldx, w, ldw, shift, y, ldy, nullptr, nullptr, 0, M, K, N, scale, slope, residual, ldr,
+                           stream);
 }
 
 // grad_w[N,K] = gy[M,N]^T x[M,K]: both operands are contiguous along the OUTPUT dimensions (MN-major for the
@@ -583,6 +640,10 @@ MPC_API int mpc_linear_wgrad_f32(const float* gy, int64_t ldg, const float* x, i
     p.zero_n4 = 0;
     p.tma_out = ((ldw & 3) == 0 && ((uintptr_t)gw & 15u) == 0) ? 1 : 0;
     p.trace = g_trace;
+    p.scale = nullptr;
+    p.slope = 1.0f;
+    p.residual = nullptr;
+    p.ldr = 0;
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, gy, M, N, ldg, 32, true);  // dims {N, M}: inner = output index n, box 32 x 32
     if (rc) return rc;
@@ -653,6 +714,10 @@ MPC_API int mpc_linear_dgrad_f32(const float* gy, int64_t ldg, const float* w, i
     p.b_mn = 1;
     p.stat_sum = nullptr;
     p.trace = g_trace;
+    p.scale = nullptr;
+    p.slope = 1.0f;
+    p.residual = nullptr;
+    p.ldr = 0;
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, gy, M, N, ldg, BLOCK_M);        // K-major: box 32 reduction columns x 128 rows
     if (rc) return rc;

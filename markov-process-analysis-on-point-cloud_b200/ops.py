@@ -293,6 +293,15 @@ def query_ball_point(radius, nsample, xyz, new_xyz, cuda=False):
 # searches see the bf16 features widened to fp32.
 # ------------------------------------------------------------------------------------------------------
 _INFER_BF16 = False
+# eval() forward without autograd: Linear -> BatchNorm(running statistics) -> LeakyReLU (+ residual) as ONE GEMM launch
+# (affine map + activation + residual in the epilogue); MPC_FUSE_EVAL=0 keeps the separate normalise kernel (A/B runs)
+_FUSE_EVAL = os.environ.get("MPC_FUSE_EVAL", "1") == "1"
+
+
+def set_fuse_eval(on):
+    global _FUSE_EVAL
+    _FUSE_EVAL = bool(on)
+
 
 
 @contextlib.contextmanager
@@ -1339,6 +1348,20 @@ def linear_bn_act(x, weight, bias, bn, training, slope, residual=None):
             y = torch.nn.functional.linear(x2d.float(), weight) * scale + shift
             y = torch.nn.functional.leaky_relu(y, float(slope))
             out = (y if res2d is None else y + res2d.float()).to(torch.bfloat16)
+        return out.view(*shape[:-1], N)
+    if (not training and not torch.is_grad_enabled() and _FUSE_EVAL and _tc_ok(x2d, weight) and N % 4 == 0
+            and x2d.data_ptr() % 16 == 0 and x2d.stride(0) % 4 == 0):
+        # inference: BatchNorm (running statistics) is a per-channel affine map -- it, the LeakyReLU and the residual
+        # add run in the GEMM's epilogue (mpc_linear_affine_act_f32): one launch, no normalise pass over HBM
+        scale, shift = _bn_affine(bias, bn)
+        x2d = _f32c(x2d)
+        w = weight.contiguous()
+        M, K = x2d.shape
+        res2d = _f32c(residual.reshape(-1, N)) if residual is not None else None
+        out = torch.empty(M, N, dtype=torch.float32, device=x2d.device)
+        call("mpc_linear_affine_act_f32", ptr(x2d), _i64(x2d.stride(0)), ptr(w), _i64(w.stride(0)), ptr(scale),
+             ptr(shift), ctypes.c_float(float(slope)), ptr(res2d), _i64(N if res2d is not None else 0), ptr(out), _i64(N),
+             _i64(M), _i64(K), _i64(N), algo_bytes=(M * K + M * N * (2 if res2d is not None else 1) + N * K) * 4)
         return out.view(*shape[:-1], N)
     if _tc_ok(x2d, weight):
         res2d = _f32c(residual.reshape(-1, N)) if residual is not None else None

@@ -254,3 +254,33 @@ def test_bn_backward_reads_strided_grad_rows(mpc):
 
     for a, b in zip(run(False), run(True)):
         torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("M,K,N,res", [(4096, 64, 64, True), (1000, 128, 256, False), (16384, 512, 1024, True),
+                                       (130, 32, 64, True), (2048, 896, 512, False)])
+def test_eval_block_fused_into_gemm_epilogue(mpc, M, K, N, res):
+    """Inference form of the shared-MLP block (mpc_linear_affine_act_f32: BatchNorm affine + LeakyReLU + residual in the
+    tcgen05 GEMM's epilogue) against the unfused kernels and against nn.Linear -> nn.BatchNorm1d.eval() -> LeakyReLU."""
+    torch.manual_seed(M + N)
+    m = mpc.pointnet2_utils.Linear(K, N, bn=False).cuda().eval()
+    with torch.no_grad():
+        m.norm2.running_mean.normal_()
+        m.norm2.running_var.uniform_(0.5, 2.0)
+        m.norm2.weight.normal_()
+        m.norm2.bias.normal_()
+    x = torch.randn(2, M // 2, K, device="cuda")
+    r = torch.randn(2, M // 2, N, device="cuda") if res else None
+    ref = torch.nn.functional.leaky_relu(m.norm2(m.linear(x.double().float()).reshape(-1, N)), 0.2).view(2, M // 2, N)
+    if res:
+        ref = ref + r
+    with torch.no_grad():
+        n0 = mpc.ops.launches()
+        fused = m(x, residual=r)
+        assert mpc.ops.launches() - n0 == 1
+        mpc.ops.set_fuse_eval(False)
+        try:
+            unfused = m(x, residual=r)
+        finally:
+            mpc.ops.set_fuse_eval(True)
+    torch.testing.assert_close(fused, unfused, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(fused, ref.detach(), rtol=2e-4, atol=2e-4)  # (nn.Linear on cuBLAS may use TF32-free fp32)

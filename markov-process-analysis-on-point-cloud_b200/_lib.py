@@ -67,7 +67,7 @@ SIGNATURES = {
 
 # kernels each entry point enqueues (cudaMemsetAsync calls not counted)
 KERNELS_PER_CALL = {
-    "mpc_fps_f32": 1, "mpc_knn_f32": 1, "mpc_knn_tc_workspace_bytes": 0, "mpc_knn_tc_f32": 3, "mpc_knn3_grid_workspace_bytes": 0, "mpc_knn3_grid_f32": 5, "mpc_ball_query_f32": 1, "mpc_gather_f32": 1, "mpc_gather_bwd_f32": 1,
+    "mpc_fps_f32": 1, "mpc_knn_f32": 1, "mpc_knn_tc_workspace_bytes": 0, "mpc_knn_tc_f32": 4, "mpc_knn3_grid_workspace_bytes": 0, "mpc_knn3_grid_f32": 5, "mpc_ball_query_f32": 1, "mpc_gather_f32": 1, "mpc_gather_bwd_f32": 1,
     "mpc_gather_i64": 1, "mpc_gather_bf16": 1, "mpc_gather_bwd_bf16": 1, "mpc_reduction_scratch_bytes": 0, "mpc_transition_fwd_f32": 3, "mpc_transition_bwd_f32": 1, "mpc_transition_fwd_csr_f32": 4, "mpc_transition_csr_build": 3, "mpc_transition_csr_apply_f32": 1,
     "mpc_three_interpolate_fwd_f32": 2, "mpc_three_interpolate_bwd_f32": 1, "mpc_attn_feat_fwd_f32": 1, "mpc_attn_feat_fwd_bf16": 1, "mpc_linear_bf16": 1, "mpc_f32_to_bf16": 1,
     "mpc_attn_feat_bwd_f32": 1, "mpc_attn_xyz_fwd_f32": 1, "mpc_attn_xyz_bwd_f32": 1, "mpc_bn_stats_f32": 1, "mpc_col_sum_f32": 1, "mpc_bn_finalize_f32": 1, "mpc_bn_act_fwd_sums_f32": 1,

@@ -35,6 +35,7 @@ __device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bi)[K], float 
 // candidate to a small per-thread queue in shared memory, and the warp drains all queues together when any of
 // them is close to full: the insertion network then runs ~20x less often and with most lanes busy.  Arrival
 // order (ascending index) is preserved, so equal distances still resolve to the lower index.
+constexpr int KNN_FEW_MAX = 48;  // listed queries per cloud up to which knn_few_kernel (one CTA per query) takes them
 constexpr int KNN_THREADS = 128;
 constexpr int KNN_Q = 8;      // queue slots per thread
 constexpr int KNN_QFLUSH = 4; // drain when any lane holds more than this many (<= KNN_Q - unroll)
@@ -488,6 +489,7 @@ knn_tiled_kernel(const float* __restrict__ ref, const float* __restrict__ qry, f
     // CTAs beyond the live range leave at once.
     const int S_live = qcount ? qcount[blockIdx.y] : S;
     if ((int)(blockIdx.x * KT_Q) >= S_live) return;
+    if (qcount && S_live <= KNN_FEW_MAX) return;  // a handful of listed queries: knn_few_kernel serves them
     extern __shared__ __align__(16) float sm[];
     float* qt = sm;                              // [C][KT_Q]   queries, transposed
     float* rt = qt + (size_t)C * KT_Q;           // [KT_CK][KT_R] reference chunk, transposed
@@ -818,6 +820,99 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
     return MPC_OK;
 }
 
+// A handful of listed queries (<= KNN_FEW_MAX per cloud): one CTA per query.  The tiled kernel works on 64-query tiles,
+// so three undecided queries cost it a full tile's sweep over the reference set on a single SM (4.4 ms at 24 000
+// points -- on the critical path of the step); here the reference rows are split over the CTA's threads, every thread
+// keeps its own sorted K-list of exact distances (the contract's expression: fma chain over c from 0, sequential
+// non-fused norms, ((-2 dot) + |q|^2) + |r|^2) and the lists are merged by K rounds of a block-wide lexicographic
+// (distance, index) arg-min: ~20 us.
+constexpr int KNN_FEW_THREADS = 256;
+
+__device__ __forceinline__ unsigned long long few_key(float d, int n) {
+    const unsigned u = __float_as_uint(d);
+    const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving map of float to unsigned
+    return ((unsigned long long)ord << 32) | (unsigned)n;
+}
+
+template <int K>
+__global__ void __launch_bounds__(KNN_FEW_THREADS)
+knn_few_kernel(const float* __restrict__ ref, const float* __restrict__ qry, float* __restrict__ dist_out,
+               int64_t* __restrict__ idx_out, int N, int S, int C, const int* __restrict__ qlist,
+               const int* __restrict__ qcount) {
+    const int b = blockIdx.y;
+    const int live = qcount[b];
+    if (live > KNN_FEW_MAX || (int)blockIdx.x >= live) return;
+    extern __shared__ __align__(16) float qs[];  // [C]
+    __shared__ unsigned long long wbest[KNN_FEW_THREADS / 32];
+    __shared__ unsigned long long round_best;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = qlist[(size_t)b * S + blockIdx.x];
+    const float* q = qry + ((size_t)b * S + s) * C;
+    for (int c = tid; c < C; c += KNN_FEW_THREADS) qs[c] = q[c];
+    __syncthreads();
+    float qn = __fmul_rn(qs[0], qs[0]);
+    for (int c = 1; c < C; ++c) qn = __fadd_rn(qn, __fmul_rn(qs[c], qs[c]));
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        bd[k] = __int_as_float(0x7f800000);
+        bi[k] = 0x7fffffff;
+    }
+    const float* rb = ref + (size_t)b * N * C;
+    for (int n = tid; n < N; n += KNN_FEW_THREADS) {
+        const float4* r4 = reinterpret_cast<const float4*>(rb + (size_t)n * C);
+        float dot = 0.f, rn = 0.f;
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 r = __ldg(r4 + c4);
+            dot = __fmaf_rn(qs[4 * c4 + 0], r.x, dot);
+            dot = __fmaf_rn(qs[4 * c4 + 1], r.y, dot);
+            dot = __fmaf_rn(qs[4 * c4 + 2], r.z, dot);
+            dot = __fmaf_rn(qs[4 * c4 + 3], r.w, dot);
+            rn = c4 == 0 ? __fmul_rn(r.x, r.x) : __fadd_rn(rn, __fmul_rn(r.x, r.x));
+            rn = __fadd_rn(rn, __fmul_rn(r.y, r.y));
+            rn = __fadd_rn(rn, __fmul_rn(r.z, r.z));
+            rn = __fadd_rn(rn, __fmul_rn(r.w, r.w));
+        }
+        const float d = sqdist_from_dot(dot, qn, rn);
+        if (d < bd[K - 1]) topk_insert<K>(bd, bi, d, n);  // ascending n within a thread: strict < keeps the lower index
+    }
+    // K rounds: block-wide arg-min over the heads of the per-thread lists; the winning thread pops its head
+    int head = 0;
+    for (int k = 0; k < K; ++k) {
+        float hd = __int_as_float(0x7f800000);
+        int hn = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j == head) {
+                hd = bd[j];
+                hn = bi[j];
+            }
+        unsigned long long key = head < K ? few_key(hd, hn) : ~0ull;
+        unsigned long long m = key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = t < m ? t : m;
+        }
+        if (lane == 0) wbest[warp] = m;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long g = wbest[0];
+            for (int w2 = 1; w2 < KNN_FEW_THREADS / 32; ++w2) g = wbest[w2] < g ? wbest[w2] : g;
+            round_best = g;
+        }
+        __syncthreads();
+        if (key == round_best && head < K) {  // keys are unique (distinct indices): exactly one thread
+            const size_t o = ((size_t)b * S + s) * K + k;
+            if (dist_out) dist_out[o] = hd;
+            idx_out[o] = hn;
+            ++head;
+        }
+        __syncthreads();
+    }
+}
+
 // Exact search for an indirect list of queries (see knn_tiled_kernel): the fallback pass of mpc_knn_tc_f32.
 int launch_knn_tiled_indirect8(const float* ref, const float* qry, float* dist_out, int64_t* idx_out, const int* qlist,
                                const int* qcount, int B, int N, int S, int C, cudaStream_t st) {
@@ -827,6 +922,10 @@ int launch_knn_tiled_indirect8(const float* ref, const float* qry, float* dist_o
     MPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(S, KT_Q), (unsigned)B);
     kern<<<grid, KT_THREADS, smem, st>>>(ref, qry, dist_out, idx_out, N, S, C, qlist, qcount);
+    MPC_LAUNCH_CHECK();
+    // (the two kernels partition the clouds by their listed-query count; each leaves the other's clouds at once)
+    knn_few_kernel<8><<<dim3((unsigned)(S < KNN_FEW_MAX ? S : KNN_FEW_MAX), (unsigned)B), KNN_FEW_THREADS,
+                        (size_t)C * sizeof(float), st>>>(ref, qry, dist_out, idx_out, N, S, C, qlist, qcount);
     MPC_LAUNCH_CHECK();
     return MPC_OK;
 }

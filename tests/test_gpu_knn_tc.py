@@ -84,6 +84,20 @@ def test_knn_tc_bit_exact_vs_oracle(mpc, orc, kind, B, N, S):
         assert fallback <= B * S // 100
 
 
+@pytest.mark.parametrize("ntie", [9, 20, 47, 48, 49, 130])
+def test_knn_tc_small_fallback_counts(mpc, orc, ntie):
+    """A group of `ntie` identical rows makes exactly those queries undecidable for the filter: up to 48 listed queries per
+    cloud go through the one-CTA-per-query kernel, more through the tiled one -- both must reproduce the oracle."""
+    ref = features(2, 3000, seed=ntie, kind="random")
+    ref[:, 100:100 + ntie] = ref[:, 7:8].clone()
+    ref[1, 2000:2003] = ref[1, 7:8].clone()
+    d0, i0 = orc.knn_point(8, ref, ref)
+    rg = ref.cuda()
+    d1, i1, fallback, _ = run_tc(mpc, rg, rg)
+    assert fallback >= (2 * ntie if ntie >= 20 else 1)  # (up to 8 ties still fit the 16-entry candidate list)
+    assert torch.equal(i1.cpu(), i0) and torch.equal(d1.cpu(), d0)
+
+
 def test_knn_tc_equals_brute_force_at_24k(mpc):
     """24 000 x 24 000 and 12 000 x 24 000 (the two largest searches of a 24 000-point block), tie-heavy features."""
     ref = features(2, 24000, seed=5, kind="relu").cuda()

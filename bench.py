@@ -21,6 +21,9 @@ cpu_baseline / clocks:
 Own arm, per workload:
   value        device-resident inputs; the step is captured once into a CUDA graph and replayed; CUDA events around
                every step, a 256 MiB buffer written between timed steps (L2 flush, outside the events); max over ranks.
+               The FPS chain (a latency chain that depends on the coordinates only) is computed one batch ahead: the
+               graph of step i samples batch i+1 on its own stream beside the forward/backward of batch i -- one
+               sampling chain and one forward/backward per step, results lag one step (--no-fps-ahead: off).
   e2e          the same step through the public module call with the step's inputs copied from pinned host memory and
                the result (loss, or the logits of the forward-only workload) read back; copies inside the timed region.
   roofline     the dominant kernel of ours in that workload's step (most device time in one instrumented step),
@@ -186,6 +189,7 @@ class Workload:
             self.fps_sizes = (self.N, self.N // 2, self.N // 4, self.N // 8)
         else:
             self.fps_sizes = (1024, 512, 256, 128, 64)
+        self.fps_npoints = tuple(n // 2 for n in self.fps_sizes)  # every sampling step halves its state
 
     # ---- identical in both arms (the driver compares them)
     def config(self):
@@ -379,22 +383,35 @@ class Step:
 class GraphedStep:
     """The same step captured once into a CUDA graph (static input buffers, private memory pool) and replayed:
     the ~1000-1800 kernel launches per step otherwise make the step CPU-launch-bound.  The NCCL all-reduce runs
-    between the step graph and the optimiser graph."""
+    between the step graph and the optimiser graph.
 
-    def __init__(self, step, inputs, starts):
+    Sampling one batch ahead (default; --no-fps-ahead switches it off): the FPS chain of a forward depends on nothing
+    but the input coordinates and is a pure latency chain (22 500 sequential rounds per 24 000-point block), so the graph
+    of step i also runs the chain for the batch of step i+1, on its own stream beside the forward / backward of batch i,
+    and hands the indices over at the end (ops.sampling_pyramid / ops.sampled_ahead).  Every replay therefore still
+    performs exactly one forward(+backward) and one full sampling chain; what it returns belongs to the batch passed to
+    the PREVIOUS call (one step of pipeline latency, primed by the first batch)."""
+
+    def __init__(self, step, inputs, starts, ahead=True):
         self.step = step
+        self.ahead = ahead
+        wl, ops = step.wl, step.mpc.ops
         self.inputs = [t.clone() for t in inputs]
         self.starts = [s.clone() for s in starts]
+        if ahead:  # self.inputs / self.starts receive the NEXT batch; self.cur / self.pyr are what the step consumes
+            self.cur = [t.clone() for t in inputs]
+            self.pyr = [t.clone() for t in ops.sampling_pyramid(self._coords(self.cur), wl.fps_npoints, self.starts)]
+            self.fps_stream = torch.cuda.Stream(priority=-1)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm the allocator / autograd on the capture stream
             for _ in range(2):
-                step.device_part(self.inputs, self.starts)
+                self._part()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.res = step.device_part(self.inputs, self.starts)
+            self.res = self._part()
         self.gopt = None
         if step.opt is not None:
             if step.world > 1:
@@ -402,6 +419,28 @@ class GraphedStep:
             self.gopt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.gopt):
                 step.opt.step()
+
+    @staticmethod
+    def _coords(inputs):
+        return inputs[0].permute(0, 2, 1).contiguous()  # [B,3,N] -> [B,N,3], as the models do
+
+    def _part(self):
+        if not self.ahead:
+            return self.step.device_part(self.inputs, self.starts)
+        ops, wl = self.step.mpc.ops, self.step.wl
+        cur = torch.cuda.current_stream()
+        self.fps_stream.wait_stream(cur)
+        with torch.cuda.stream(self.fps_stream):  # the sampling chain of the NEXT batch, beside this batch's step
+            nxt = ops.sampling_pyramid(self._coords(self.inputs), wl.fps_npoints, self.starts)
+        with ops.sampled_ahead(self.pyr):
+            res = self.step.device_part(self.cur, [])
+        cur.wait_stream(self.fps_stream)
+        for d, s in zip(self.pyr, nxt):
+            d.copy_(s)
+            s.record_stream(cur)
+        for d, s in zip(self.cur, self.inputs):
+            d.copy_(s)
+        return res
 
     def __call__(self, inputs, starts):
         for d, s in zip(self.inputs, inputs):
@@ -685,7 +724,7 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
     graphed = False
     if not args.no_graph:
         try:
-            run_step = GraphedStep(step, inputs, device_starts())
+            run_step = GraphedStep(step, inputs, device_starts(), ahead=not args.no_fps_ahead)
             graphed = True
         except Exception as e:  # noqa: BLE001 -- report and fall back to eager launches
             print("bench.py: CUDA graph capture failed (%s: %s); timing eager launches" % (type(e).__name__, e),
@@ -759,6 +798,9 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
             "method": {"clouds_per_gpu": B, "parallelism": par,
                        "l2": "256 MiB flush buffer written between timed steps; step working set >> 126 MB L2",
                        "launch": "CUDA graph replay" if graphed else "eager launches",
+                       "sampling": ("the FPS chain of batch i+1 runs inside step i beside the forward/backward of batch i "
+                                    "(one sampling chain and one forward/backward per step; results lag one step)"
+                                    if graphed and not args.no_fps_ahead else "inside the forward"),
                        "points_per_s": clouds * wl.N / (dev_ms / 1e3)},
             "e2e": {"value": clouds / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
@@ -840,6 +882,8 @@ def main():
                     "cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
+    ap.add_argument("--no-fps-ahead", action="store_true", help="keep the FPS chain inside the forward it belongs to "
+                    "instead of computing it one batch ahead (see GraphedStep)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

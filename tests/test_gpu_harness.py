@@ -65,3 +65,37 @@ def test_vote_segment_graph_equals_eager(mpc, orc, golden_specs):
     target[0, 0], target[1, 0] = 12, 47
     pred, correct, seen, ious = h.segmentation_metrics(out[0], target)
     assert pred.shape == (2, 2048) and seen == 4096 and len(ious["Chair"]) == 1 and len(ious["Table"]) == 1
+
+
+def test_sampling_one_batch_ahead_reproduces_the_plain_step(mpc):
+    """bench.py's graph-captured step with the FPS chain computed one batch ahead (ops.sampling_pyramid /
+    ops.sampled_ahead) returns, one call later, exactly the loss the plain step computes for the same batch and start
+    indices -- the sampling indices are the same, so the forward is the same."""
+    import argparse
+    import bench
+
+    wl = bench.Workload("cls1024_train", 1)
+    wl.B = 8
+    dev = torch.device("cuda")
+    step = bench.Step(wl, mpc, dev, 1)
+    step.model.drop1.p = step.model.drop2.p = 0.0  # (the masks would differ from run to run)
+    gen = torch.Generator().manual_seed(3)
+    batches = [[t.to(dev) for t in wl.synth(wl.B, gen)] for _ in range(3)]
+    starts = [[s.to(dev) for s in wl.starts(wl.B, gen)] for _ in range(3)]
+    plain = []
+    for b, s in zip(batches, starts):
+        plain.append(float(step.device_part(b, [x.clone() for x in s]).detach()))
+    # sampling_pyramid == the indices the forward computes itself
+    rec = []
+    with mpc.ops.index_tape(record=rec, fps_starts=[x.clone() for x in starts[0]]):
+        wl.forward(step.model, batches[0])
+    own = [i for k, i in rec if k == "fps"]
+    ahead = mpc.ops.sampling_pyramid(batches[0][0].permute(0, 2, 1).contiguous(), wl.fps_npoints, starts[0])
+    assert len(own) == len(ahead) == 5 and all(torch.equal(a, b) for a, b in zip(own, ahead))
+    g = bench.GraphedStep(step, batches[0], starts[0], ahead=True)
+    # call i hands over batch i+1 and returns the result of batch i
+    got = []
+    for i in (1, 2, 0):
+        got.append(float(g(batches[i], starts[i]).detach()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(got, [plain[0], plain[1], plain[2]], rtol=2e-5)

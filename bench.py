@@ -23,7 +23,7 @@ Own arm, per workload:
                every step, a 256 MiB buffer written between timed steps (L2 flush, outside the events); max over ranks.
                The FPS chain (a latency chain that depends on the coordinates only) is computed one batch ahead: the
                graph of step i samples batch i+1 on its own stream beside the forward/backward of batch i -- one
-               sampling chain and one forward/backward per step, results lag one step (--no-fps-ahead: off).
+               sampling chain and one forward/backward per step, results lag (--fps-ahead 0: off; default 2: see GraphedStep).
   e2e          the same step through the public module call with the step's inputs copied from pinned host memory and
                the result (loss, or the logits of the forward-only workload) read back; copies inside the timed region.
   roofline     the dominant kernel of ours in that workload's step (most device time in one instrumented step),
@@ -389,19 +389,31 @@ class GraphedStep:
     but the input coordinates and is a pure latency chain (22 500 sequential rounds per 24 000-point block), so the graph
     of step i also runs the chain for the batch of step i+1, on its own stream beside the forward / backward of batch i,
     and hands the indices over at the end (ops.sampling_pyramid / ops.sampled_ahead).  Every replay therefore still
-    performs exactly one forward(+backward) and one full sampling chain; what it returns belongs to the batch passed to
-    the PREVIOUS call (one step of pipeline latency, primed by the first batch)."""
+    performs exactly one forward(+backward) and one full sampling chain's worth of rounds; what it returns belongs to a
+    batch passed to an EARLIER call (`ahead` steps of pipeline latency, primed by the first batch)."""
 
-    def __init__(self, step, inputs, starts, ahead=True):
+    def __init__(self, step, inputs, starts, ahead=2):
         self.step = step
         self.ahead = ahead
         wl, ops = step.wl, step.mpc.ops
         self.inputs = [t.clone() for t in inputs]
         self.starts = [s.clone() for s in starts]
-        if ahead:  # self.inputs / self.starts receive the NEXT batch; self.cur / self.pyr are what the step consumes
+        if ahead:
+            # self.inputs / self.starts receive the batch handed in by a call; self.cur / self.pyr are what the step
+            # consumes.  ahead = 1: the whole chain of the handed-in batch runs in this step.  ahead = 2: the chain is
+            # cut after its first level (more than half of the rounds: 12 000 of 22 500 on a 24 000-point block); this
+            # step runs the first level of the handed-in batch and the remaining levels of the batch handed in one call
+            # earlier (self.mid*), so no step waits for more than the longer of the two segments.
+            nl = len(wl.fps_npoints)
             self.cur = [t.clone() for t in inputs]
             self.pyr = [t.clone() for t in ops.sampling_pyramid(self._coords(self.cur), wl.fps_npoints, self.starts)]
             self.fps_stream = torch.cuda.Stream(priority=-1)
+            if ahead >= 2:
+                self.mid = [t.clone() for t in inputs]
+                self.mid_starts = [s.clone() for s in starts]
+                idx0, base1 = ops.sampling_pyramid(self._coords(self.mid), wl.fps_npoints, self.starts, levels=(0, 1))
+                self.mid_idx0, self.mid_base = idx0[0].clone(), base1.clone()
+                self.fps_stream2 = torch.cuda.Stream(priority=-1)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm the allocator / autograd on the capture stream
@@ -428,18 +440,42 @@ class GraphedStep:
         if not self.ahead:
             return self.step.device_part(self.inputs, self.starts)
         ops, wl = self.step.mpc.ops, self.step.wl
+        nl = len(wl.fps_npoints)
         cur = torch.cuda.current_stream()
         self.fps_stream.wait_stream(cur)
-        with torch.cuda.stream(self.fps_stream):  # the sampling chain of the NEXT batch, beside this batch's step
-            nxt = ops.sampling_pyramid(self._coords(self.inputs), wl.fps_npoints, self.starts)
+        if self.ahead >= 2:
+            self.fps_stream2.wait_stream(cur)
+            with torch.cuda.stream(self.fps_stream):   # first level of the batch handed in by this call
+                idx0, base1 = ops.sampling_pyramid(self._coords(self.inputs), wl.fps_npoints, self.starts, levels=(0, 1))
+            with torch.cuda.stream(self.fps_stream2):  # remaining levels of the batch handed in one call earlier
+                rest, _ = ops.sampling_pyramid(None, wl.fps_npoints, self.mid_starts, levels=(1, nl), base=self.mid_base)
+            nxt = [self.mid_idx0] + rest
+        else:
+            with torch.cuda.stream(self.fps_stream):   # the whole chain of the handed-in batch
+                nxt = ops.sampling_pyramid(self._coords(self.inputs), wl.fps_npoints, self.starts)
         with ops.sampled_ahead(self.pyr):
             res = self.step.device_part(self.cur, [])
         cur.wait_stream(self.fps_stream)
-        for d, s in zip(self.pyr, nxt):
-            d.copy_(s)
-            s.record_stream(cur)
-        for d, s in zip(self.cur, self.inputs):
-            d.copy_(s)
+        if self.ahead >= 2:
+            cur.wait_stream(self.fps_stream2)
+            for d, s in zip(self.pyr, nxt):
+                d.copy_(s)
+            for d, s in zip(self.cur, self.mid):
+                d.copy_(s)
+            self.mid_idx0.copy_(idx0[0])
+            self.mid_base.copy_(base1)
+            for d, s in zip(self.mid, self.inputs):
+                d.copy_(s)
+            for d, s in zip(self.mid_starts, self.starts):
+                d.copy_(s)
+            for t in rest + idx0 + [base1]:
+                t.record_stream(cur)
+        else:
+            for d, s in zip(self.pyr, nxt):
+                d.copy_(s)
+                s.record_stream(cur)
+            for d, s in zip(self.cur, self.inputs):
+                d.copy_(s)
         return res
 
     def __call__(self, inputs, starts):
@@ -724,7 +760,7 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
     graphed = False
     if not args.no_graph:
         try:
-            run_step = GraphedStep(step, inputs, device_starts(), ahead=not args.no_fps_ahead)
+            run_step = GraphedStep(step, inputs, device_starts(), ahead=args.fps_ahead)
             graphed = True
         except Exception as e:  # noqa: BLE001 -- report and fall back to eager launches
             print("bench.py: CUDA graph capture failed (%s: %s); timing eager launches" % (type(e).__name__, e),
@@ -800,7 +836,9 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
                        "launch": "CUDA graph replay" if graphed else "eager launches",
                        "sampling": ("the FPS chain of batch i+1 runs inside step i beside the forward/backward of batch i "
                                     "(one sampling chain and one forward/backward per step; results lag one step)"
-                                    if graphed and not args.no_fps_ahead else "inside the forward"),
+                                    + ("; the chain is cut after its first level and the two segments of consecutive "
+                                       "batches run side by side (results lag two steps)" if args.fps_ahead >= 2 else "")
+                                    if graphed and args.fps_ahead else "inside the forward"),
                        "points_per_s": clouds * wl.N / (dev_ms / 1e3)},
             "e2e": {"value": clouds / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
@@ -882,8 +920,9 @@ def main():
                     "cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
-    ap.add_argument("--no-fps-ahead", action="store_true", help="keep the FPS chain inside the forward it belongs to "
-                    "instead of computing it one batch ahead (see GraphedStep)")
+    ap.add_argument("--fps-ahead", type=int, default=2, choices=[0, 1, 2], help="software pipeline depth of the FPS chain "
+                    "(see GraphedStep): 0 = inside the forward it belongs to, 1 = one batch ahead, 2 = two batches ahead "
+                    "in two segments")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -311,7 +311,8 @@ fps_pruned_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ sta
 #ifdef FP_DEBUG
     long long t0 = clock64();
     unsigned long long acc[6] = {0, 0, 0, 0, 0, 0};
-#define FP_MARK(i) { long long t1 = clock64(); acc[i] += (unsigned long long)(t1 - t0); t0 = t1; }
+#define FP_MARK(i) { long long t1 = clock64(); acc[i] += (unsigned long long)(t1 - t0); t0 = t1; \
+    if (dbg && it >= 1000 && it < 1016 && lane == 0 && blockIdx.x == 0) dbg[64 + ((it - 1000) * NW + w) * 8 + i] = (unsigned long long)t1; }
 #else
 #define FP_MARK(i)
 #endif

@@ -138,20 +138,24 @@ def sampled_ahead(indices):
 
 @on_tensor_device
 @torch.no_grad()
-def sampling_pyramid(xyz, npoints, starts=None):
+def sampling_pyramid(xyz, npoints, starts=None, levels=None, base=None):
     """The sampling chain of a forward on coordinates xyz [B,N,3]: FPS to npoints[0], gather, FPS to npoints[1], ...
     -> list of int64 [B,npoint] index tensors (level i indexes level i-1's points).  `starts`: one [B] start-index
-    tensor per level (default: drawn like the reference draws them, R/modules/pointnet2_utils.py:96)."""
-    require_cuda(xyz)
-    out, base = [], xyz
-    for i, npoint in enumerate(npoints):
-        B, N, _ = base.shape
-        start = starts[i] if starts is not None else draw_fps_start(B, N, base.device)
-        idx = _fps_launch(base, npoint, start)
+    tensor per level (default: drawn like the reference draws them, R/modules/pointnet2_utils.py:96).
+    A chain can be computed in segments (a deeper software pipeline: different batches' segments run side by side):
+    levels = (first, last) restricts the call to levels first..last-1, `base` = the coordinates level `first` samples
+    from (the third return value of the previous segment); returns (indices of these levels, next base)."""
+    require_cuda(xyz if base is None else base)
+    first, last = levels if levels is not None else (0, len(npoints))
+    out, cur = [], (xyz if base is None else base)
+    for i in range(first, last):
+        B, N, _ = cur.shape
+        start = starts[i] if starts is not None else draw_fps_start(B, N, cur.device)
+        idx = _fps_launch(cur, npoints[i], start)
         out.append(idx)
         if i + 1 < len(npoints):
-            base = index_points(base, idx)
-    return out
+            cur = index_points(cur, idx)
+    return out if levels is None else (out, cur)
 
 
 @on_tensor_device

@@ -13,7 +13,7 @@ int main(int argc, char** argv) {
     srand(1);
     for (auto& v : h) v = 2.f * rand() / RAND_MAX - 1.f;
     float* d; int64_t *st, *out; unsigned long long* dbg;
-    cudaMalloc(&d, h.size() * 4); cudaMalloc(&st, B * 8); cudaMalloc(&out, (size_t)B * np * 8); cudaMalloc(&dbg, 64);
+    cudaMalloc(&d, h.size() * 4); cudaMalloc(&st, B * 8); cudaMalloc(&out, (size_t)B * np * 8); cudaMalloc(&dbg, 64 * 8 + 16 * 32 * 8 * 8);
     cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
     cudaMemset(st, 0, B * 8); cudaMemset(dbg, 0, 64);
     mpc::g_fp_dbg = dbg;
@@ -40,6 +40,21 @@ int main(int argc, char** argv) {
     }
     float ms; cudaEventElapsedTime(&ms, a, b);
     unsigned long long r[8]; cudaMemcpy(r, dbg, 64, cudaMemcpyDeviceToHost);
+    if (argc > 5) {
+        const int NW = atoi(argv[5]);
+        std::vector<unsigned long long> tr(16 * NW * 8);
+        cudaMemcpy(tr.data(), dbg + 64, tr.size() * 8, cudaMemcpyDeviceToHost);
+        for (int r = 0; r < 16; ++r) {
+            unsigned long long base = ~0ull;
+            for (int w = 0; w < NW; ++w) if (tr[(r * NW + w) * 8 + 1] && tr[(r * NW + w) * 8 + 1] < base) base = tr[(r * NW + w) * 8 + 1];
+            printf("round %d (test | update | publish+refresh | wait | reduce end, cycles after the round's first test end):\n", 1000 + r);
+            for (int w = 0; w < NW; ++w) {
+                printf("  w%02d", w);
+                for (int i = 1; i <= 5; ++i) printf(" %6lld", (long long)(tr[(r * NW + w) * 8 + i] - base));
+                printf("\n");
+            }
+        }
+    }
     printf("B %d N %d np %d: %.3f ms = %.3f us/round; touched buckets/round/cloud %.2f of %d; warp0 cycles/round: test %.0f update %.0f publish %.0f wait %.0f reduce %.0f\n",
            B, N, np, ms, 1e3 * ms / np, (double)r[0] / np / B, (N + 31) / 32, (double)r[1] / np, (double)r[2] / np,
            (double)r[3] / np, (double)r[4] / np, (double)r[5] / np);

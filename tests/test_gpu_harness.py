@@ -92,10 +92,14 @@ def test_sampling_one_batch_ahead_reproduces_the_plain_step(mpc):
     own = [i for k, i in rec if k == "fps"]
     ahead = mpc.ops.sampling_pyramid(batches[0][0].permute(0, 2, 1).contiguous(), wl.fps_npoints, starts[0])
     assert len(own) == len(ahead) == 5 and all(torch.equal(a, b) for a, b in zip(own, ahead))
-    g = bench.GraphedStep(step, batches[0], starts[0], ahead=True)
-    # call i hands over batch i+1 and returns the result of batch i
-    got = []
-    for i in (1, 2, 0):
-        got.append(float(g(batches[i], starts[i]).detach()))
+    # one batch ahead: call i hands over batch i+1 and returns the result of batch i
+    g = bench.GraphedStep(step, batches[0], starts[0], ahead=1)
+    got = [float(g(batches[i], starts[i]).detach()) for i in (1, 2, 0)]
     torch.cuda.synchronize()
     np.testing.assert_allclose(got, [plain[0], plain[1], plain[2]], rtol=2e-5)
+    # two batches ahead in two segments: results lag two calls (the priming batch is seen twice)
+    del g
+    g = bench.GraphedStep(step, batches[0], starts[0], ahead=2)
+    got = [float(g(batches[i], starts[i]).detach()) for i in (1, 2, 0, 1)]
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(got, [plain[0], plain[0], plain[1], plain[2]], rtol=2e-5)

@@ -357,11 +357,12 @@ fps_pruned_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ sta
             do {
                 const int j0 = __ffs(m2) - 1;
                 m2 &= m2 - 1;
-                const int j1 = m2 ? __ffs(m2) - 1 : j0;  // (a lone bucket is simply processed twice: idempotent)
+                const bool two = m2 != 0;
+                const int j1 = two ? __ffs(m2) - 1 : j0;
                 m2 &= m2 - 1;
                 const int s0 = (j0 * NW + w) * 32 + lane, s1 = (j1 * NW + w) * 32 + lane;
                 const float x0 = sx[s0], y0 = sy[s0], z0 = sz[s0], x1 = sx[s1], y1 = sy[s1], z1 = sz[s1];
-                float m0 = smd[s0];
+                float m0 = smd[s0], m1 = smd[s1];
                 const unsigned i0 = sid[s0], i1 = sid[s1];
                 {
                     const float dx = __fsub_rn(x0, cx), dy = __fsub_rn(y0, cy), dz = __fsub_rn(z0, cz);
@@ -378,8 +379,7 @@ fps_pruned_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ sta
                         cslot = s0;
                     }
                 }
-                {
-                    float m1 = smd[s1];  // (after the store above: s1 may be s0)
+                if (two) {  // (warp-uniform)
                     const float dx = __fsub_rn(x1, cx), dy = __fsub_rn(y1, cy), dz = __fsub_rn(z1, cz);
                     const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                     if (d < m1) {

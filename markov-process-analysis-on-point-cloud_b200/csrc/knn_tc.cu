@@ -23,8 +23,10 @@
 //      same feature vector) the query is appended to a per-cloud list and the exact brute-force kernel (knn.cu) runs
 //      on the listed queries only.
 //
-// Warp roles (192 threads, one CTA per SM by shared memory): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-5 selection / refinement (TMEM lane quadrant = warp % 4).
+// Warp roles (320 threads, one CTA per SM by shared memory): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2-5 selection / refinement (TMEM lane quadrant = warp % 4), warps 6-9 splitters: only the raw reference rows
+// stream from L2 (every CTA reads the whole reference set for its 128 queries: 3.4 TB/s of L2 traffic with a
+// precomputed lo copy, the kernel's bound), their lo term is made in shared memory.
 #include "tc_common.cuh"
 
 namespace mpc {
@@ -41,7 +43,8 @@ constexpr int B_STAGE_BYTES = 2 * KCH * CHUNK_BYTES;  // hi + lo of one referenc
 constexpr int STAGES = 2;
 constexpr int LIST = 16;                         // candidates kept per query
 constexpr int DROW = 36;                         // floats per row of the per-thread distance scratch (16 B aligned)
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;                     // warp 0 TMA, warp 1 MMA, warps 2-5 selection, warps 6-9 splitters
+constexpr int SPLIT_THREADS = 128;
 constexpr int DYN_SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 1024;
 
 struct Params {
@@ -56,6 +59,7 @@ struct Params {
     float* dist_out;      // [B,S,K] or null
     int64_t* idx_out;     // [B,S,K]
     int N, S, Npad, qn_stride, ntiles;
+    int debug;  // timing experiments only (knob 4 of mpc_debug_set_knob >= 100): 101 = selection skips its work, 102 = no MMAs
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -89,9 +93,9 @@ __device__ __forceinline__ void list_insert(float (&ld)[LIST], int (&li)[LIST], 
 template <int K>
 __global__ void __launch_bounds__(THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
-              const __grid_constant__ CUtensorMap map_rhi, const __grid_constant__ CUtensorMap map_rlo, const Params p) {
+              const __grid_constant__ CUtensorMap map_rhi, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_tmem_full[2], bar_tmem_empty[2];
+    __shared__ uint64_t bar_a, bar_full[STAGES], bar_split[STAGES], bar_empty[STAGES], bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float rn_s[4][2][BN];       // [selection warp][buffer][column]: |r|^2 of a tile
     __shared__ __align__(16) float drow[BM * DROW];      // per-thread scratch: the 32 distances of one TMEM slab
@@ -108,6 +112,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
         mbar_init(&bar_a, 1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_split[s], SPLIT_THREADS);
             mbar_init(&bar_empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -120,7 +125,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qlo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rlo) : "memory");
     }
     if (warp == 1) {  // TMEM: 2 accumulator stages x 128 fp32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
@@ -147,11 +151,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                 mbar_wait(&bar_empty[s], ph ^ 1);
                 uint8_t* st = b_s + (size_t)s * B_STAGE_BYTES;
                 const int rrow = b * p.N + j * BN;
-                mbar_arrive_expect_tx(&bar_full[s], B_STAGE_BYTES);
-                for (int kc = 0; kc < KCH; ++kc) {
+                // only the raw rows travel (kind::tf32 reads their top 19 bits: the hi term); the lo term is made in
+                // shared memory by the splitter warps -- half the L2 traffic of streaming a precomputed lo copy, which is
+                // what bounds this kernel (every CTA streams the whole reference set for its 128 queries)
+                mbar_arrive_expect_tx(&bar_full[s], B_STAGE_BYTES / 2);
+                for (int kc = 0; kc < KCH; ++kc)
                     tma_load_2d(&map_rhi, &bar_full[s], st + kc * CHUNK_BYTES, kc * BLOCK_K, rrow);
-                    tma_load_2d(&map_rlo, &bar_full[s], st + (KCH + kc) * CHUNK_BYTES, kc * BLOCK_K, rrow);
-                }
             }
         }
     } else if (warp == 1) {
@@ -169,12 +174,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                 mbar_wait(&bar_tmem_empty[as], aph ^ 1);
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
-                mbar_wait(&bar_full[s], ph);
+                mbar_wait(&bar_split[s], ph);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                 const uint32_t b0 = smem_u32(b_s + (size_t)s * B_STAGE_BYTES);
 #pragma unroll
-                for (int kc = 0; kc < KCH; ++kc) {
+                for (int kc = 0; kc < (p.debug == 102 ? 0 : KCH); ++kc) {
                     const uint64_t a_hi = make_desc(a0 + kc * CHUNK_BYTES), a_lo = make_desc(a0 + (KCH + kc) * CHUNK_BYTES);
                     const uint64_t b_hi = make_desc(b0 + kc * CHUNK_BYTES), b_lo = make_desc(b0 + (KCH + kc) * CHUNK_BYTES);
 #pragma unroll
@@ -188,6 +193,34 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                 umma_commit(&bar_empty[s]);        // the stage may be refilled once these MMAs have read it
                 umma_commit(&bar_tmem_full[as]);   // accumulator complete
             }
+        }
+    } else if (warp >= 6) {
+        // ===== splitters: lo = x - trunc_tf32(x) of every reference tile, next to the raw tile =====
+        const int t = threadIdx.x - 192;
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % STAGES;
+            const uint32_t ph = (j / STAGES) & 1;
+            mbar_wait(&bar_full[s], ph);
+            uint4* hi = reinterpret_cast<uint4*>(b_s + (size_t)s * B_STAGE_BYTES);
+            uint4* lo = hi + (B_STAGE_BYTES / 2) / 16;
+            constexpr int PER = (B_STAGE_BYTES / 2) / 16 / SPLIT_THREADS;  // 16 x 16 B per thread
+#pragma unroll
+            for (int i0 = 0; i0 < PER; i0 += 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = hi[t + (i0 + u) * SPLIT_THREADS];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint4 l;
+                    l.x = __float_as_uint(__uint_as_float(v[u].x) - __uint_as_float(v[u].x & TF32_MASK));
+                    l.y = __float_as_uint(__uint_as_float(v[u].y) - __uint_as_float(v[u].y & TF32_MASK));
+                    l.z = __float_as_uint(__uint_as_float(v[u].z) - __uint_as_float(v[u].z & TF32_MASK));
+                    l.w = __float_as_uint(__uint_as_float(v[u].w) - __uint_as_float(v[u].w & TF32_MASK));
+                    lo[t + (i0 + u) * SPLIT_THREADS] = l;
+                }
+            }
+            fence_async_proxy();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            mbar_arrive(&bar_split[s]);
         }
     } else {
         // ===== selection + refinement: thread = query =====
@@ -221,31 +254,50 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             const int n0 = j * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (p.debug == 101) continue;
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
-                unsigned mask = 0u;
+                // approximate distances of this thread's query to 32 reference points, and their minimum: once the
+                // list has settled, almost every slab holds no candidate at all (16 of N points ever qualify), so the
+                // common path is 32 fma + a min tree + one compare; the candidate bookkeeping below runs rarely
+                float dmin = __int_as_float(0x7f800000);
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
                     const float4 r4 = *reinterpret_cast<const float4*>(rns + c0 + i4 * 4);  // broadcast
-                    float4 d4;
-                    d4.x = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 0]), r4.x);
-                    d4.y = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 1]), r4.y);
-                    d4.z = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 2]), r4.z);
-                    d4.w = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 3]), r4.w);
-                    mask |= (d4.x < thr ? 1u : 0u) << (i4 * 4 + 0);
-                    mask |= (d4.y < thr ? 1u : 0u) << (i4 * 4 + 1);
-                    mask |= (d4.z < thr ? 1u : 0u) << (i4 * 4 + 2);
-                    mask |= (d4.w < thr ? 1u : 0u) << (i4 * 4 + 3);
-                    *reinterpret_cast<float4*>(my_d + i4 * 4) = d4;  // own row: read back by this thread only
+                    const float dx = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 0]), r4.x);
+                    const float dy = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 1]), r4.y);
+                    const float dz = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 2]), r4.z);
+                    const float dw = fmaf(-2.0f, __uint_as_float(v[i4 * 4 + 3]), r4.w);
+                    v[i4 * 4 + 0] = __float_as_uint(dx);
+                    v[i4 * 4 + 1] = __float_as_uint(dy);
+                    v[i4 * 4 + 2] = __float_as_uint(dz);
+                    v[i4 * 4 + 3] = __float_as_uint(dw);
+                    dmin = fminf(dmin, fminf(fminf(dx, dy), fminf(dz, dw)));
                 }
-                while (mask) {  // ascending column = ascending reference index
-                    const int i = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const float d = my_d[i];
-                    if (d < thr) {
-                        list_insert(ld, li, d, n0 + c0 + i);
-                        thr = ld[LIST - 1];
+                if (dmin < thr) {
+                    unsigned mask = 0u;
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        float4 d4;
+                        d4.x = __uint_as_float(v[i4 * 4 + 0]);
+                        d4.y = __uint_as_float(v[i4 * 4 + 1]);
+                        d4.z = __uint_as_float(v[i4 * 4 + 2]);
+                        d4.w = __uint_as_float(v[i4 * 4 + 3]);
+                        mask |= (d4.x < thr ? 1u : 0u) << (i4 * 4 + 0);
+                        mask |= (d4.y < thr ? 1u : 0u) << (i4 * 4 + 1);
+                        mask |= (d4.z < thr ? 1u : 0u) << (i4 * 4 + 2);
+                        mask |= (d4.w < thr ? 1u : 0u) << (i4 * 4 + 3);
+                        *reinterpret_cast<float4*>(my_d + i4 * 4) = d4;  // own row: read back by this thread only
+                    }
+                    while (mask) {  // ascending column = ascending reference index
+                        const int i = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float d = my_d[i];
+                        if (d < thr) {
+                            list_insert(ld, li, d, n0 + c0 + i);
+                            thr = ld[LIST - 1];
+                        }
                     }
                 }
             }
@@ -342,7 +394,7 @@ knn_tc_prep_kernel(const float* __restrict__ x, float* __restrict__ lo, float* _
     float acc = __int_as_float(0x7f800000);
     if (i < n) {
         const float4* src = reinterpret_cast<const float4*>(x + ((size_t)b * n + i) * CH);
-        float4* dst = reinterpret_cast<float4*>(lo + ((size_t)b * n + i) * CH);
+        float4* dst = lo ? reinterpret_cast<float4*>(lo + ((size_t)b * n + i) * CH) : nullptr;
 #pragma unroll 4
         for (int c4 = 0; c4 < CH / 4; ++c4) {
             const float4 v = __ldg(src + c4);
@@ -351,7 +403,7 @@ knn_tc_prep_kernel(const float* __restrict__ x, float* __restrict__ lo, float* _
             l.y = v.y - __uint_as_float(__float_as_uint(v.y) & TF32_MASK);
             l.z = v.z - __uint_as_float(__float_as_uint(v.z) & TF32_MASK);
             l.w = v.w - __uint_as_float(__float_as_uint(v.w) & TF32_MASK);
-            dst[c4] = l;
+            if (lo) dst[c4] = l;
             if (c4 == 0)
                 acc = __fmul_rn(v.x, v.x);
             else
@@ -442,20 +494,20 @@ MPC_API int mpc_knn_tc_f32(const float* ref, const float* qry, float* dist_out, 
     float* qlo = self ? rlo : reinterpret_cast<float*>(ws + l.qlo);
 
     MPC_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * B + 1) * 4, st));
-    knn_tc_prep_kernel<<<dim3((unsigned)ceil_div(npad, 128), (unsigned)B), 128, 0, st>>>(ref, rlo, rn, rnmax, (int)B, (int)N,
-                                                                                          npad);
+    // (the lo split of the reference rows is only kept when they are also the queries: self search)
+    knn_tc_prep_kernel<<<dim3((unsigned)ceil_div(npad, 128), (unsigned)B), 128, 0, st>>>(ref, self ? rlo : nullptr, rn, rnmax,
+                                                                                          (int)B, (int)N, npad);
     MPC_LAUNCH_CHECK();
     if (!self) {
         knn_tc_prep_kernel<<<dim3((unsigned)ceil_div(S, 128), (unsigned)B), 128, 0, st>>>(qry, qlo, qn, nullptr, (int)B,
                                                                                           (int)S, (int)S);
         MPC_LAUNCH_CHECK();
     }
-    CUtensorMap m_qhi, m_qlo, m_rhi, m_rlo;
+    CUtensorMap m_qhi, m_qlo, m_rhi;
     int rc;
     if ((rc = make_map(&m_qhi, qry, B * S, CH, CH, BM)) != MPC_OK) return rc;
     if ((rc = make_map(&m_qlo, qlo, B * S, CH, CH, BM)) != MPC_OK) return rc;
     if ((rc = make_map(&m_rhi, ref, B * N, CH, CH, BN)) != MPC_OK) return rc;
-    if ((rc = make_map(&m_rlo, rlo, B * N, CH, CH, BN)) != MPC_OK) return rc;
     MPC_CUDA(ensure_attr());
     Params p;
     p.ref = ref;
@@ -473,7 +525,8 @@ MPC_API int mpc_knn_tc_f32(const float* ref, const float* qry, float* dist_out, 
     p.Npad = npad;
     p.qn_stride = self ? npad : (int)S;
     p.ntiles = npad / BN;
-    knn_tc_kernel<8><<<dim3((unsigned)ceil_div(S, BM), (unsigned)B), THREADS, DYN_SMEM, st>>>(m_qhi, m_qlo, m_rhi, m_rlo, p);
+    p.debug = g_knob[4] >= 100 ? (int)g_knob[4] : 0;
+    knn_tc_kernel<8><<<dim3((unsigned)ceil_div(S, BM), (unsigned)B), THREADS, DYN_SMEM, st>>>(m_qhi, m_qlo, m_rhi, p);
     MPC_LAUNCH_CHECK();
     // exact brute force for the queries the filter could not decide (near-tie groups larger than the candidate list)
     return launch_knn_tiled_indirect8(ref, qry, dist_out, idx_out, qlist, qcount, (int)B, (int)N, (int)S, (int)C, st);

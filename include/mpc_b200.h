@@ -286,7 +286,7 @@ int mpc_bn_act_bwd_f32(const float* grad_out, const float* y, const float* mean,
  * per-column sum and sum of squares of y over the M rows -- the BatchNorm batch statistics of the `Linear` block --
  * from the tile while it is still in shared memory, one atomic per column per CTA; mpc_bn_act_fwd_sums_f32 or
  * mpc_bn_finalize_f32 consume (and clear) them.
- * group_bias (optional, [M / rows_per_group, N] f32, rows_per_group % 128 == 0): a second bias shared by
+ * group_bias (optional, [ceil(M / rows_per_group), N] f32, N % 4 == 0): a second bias shared by
  * rows_per_group consecutive rows.  It carries the projection of input channels that are constant over a cloud's
  * points (the broadcast global-pool and label channels of the part-seg head, R/modules/pointnet2_utils.py:843-853):
  * y = x_a Wa^T + (g Wb^T)[cloud] + b equals the reference's Linear over cat(x_a, broadcast g) with 3.5x less work.

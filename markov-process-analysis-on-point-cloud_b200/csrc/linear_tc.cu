@@ -42,7 +42,7 @@ struct Params {
     int stages;
     const float* bias;  // may be null
     const float* bias2; // optional [groups][N]: a second bias shared by `bias2_rows` consecutive rows (a per-cloud
-    int bias2_rows;     //   vector: the projection of channels that are constant over a cloud's points); % 128 == 0
+    int bias2_rows;     //   vector: the projection of channels that are constant over a cloud's points); any multiple of 128 is looked up per tile, anything else per row
     float* y;
     int ldy;
     int a_mn, b_mn;   // operand layouts: 0 = K-major (reduction index contiguous), 1 = MN-major (output index
@@ -308,14 +308,15 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 stat_n0 = n0;
                 for (int i = lane; i < p.block_n; i += 32) my_acc0[i] = my_acc1[i] = 0.f;
             }
-            const int grp = p.bias2 ? (mt * BLOCK_M) / p.bias2_rows : 0;
+            const bool b2_row = p.bias2 && (p.bias2_rows % BLOCK_M) != 0;  // groups not tile aligned: per-row lookup
+            const int grp = (p.bias2 && !b2_row) ? (mt * BLOCK_M) / p.bias2_rows : 0;
             if (p.tma_out && (n0 != bias_n0 || grp != bias_grp)) {
                 // bias of this column tile -> shared (broadcast reads below); reloaded only when the column tile (or
                 // the row group of a per-cloud bias) changes -- once per kernel in every plain layer of both models
                 epi_barrier();
                 for (int i = threadIdx.x; i < p.block_n; i += 128) {
                     float v = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-                    if (p.bias2 && n0 + i < p.N) v += __ldg(p.bias2 + (size_t)grp * p.N + n0 + i);
+                    if (p.bias2 && !b2_row && n0 + i < p.N) v += __ldg(p.bias2 + (size_t)grp * p.N + n0 + i);
                     bias_s[i] = v;
                     if (p.scale) bias_s[256 + i] = n0 + i < p.N ? __ldg(p.scale + n0 + i) : 1.0f;
                 }
@@ -371,6 +372,29 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             }
                             srow[q4 ^ (lane & 7)] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]),
                                                                __float_as_uint(v[2]), __float_as_uint(v[3]));
+                        }
+                    } else if (b2_row) {
+                        // per-cloud bias whose row groups are not tile aligned (24 000-point blocks): this thread's row
+                        // looks its cloud's vector up itself (a [clouds, N] table, L2 resident)
+                        const int rr = row < p.M ? row : p.M - 1;
+                        const float* b2 = p.bias2 + (size_t)(rr / p.bias2_rows) * p.N + n0 + c;
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const uint32_t* src = q4 < 4 ? &r0[q4 * 4] : &r1[(q4 - 4) * 4];
+                            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (n0 + c + q4 * 4 + 4 <= p.N) {
+                                g = __ldg(reinterpret_cast<const float4*>(b2) + q4);
+                            } else {
+                                if (n0 + c + q4 * 4 + 0 < p.N) g.x = __ldg(b2 + q4 * 4 + 0);
+                                if (n0 + c + q4 * 4 + 1 < p.N) g.y = __ldg(b2 + q4 * 4 + 1);
+                                if (n0 + c + q4 * 4 + 2 < p.N) g.z = __ldg(b2 + q4 * 4 + 2);
+                            }
+                            uint4 o;
+                            o.x = __float_as_uint(__uint_as_float(src[0]) + (bias_s[c + q4 * 4 + 0] + g.x));
+                            o.y = __float_as_uint(__uint_as_float(src[1]) + (bias_s[c + q4 * 4 + 1] + g.y));
+                            o.z = __float_as_uint(__uint_as_float(src[2]) + (bias_s[c + q4 * 4 + 2] + g.z));
+                            o.w = __float_as_uint(__uint_as_float(src[3]) + (bias_s[c + q4 * 4 + 3] + g.w));
+                            srow[q4 ^ (lane & 7)] = o;
                         }
                     } else {
 #pragma unroll
@@ -540,7 +564,7 @@ static int linear_fwd_impl(const float* x, int64_t ldx, const float* w, int64_t 
     p.tma_out = tma_out;
     p.stat_sum = stat_scratch;
     if (stat_scratch && !tma_out) return MPC_ERR_UNSUPPORTED;  // zero on entry is the caller's contract
-    if (group_bias && (!tma_out || rows_per_group <= 0 || rows_per_group % BLOCK_M)) return MPC_ERR_UNSUPPORTED;
+    if (group_bias && (!tma_out || rows_per_group <= 0 || (N & 3))) return MPC_ERR_UNSUPPORTED;
     p.bias2 = group_bias;
     p.bias2_rows = (int)(group_bias ? rows_per_group : 1);
     p.zero_ptr = nullptr;

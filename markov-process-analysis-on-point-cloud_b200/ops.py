@@ -1360,7 +1360,7 @@ class LinearBNActSplit(torch.autograd.Function):
 @on_tensor_device
 def linear_bn_act_split(x_a, g, weight, bias, bn, training, slope):
     """x_a [B,Np,Ka] (per-point channels), g [B,Kb] (per-cloud channels) -> act(BN(Linear(cat(x_a, broadcast g)))),
-    [B,Np,N]; see LinearBNActSplit.  Caller guarantees Np % 128 == 0 and Ka % 32 == 0."""
+    [B,Np,N]; see LinearBNActSplit.  Caller guarantees Ka % 32 == 0 (split_supported)."""
     require_cuda(x_a, g)
     B, Np, Ka = x_a.shape
     N = weight.shape[0]
@@ -1379,7 +1379,7 @@ def _momentum(bn):
 
 
 def split_supported(n_points, Ka, N):
-    return (_GEMM_IMPL == "tcgen05" and n_points % 128 == 0 and Ka % 32 == 0 and N % 4 == 0 and N <= 1024
+    return (_GEMM_IMPL == "tcgen05" and n_points > 0 and Ka % 32 == 0 and N % 4 == 0 and N <= 1024
             and 1024 % N == 0)
 
 

@@ -1,23 +1,24 @@
-"""Per-shape table of the GEMM launches of one part-seg training step (bench.py's workload): every distinct
-(entry point, M, K, N) is re-issued 24 times back to back in its own CUDA graph over 6 rotating buffer sets and
-timed with CUDA events.  Prints count, us per launch, algorithmic GB/s and the share of the step's GEMM time."""
+"""Per-shape table of the GEMM launches of one training step of a bench.py workload (default partseg2048; argv[1] =
+workload key): every distinct (entry point, M, K, N) is re-issued 24 times back to back in its own CUDA graph over 6
+rotating buffer sets and timed with CUDA events.  Prints count, us per launch, algorithmic GB/s and the share of the
+step's GEMM time."""
 import importlib, sys, torch
 sys.path.insert(0, '.')
 import bench
 mpc = importlib.import_module(bench.PKG)
 mpc._lib.load()
 dev = torch.device("cuda")
-step = bench.Step(mpc, dev, 1)
+wl = bench.Workload(sys.argv[1] if len(sys.argv) > 1 else "partseg2048", 1)
+step = bench.Step(wl, mpc, dev, 1)
 gen = torch.Generator().manual_seed(1)
-B = int(sys.argv[1]) if len(sys.argv) > 1 else bench.B_PER_GPU
-xyz, label, target = (t.to(dev) for t in bench.synth_batch(B, gen))
-starts = lambda: [s.to(dev) for s in bench.fps_starts(B, gen)]
+inputs = [t.to(dev) for t in wl.synth(wl.B, gen)]
+starts = lambda: [s.to(dev) for s in wl.starts(wl.B, gen)]
 for _ in range(2):
-    step(xyz, label, target, starts())
+    step.device_part(inputs, starts())
 torch.cuda.synchronize()
 names = {"mpc_linear_fwd_f32", "mpc_linear_dgrad_f32", "mpc_linear_wgrad_f32"}
 mpc._lib.profiler = {"names": names, "calls": []}
-step(xyz, label, target, starts())
+step.device_part(inputs, starts())
 torch.cuda.synchronize()
 calls = mpc._lib.profiler["calls"]
 mpc._lib.profiler = None

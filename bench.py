@@ -151,7 +151,8 @@ class Workload:
         self.eval_blocks = ()
         self.bf16 = False
         if key == "sem24k":
-            self.total = 8
+            # (MPC_BENCH_SEM_BLOCKS: experiments only, e.g. 1 block on 1 GPU = the per-GPU load of the 8-GPU run)
+            self.total = int(os.environ.get("MPC_BENCH_SEM_BLOCKS", "8"))
             if self.total % world:
                 raise SystemExit("bench.py: sem24k shards 8 blocks; --gpus must divide 8")
             self.B, self.N, self.classes, self.scaling = self.total // world, 24000, 13, "strong"
@@ -490,10 +491,11 @@ class GraphedStep:
         return self.res
 
 
-GEMM_ENTRIES = ("mpc_linear_fwd_f32", "mpc_linear_dgrad_f32", "mpc_linear_wgrad_f32")
-# C-ABI entry point -> the CUDA kernel that does its work (the three GEMM entry points share one kernel)
-KERNEL_OF = {n: "linear_3xtf32_kernel" for n in GEMM_ENTRIES}
-KERNEL_OF.update({"mpc_linear_bf16": "linear_bf16_kernel (tcgen05 kind::f16, fused BatchNorm affine + LeakyReLU + residual)",
+GEMM_ENTRIES = ("mpc_linear_fwd_f32", "mpc_linear_dgrad_f32", "mpc_linear_wgrad_f32", "mpc_linear_affine_act_f32",
+                "mpc_linear_bf16")
+# C-ABI entry point -> the CUDA kernel that does its work (the fp32 GEMM entry points share one kernel)
+KERNEL_OF = {n: "linear_3xtf32_kernel" for n in GEMM_ENTRIES[:4]}
+KERNEL_OF.update({"mpc_linear_bf16": "linear_bf16_kernel",
                   "mpc_knn3_grid_f32": "knn3_grid_kernel (uniform-grid coordinate search) + grid build",
                   "mpc_knn_f32": "knn3 / knn_tiled / knn64 kernels (FP32 SIMT, by shape)",
                   "mpc_knn_tc_f32": "knn_tc_kernel (tcgen05 filter + exact refinement)",
@@ -547,6 +549,23 @@ def rebind_gemm_calls(mpc, calls, device):
             g, x, w = buf(M, ldg), buf(M, ldx), buf(N, ldw)
             keep += [g, x, w]
             na = (P(g), a[1], P(x), a[3], P(w), a[5], a[6], a[7], a[8], a[9])
+        elif name == "mpc_linear_affine_act_f32":
+            ldx, ldw, ldr, ldy, M, K, N = (val(a[i]) for i in (1, 3, 8, 10, 11, 12, 13))
+            x, w, y = buf(M, ldx), buf(N, ldw), buf(M, ldy)
+            sc, sh = torch.rand(N, device=device) + 0.5, torch.randn(N, device=device)
+            res = buf(M, ldr) if val(a[7]) else None
+            keep += [x, w, y, sc, sh, res]
+            na = (P(x), a[1], P(w), a[3], P(sc), P(sh), a[6], P(res), a[8], P(y), a[10], a[11], a[12], a[13])
+        elif name == "mpc_linear_bf16":
+            ldx, ldw, ldr, ldo, f32o, M, K, N = (val(a[i]) for i in (1, 3, 8, 10, 11, 12, 13, 14))
+            b16 = lambda rows, ld: buf(rows, ld).to(torch.bfloat16)
+            x, w = b16(M, ldx), b16(N, ldw)
+            y = buf(M, ldo) if f32o else b16(M, ldo)
+            sc = torch.rand(N, device=device) + 0.5 if val(a[4]) else None
+            sh = torch.randn(N, device=device) if val(a[5]) else None
+            res = b16(M, ldr) if val(a[7]) else None
+            keep += [x, w, y, sc, sh, res]
+            na = (P(x), a[1], P(w), a[3], P(sc), P(sh), a[6], P(res), a[8], P(y), a[10], a[11], a[12], a[13], a[14])
         else:
             return None, None
         out.append((name, na, by))
@@ -613,8 +632,12 @@ def measure_roofline(wl, step, mpc, device, inputs, starts_fn, flush, full, dev_
         ideal_ms = 0.0  # every launch at the faster of its two rooflines (HBM bytes; 3 x 2MNK at half the bf16 rate)
         for cname, a, cby in calls:
             dims = [x.value for x in a if isinstance(x, ctypes.c_int64)]
-            Mg, Kg, Ng = dims[-3:] if cname == "mpc_linear_fwd_f32" else dims[-4:-1]
-            ideal_ms += 1e3 * max(cby / (pk["hbm_gbs"] * 1e9), 3 * 2.0 * Mg * Kg * Ng / (pk["bf16_tflops"] * 0.5e12))
+            Mg, Kg, Ng = dims[-3:] if cname in ("mpc_linear_fwd_f32", "mpc_linear_affine_act_f32",
+                                                "mpc_linear_bf16") else dims[-4:-1]
+            # tensor-pipe floor: 3 split terms at half the bf16 rate (3xTF32), or one bf16 pass
+            tens = (2.0 * Mg * Kg * Ng / (pk["bf16_tflops"] * 1e12) if cname == "mpc_linear_bf16"
+                    else 3 * 2.0 * Mg * Kg * Ng / (pk["bf16_tflops"] * 0.5e12))
+            ideal_ms += 1e3 * max(cby / (pk["hbm_gbs"] * 1e9), tens)
         n = len(calls)
         del kgraph, keep
         achieved = by / 1e9 / (ms / 1e3)
@@ -623,9 +646,10 @@ def measure_roofline(wl, step, mpc, device, inputs, starts_fn, flush, full, dev_
                 "peak_kind": pk_kind + " (burst copy)", "launches_per_step": n, "avg_launch_us": 1e3 * ms / max(n, 1),
                 "algo_bytes_per_launch": by / max(n, 1), "kernel_ms_per_step": ms,
                 "share_of_step": ms / dev_ms_per_step, "frac_mixed_bound": ideal_ms / ms,
-                "frac_mixed_bound_how": "sum over the launches of max(bytes / HBM peak, 3 x 2MNK / (bf16 peak / 2)) "
-                                        "divided by the measured time: the wide layers are tensor-pipe bound under "
-                                        "the 3xTF32 split, not HBM bound",
+                "frac_mixed_bound_how": "sum over the launches of max(bytes / HBM peak, tensor-pipe floor) divided by the "
+                                        "measured time; tensor-pipe floor = 3 x 2MNK / (bf16 peak / 2) under the 3xTF32 "
+                                        "split (the wide layers are tensor-pipe bound, not HBM bound), 2MNK / bf16 peak "
+                                        "for the bf16 kernel",
                 "how": "all %d launches of one step re-issued back to back in a CUDA graph, CUDA events around %d "
                        "replays; share_of_step relates that serialised time to the multi-stream graph step" % (n, reps)}
     # anything else: bracket every launch of the kernel in place, during one eager step with the side streams off

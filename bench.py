@@ -722,15 +722,19 @@ def measure_roofline(wl, step, mpc, device, inputs, starts_fn, flush, full, dev_
 
 
 def committed_traffic(kernel, key):
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu capture of this
-    command (profiles/r2_traffic.json: {workload: {"kernel":..., "dram_bytes_per_launch":...}}), else null."""
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu launch list of this
+    command (profiles/r2_traffic.json: {workload: [{"kernel": name fragment, "dram_bytes_per_launch": ...}, ...]}),
+    else null."""
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
-        tj = json.load(f).get(key)
-    if tj and tj.get("kernel") == kernel:
-        return tj.get("dram_bytes_per_launch")
+        entries = json.load(f).get(key) or []
+    if isinstance(entries, dict):
+        entries = [entries]
+    for e in entries:
+        if e.get("kernel") and e["kernel"] in kernel:
+            return e.get("dram_bytes_per_launch")
     return None
 
 
@@ -761,15 +765,28 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
                 step.make_optimizer()
         step.exchange()
     torch.cuda.synchronize()
-    mpc._lib.profiler = {"names": None, "records": {}}
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    step.device_part(inputs, device_starts(), pack=False)
-    ev1.record()
-    torch.cuda.synchronize()
-    full = op_table(mpc._lib.profiler["records"])
-    instrumented_step_ms = ev0.elapsed_time(ev1)
-    mpc._lib.profiler = None
+    # (single-stream: with the side streams on, an entry point's event bracket also measures the kernels of other
+    # streams it shares the GPU with, and the ranking would not be the kernels' own device time)
+    streams_were = mpc.ops._STREAMS_ENABLED
+    mpc.ops._STREAMS_ENABLED = False
+    try:
+        mpc._lib.profiler = {"names": None, "records": {}}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        step.device_part(inputs, device_starts(), pack=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        full = op_table(mpc._lib.profiler["records"])
+        instrumented_step_ms = ev0.elapsed_time(ev1)
+    finally:
+        mpc._lib.profiler = None
+        mpc.ops._STREAMS_ENABLED = streams_were
+    if not args.no_graph and args.fps_ahead:
+        # the sampling chain runs beside the step, one or two batches ahead (GraphedStep): it is not what the timed step
+        # waits for, so it does not compete for "dominant kernel of the step" (its device time stays in --profile-ops)
+        ranked = [r for r in full if r[0] != "mpc_fps_f32"]
+    else:
+        ranked = full
     if args.profile_ops and rank == 0:
         with open(args.profile_ops, "a") as f:
             f.write("# %s: one instrumented eager step (%.3f ms incl. event overhead); per C-ABI entry point\n"
@@ -842,7 +859,7 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
     d2h = res_host.numel() * res_host.element_size()
 
     # ---- roofline of the dominant kernel (after the timed region: it re-runs eager steps)
-    roof = measure_roofline(wl, step, mpc, device, inputs, device_starts, flush, full, dev_ms / args.steps) \
+    roof = measure_roofline(wl, step, mpc, device, inputs, device_starts, flush, ranked, dev_ms / args.steps) \
         if rank == 0 else None
     barrier()
     rec = None

@@ -826,7 +826,7 @@ static int launch_knn(const float* ref, const float* qry, float* dist_out, int64
 // keeps its own sorted K-list of exact distances (the contract's expression: fma chain over c from 0, sequential
 // non-fused norms, ((-2 dot) + |q|^2) + |r|^2) and the lists are merged by K rounds of a block-wide lexicographic
 // (distance, index) arg-min: ~20 us.
-constexpr int KNN_FEW_THREADS = 256;
+constexpr int KNN_FEW_THREADS = 1024;  // (the CTA is alone on its query: reference rows over as many threads as fit)
 
 __device__ __forceinline__ unsigned long long few_key(float d, int n) {
     const unsigned u = __float_as_uint(d);

@@ -36,7 +36,8 @@ if "--traffic" in sys.argv:
         cur = json.load(open(out))
     except Exception:
         cur = {}
-    cur[key] = {"kernel": sub, "launches_per_step": n, "dram_bytes_per_launch": by / max(n, 1), "kernel_us_per_step": us,
+    cur[key] = [e for e in cur.get(key, []) if isinstance(e, dict) and e.get("kernel") != sub] if isinstance(cur.get(key), list) else []
+    cur[key].append({"kernel": sub, "launches_per_step": n, "dram_bytes_per_launch": by / max(n, 1), "kernel_us_per_step": us,
                 "step_kernel_us_total": tot, "share_of_step": us / tot,
-                "source": "%s (ncu gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum; one eager step of bench.py)" % path}
+                "source": "%s (ncu gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum; one eager step of bench.py)" % path})
     json.dump(cur, open(out, "w"), indent=1)

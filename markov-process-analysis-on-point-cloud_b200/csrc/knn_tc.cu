@@ -59,6 +59,7 @@ struct Params {
     float* dist_out;      // [B,S,K] or null
     int64_t* idx_out;     // [B,S,K]
     int N, S, Npad, qn_stride, ntiles;
+    long long* trace;  // debug: clock64() timeline of CTA (0,0), tiles 40..55: [role 0..3][tile][2]
     int debug;  // timing experiments only (knob 4 of mpc_debug_set_knob >= 100): 101 = selection skips its work, 102 = no MMAs
 };
 
@@ -89,6 +90,12 @@ __device__ __forceinline__ void list_insert(float (&ld)[LIST], int (&li)[LIST], 
         }
     }
 }
+
+#define KNN_TRACE(role, j, k)                                                                            \
+    do {                                                                                                  \
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (j) >= 40 && (j) < 56)                      \
+            p.trace[((role) * 16 + ((j) - 40)) * 2 + (k)] = clock64();                                     \
+    } while (0)
 
 template <int K>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -149,6 +156,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 mbar_wait(&bar_empty[s], ph ^ 1);
+                KNN_TRACE(0, j, 0);
                 uint8_t* st = b_s + (size_t)s * B_STAGE_BYTES;
                 const int rrow = b * p.N + j * BN;
                 // only the raw rows travel (kind::tf32 reads their top 19 bits: the hi term); the lo term is made in
@@ -172,9 +180,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                 const int as = j & 1;
                 const uint32_t aph = (j >> 1) & 1;
                 mbar_wait(&bar_tmem_empty[as], aph ^ 1);
+                KNN_TRACE(2, j, 0);
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 mbar_wait(&bar_split[s], ph);
+                KNN_TRACE(2, j, 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                 const uint32_t b0 = smem_u32(b_s + (size_t)s * B_STAGE_BYTES);
@@ -201,6 +211,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             const int s = j % STAGES;
             const uint32_t ph = (j / STAGES) & 1;
             mbar_wait(&bar_full[s], ph);
+            if (t == 0) KNN_TRACE(1, j, 0);
             uint4* hi = reinterpret_cast<uint4*>(b_s + (size_t)s * B_STAGE_BYTES);
             uint4* lo = hi + (B_STAGE_BYTES / 2) / 16;
             constexpr int PER = (B_STAGE_BYTES / 2) / 16 / SPLIT_THREADS;  // 16 x 16 B per thread
@@ -221,6 +232,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             }
             fence_async_proxy();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
             mbar_arrive(&bar_split[s]);
+            if (t == 0) KNN_TRACE(1, j, 1);
         }
     } else {
         // ===== selection + refinement: thread = query =====
@@ -249,6 +261,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             __syncwarp();
             if (j + 1 < ntiles) pre = __ldg(reinterpret_cast<const float4*>(rnb + (size_t)(j + 1) * BN) + lane);
             mbar_wait(&bar_tmem_full[as], aph);
+            if (threadIdx.x == 64) KNN_TRACE(3, j, 0);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quad * 32) << 16);
             const int n0 = j * BN;
@@ -303,6 +316,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive(&bar_tmem_empty[as]);
+            if (threadIdx.x == 64) KNN_TRACE(3, j, 1);
         }
         // ---- refinement
         const float qn = active ? __ldg(p.qn + (size_t)b * p.qn_stride + s_idx) : 0.f;
@@ -525,6 +539,7 @@ MPC_API int mpc_knn_tc_f32(const float* ref, const float* qry, float* dist_out, 
     p.Npad = npad;
     p.qn_stride = self ? npad : (int)S;
     p.ntiles = npad / BN;
+    p.trace = tc::g_trace;
     p.debug = g_knob[4] >= 100 ? (int)g_knob[4] : 0;
     knn_tc_kernel<8><<<dim3((unsigned)ceil_div(S, BM), (unsigned)B), THREADS, DYN_SMEM, st>>>(m_qhi, m_qlo, m_rhi, p);
     MPC_LAUNCH_CHECK();

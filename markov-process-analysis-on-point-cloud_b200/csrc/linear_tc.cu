@@ -485,7 +485,7 @@ linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
 }
 
-static long long* g_trace = nullptr;  // debug only, see mpc_debug_trace_buffer
+long long* g_trace = nullptr;  // debug only, see mpc_debug_trace_buffer (also read by knn_tc.cu)
 
 // Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream
 // is still draining (it blocks in griddepcontrol.wait before reading anything the predecessor wrote).

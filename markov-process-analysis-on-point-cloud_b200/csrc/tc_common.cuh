@@ -14,6 +14,7 @@ namespace tc {
 constexpr int BLOCK_K = 32;               // fp32 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction
 constexpr uint32_t TF32_MASK = 0xffffe000u;
+extern long long* g_trace;  // debug timeline buffer (mpc_debug_trace_buffer, linear_tc.cu)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -250,6 +250,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             ld[e] = __int_as_float(0x7f800000);
             li[e] = 0;
         }
+        // A candidate only matters if it can lie within 2 eps of the final K-th best approximate distance: the insertion
+        // threshold is min(16th best, K-th best + 2.5 eps) -- the K-th best only ever decreases, so what this rejects is
+        // outside the final bound.  Twice as selective as the 16th best alone, and the bookkeeping path below is
+        // entered per warp whenever ANY of its 32 queries has a candidate in the slab.
+        const float qn = active ? __ldg(p.qn + (size_t)b * p.qn_stride + s_idx) : 0.f;
+        const float scale = qn + __uint_as_float(__ldg(p.rnmax + b));
+        const float eps = scale * 6.103515625e-05f;  // 2^-14
         float thr = __int_as_float(0x7f800000);
         float4 pre = __ldg(reinterpret_cast<const float4*>(rnb) + lane);  // |r|^2 of tile 0, 4 columns per lane
         for (int j = 0; j < ntiles; ++j) {
@@ -309,7 +316,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                         const float d = my_d[i];
                         if (d < thr) {
                             list_insert(ld, li, d, n0 + c0 + i);
-                            thr = ld[LIST - 1];
+                            thr = fminf(ld[LIST - 1], ld[K - 1] + 2.5f * eps);
                         }
                     }
                 }
@@ -319,9 +326,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             if (threadIdx.x == 64) KNN_TRACE(3, j, 1);
         }
         // ---- refinement
-        const float qn = active ? __ldg(p.qn + (size_t)b * p.qn_stride + s_idx) : 0.f;
-        const float scale = qn + __uint_as_float(__ldg(p.rnmax + b));
-        const float eps = scale * 6.103515625e-05f;  // 2^-14
         const float bound = ld[K - 1] + 2.5f * eps;  // (2 eps, and the rounding of this very sum)
         const bool overflow = !(ld[LIST - 1] > bound);
         float dev = 0.f;

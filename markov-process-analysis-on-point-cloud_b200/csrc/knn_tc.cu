@@ -42,7 +42,6 @@ constexpr int A_BYTES = 2 * KCH * CHUNK_BYTES;   // hi + lo of the query tile: 6
 constexpr int B_STAGE_BYTES = 2 * KCH * CHUNK_BYTES;  // hi + lo of one reference tile: 64 KB
 constexpr int STAGES = 2;
 constexpr int LIST = 16;                         // candidates kept per query
-constexpr int DROW = 36;                         // floats per row of the per-thread distance scratch (16 B aligned)
 constexpr int THREADS = 320;                     // warp 0 TMA, warp 1 MMA, warps 2-5 selection, warps 6-9 splitters
 constexpr int SPLIT_THREADS = 128;
 constexpr int DYN_SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 1024;
@@ -105,7 +104,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
     __shared__ uint64_t bar_a, bar_full[STAGES], bar_split[STAGES], bar_empty[STAGES], bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float rn_s[4][2][BN];       // [selection warp][buffer][column]: |r|^2 of a tile
-    __shared__ __align__(16) float drow[BM * DROW];      // per-thread scratch: the 32 distances of one TMEM slab
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_s = smem;                 // [hi k0][hi k1][lo k0][lo k1], 16 KB each
@@ -242,7 +240,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
         const int s_idx = q0 + row;
         const bool active = s_idx < p.S;
         const float* rnb = p.rn + (size_t)b * p.Npad;
-        float* my_d = drow + row * DROW;
         float ld[LIST];
         int li[LIST];
 #pragma unroll
@@ -295,30 +292,23 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                     v[i4 * 4 + 3] = __float_as_uint(dw);
                     dmin = fminf(dmin, fminf(fminf(dx, dy), fminf(dz, dw)));
                 }
-                if (dmin < thr) {
-                    unsigned mask = 0u;
+                // candidates of this slab, smallest first, straight from the registers: the position of the minimum (the
+                // lowest column among equal values, so equal distances still enter in ascending index order), insert,
+                // knock it out, next minimum.  Most slabs that get here hold one candidate for one or two of the warp's
+                // 32 queries.
+                while (dmin < thr) {
+                    int pos = 31;
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        float4 d4;
-                        d4.x = __uint_as_float(v[i4 * 4 + 0]);
-                        d4.y = __uint_as_float(v[i4 * 4 + 1]);
-                        d4.z = __uint_as_float(v[i4 * 4 + 2]);
-                        d4.w = __uint_as_float(v[i4 * 4 + 3]);
-                        mask |= (d4.x < thr ? 1u : 0u) << (i4 * 4 + 0);
-                        mask |= (d4.y < thr ? 1u : 0u) << (i4 * 4 + 1);
-                        mask |= (d4.z < thr ? 1u : 0u) << (i4 * 4 + 2);
-                        mask |= (d4.w < thr ? 1u : 0u) << (i4 * 4 + 3);
-                        *reinterpret_cast<float4*>(my_d + i4 * 4) = d4;  // own row: read back by this thread only
+                    for (int i = 30; i >= 0; --i) pos = __uint_as_float(v[i]) == dmin ? i : pos;
+                    list_insert(ld, li, dmin, n0 + c0 + pos);
+                    thr = fminf(ld[LIST - 1], ld[K - 1] + 2.5f * eps);
+                    float nmin = __int_as_float(0x7f800000);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i == pos) v[i] = 0x7f800000u;  // +inf
+                        nmin = fminf(nmin, __uint_as_float(v[i]));
                     }
-                    while (mask) {  // ascending column = ascending reference index
-                        const int i = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float d = my_d[i];
-                        if (d < thr) {
-                            list_insert(ld, li, d, n0 + c0 + i);
-                            thr = fminf(ld[LIST - 1], ld[K - 1] + 2.5f * eps);
-                        }
-                    }
+                    dmin = nmin;
                 }
             }
             tc_fence_before();

@@ -340,17 +340,56 @@ class Step:
         self.params = list(self.model.parameters())
         self.bucket = None   # dist.GradBucket, built after the first backward
         self.opt = None
+        # Overlapped exchange (--graph-allreduce, N > 1): the parameters of everything that runs AFTER the encoder's last
+        # stage in forward (classifier: la5, conv3/4, head = 80 % of the gradient bytes; part-seg: decoder + head) have
+        # their gradients complete when backward reaches that stage's output; their part of the flat bucket is
+        # all-reduced on a communication stream from a tensor hook there, beside the encoder's backward.
+        self.overlap = False
+        self.comm = None
+        self._armed = False
+        enc = ("keepHigh.start.", "keepHigh.la0.", "keepHigh.la1.", "keepHigh.la2.", "keepHigh.la3.", "keepHigh.la4.")
+        self._late = {id(p) for n, p in self.model.named_parameters() if n.startswith(enc)}
+        if wl.train:
+            self.model.keepHigh.la4.register_forward_hook(self._boundary_forward_hook)
+
+    def _boundary_forward_hook(self, module, inputs, output):
+        feat = output[0]
+        if self.overlap and self._armed and feat.requires_grad:
+            feat.register_hook(self._boundary_grad_hook)
+
+    def _boundary_grad_hook(self, grad):
+        cur = torch.cuda.current_stream()
+        self.comm.wait_stream(cur)
+        wg = self.mpc.ops._wgrad_streams.get(cur.device)
+        if wg is not None:
+            self.comm.wait_stream(wg)  # deferred weight gradients of the early group are still being written there
+        with torch.cuda.stream(self.comm):
+            self.bucket.pack(0)
+            self.bucket.all_reduce(self.world, 0)
+        self._fired = True
+        return None
 
     def device_part(self, inputs, starts, pack=True):
         wl = self.wl
         if wl.train:
             for p in self.params:
                 p.grad = None
+            self._armed = bool(pack and self.overlap and self.bucket is not None)
+            self._fired = False
             with self.mpc.ops.index_tape(fps_starts=starts):
                 res = wl.forward(self.model, inputs)
             res.backward()
-            if pack and self.bucket is not None and self.world > 1:
-                self.bucket.pack()
+            if self._armed and self._fired:
+                # part 0 is on its way on the communication stream; the encoder's gradients follow on this one
+                self.bucket.pack(1)
+                self.bucket.all_reduce(self.world, 1)
+                torch.cuda.current_stream().wait_stream(self.comm)
+                self._exchanged = True
+            else:
+                self._exchanged = False
+                if pack and self.bucket is not None and self.world > 1:
+                    self.bucket.pack()
+            self._armed = False
             return res
         mode = self.mpc.ops.bf16_inference() if wl.bf16 else contextlib.nullcontext()
         with torch.no_grad(), mode, self.mpc.ops.index_tape(fps_starts=starts):
@@ -358,13 +397,14 @@ class Step:
 
     def ensure_bucket(self):
         if self.wl.train and self.bucket is None:
-            self.bucket = self.mpc.dist.GradBucket(self.params)
+            self.bucket = self.mpc.dist.GradBucket(self.params, early=lambda p: id(p) not in self._late)
 
     def exchange(self):
         """The path's one exchange step: mean of the gradients over the data-parallel ranks, one all-reduce of the
         flat fp32 bucket (16.5 MB part-seg / 34.1 MB classifier) with the 1/world folded into the reduction."""
         if self.wl.train and self.world > 1:
-            self.bucket.all_reduce(self.world)
+            if not getattr(self, "_exchanged", False):
+                self.bucket.all_reduce(self.world)
             self.bucket.attach()
 
     def make_optimizer(self):
@@ -393,9 +433,15 @@ class GraphedStep:
     performs exactly one forward(+backward) and one full sampling chain's worth of rounds; what it returns belongs to a
     batch passed to an EARLIER call (`ahead` steps of pipeline latency, primed by the first batch)."""
 
-    def __init__(self, step, inputs, starts, ahead=2):
+    def __init__(self, step, inputs, starts, ahead=2, one_graph=False):
         self.step = step
         self.ahead = ahead
+        # one_graph: the gradient all-reduce (NCCL, captured) and the optimiser step are part of the step graph -- no host
+        # round trip between backward, exchange and optimiser
+        self.one_graph = bool(one_graph) and step.wl.train and step.world > 1
+        if self.one_graph:
+            step.overlap = True
+            step.comm = torch.cuda.Stream()
         wl, ops = step.wl, step.mpc.ops
         self.inputs = [t.clone() for t in inputs]
         self.starts = [s.clone() for s in starts]
@@ -425,8 +471,12 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.res = self._part()
+            if self.one_graph:
+                step.exchange()
+                if step.opt is not None:
+                    step.opt.step()
         self.gopt = None
-        if step.opt is not None:
+        if step.opt is not None and not self.one_graph:
             if step.world > 1:
                 step.bucket.attach()  # the optimiser reads the averaged gradients from the bucket views
             self.gopt = torch.cuda.CUDAGraph()
@@ -485,6 +535,8 @@ class GraphedStep:
         for d, s in zip(self.starts, starts):
             d.copy_(s, non_blocking=True)
         self.graph.replay()
+        if self.one_graph:
+            return self.res
         self.step.exchange()
         if self.gopt is not None:
             self.gopt.replay()
@@ -800,14 +852,24 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
     run_step = step
     graphed = False
     if not args.no_graph:
+        one_graph = not args.no_graph_allreduce
         try:
-            run_step = GraphedStep(step, inputs, device_starts(), ahead=args.fps_ahead)
+            run_step = GraphedStep(step, inputs, device_starts(), ahead=args.fps_ahead, one_graph=one_graph)
             graphed = True
-        except Exception as e:  # noqa: BLE001 -- report and fall back to eager launches
-            print("bench.py: CUDA graph capture failed (%s: %s); timing eager launches" % (type(e).__name__, e),
-                  file=sys.stderr)
+        except Exception as e:  # noqa: BLE001 -- report and fall back
+            print("bench.py: CUDA graph capture failed (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
             torch.cuda.synchronize()
+            step.overlap = False
             run_step = step
+            if one_graph and world > 1:  # second attempt with the exchange outside the graph
+                try:
+                    run_step = GraphedStep(step, inputs, device_starts(), ahead=args.fps_ahead, one_graph=False)
+                    graphed = True
+                except Exception as e2:  # noqa: BLE001
+                    print("bench.py: capture without the collective failed too (%s: %s); timing eager launches"
+                          % (type(e2).__name__, e2), file=sys.stderr)
+                    torch.cuda.synchronize()
+                    run_step = step
     for _ in range(2):
         run_step(inputs, device_starts())
 
@@ -865,7 +927,9 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
     rec = None
     if rank == 0:
         par = "single GPU" if world == 1 else (
-            "dp%d (batch shards; one all-reduce of the flat fp32 gradient bucket)" % world if wl.train
+            "dp%d (batch shards; the flat fp32 gradient bucket all-reduced in two parts, the late layers' part beside the "
+            "encoder's backward, captured in the step graph)" % world if (wl.train and getattr(run_step, "one_graph", False))
+            else "dp%d (batch shards; one all-reduce of the flat fp32 gradient bucket)" % world if wl.train
             else "dp%d (batch shards; no collective in forward)" % world)
         rec = {
             "metric": METRIC if wl.key == HEADLINE else "point clouds/s (%s)" % wl.key,
@@ -961,6 +1025,9 @@ def main():
                     "cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
+    ap.add_argument("--no-graph-allreduce", action="store_true", help="N > 1: keep the NCCL gradient all-reduce and the "
+                    "optimiser step outside the step graph (default: both are captured in it, and the all-reduce of the "
+                    "late layers' gradients runs on a communication stream beside the encoder's backward)")
     ap.add_argument("--fps-ahead", type=int, default=2, choices=[0, 1, 2], help="software pipeline depth of the FPS chain "
                     "(see GraphedStep): 0 = inside the forward it belongs to, 1 = one batch ahead, 2 = two batches ahead "
                     "in two segments")

@@ -26,34 +26,55 @@ class GradBucket:
     backward: which parameters are used does not depend on the data, so every rank builds the same layout; the
     reference's constructed-but-unused sub-modules are left out on every rank alike)."""
 
-    def __init__(self, params, group=None):
-        self.params = [p for p in params if p.grad is not None]
-        if not self.params:
+    def __init__(self, params, group=None, early=None):
+        """early: optional predicate on a parameter -> True for the parameters whose gradients are complete EARLY in the
+        backward pass (the layers that run LAST in forward).  They are laid out first in the flat buffer, so that part 0
+        (= the early group) can be exchanged while the rest of the backward pass is still running; part 1 is the
+        remainder."""
+        used = [p for p in params if p.grad is not None]
+        if not used:
             raise ValueError("GradBucket needs parameters that already hold a gradient (run one backward first)")
+        first = [p for p in used if early is not None and early(p)]
+        rest = [p for p in used if not (early is not None and early(p))]
+        self.params = first + rest
+        self.n_early = len(first)
         dev = self.params[0].device
         self.group = group
         self.numel = sum(p.numel() for p in self.params)
+        self.split = sum(p.numel() for p in first)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
-    def pack(self):
-        """Copy the freshly written gradients into the bucket (multi-tensor copy: ~1 launch per 100 tensors)."""
-        torch._foreach_copy_(self.views, [p.grad for p in self.params])
+    def _range(self, part):
+        if part is None:
+            return 0, len(self.params), self.flat
+        if part == 0:
+            return 0, self.n_early, self.flat[:self.split]
+        return self.n_early, len(self.params), self.flat[self.split:]
 
-    def all_reduce(self, world=None):
-        """Mean over the ranks, in place in the bucket.  No-op for a single rank."""
+    def pack(self, part=None):
+        """Copy the freshly written gradients into the bucket (multi-tensor copy: ~1 launch per 100 tensors)."""
+        lo, hi, _ = self._range(part)
+        if hi > lo:
+            torch._foreach_copy_(self.views[lo:hi], [p.grad for p in self.params[lo:hi]])
+
+    def all_reduce(self, world=None, part=None):
+        """Mean over the ranks, in place in the bucket (or in one of its two parts).  No-op for a single rank."""
         if world is None:
             world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world <= 1:
             return
-        if self.flat.is_cuda:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        flat = self._range(part)[2]
+        if flat.numel() == 0:
+            return
+        if flat.is_cuda:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
         else:  # gloo has no AVG
-            dist.all_reduce(self.flat, group=self.group)
-            self.flat.div_(float(world))
+            dist.all_reduce(flat, group=self.group)
+            flat.div_(float(world))
 
     def attach(self):
         """Point every p.grad at its slice of the (averaged) bucket."""

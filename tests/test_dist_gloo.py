@@ -31,11 +31,23 @@ def _worker(rank, world, port, out_dir):
         p.grad = g.clone()
     bucket = mpc.dist.GradBucket(list(twin.parameters()) + list(twin_unused.parameters()))
     bucket.exchange(world)
+    # two-part exchange (the bias as the "early" group): part 0 first, part 1 later, same result
+    twin2 = torch.nn.Linear(5, 3)
+    for p, g in zip(twin2.parameters(), local):
+        p.grad = g.clone()
+    b2 = mpc.dist.GradBucket(list(twin2.parameters()), early=lambda p: p.dim() == 1)
+    b2.pack(0)
+    b2.all_reduce(world, 0)
+    b2.pack(1)
+    b2.all_reduce(world, 1)
+    b2.attach()
     n = mpc.dist.allreduce_mean_grads(list(lin.parameters()) + list(unused.parameters()), world)
     torch.save({"n": n, "local": local, "avg": [p.grad.clone() for p in lin.parameters()], "shard": (lo, hi),
                 "bucket": [p.grad.clone() for p in twin.parameters()], "bucket_numel": bucket.numel,
                 "bucket_views": all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views)),
-                "bucket_skipped_unused": all(p.grad is None for p in twin_unused.parameters())},
+                "bucket_skipped_unused": all(p.grad is None for p in twin_unused.parameters()),
+                "two_part": [p.grad.clone() for p in twin2.parameters()], "two_part_split": (b2.split, b2.n_early,
+                                                                                              b2.params[0].dim())},
                os.path.join(out_dir, "r%d.pt" % rank))
     dist.destroy_process_group()
 
@@ -63,4 +75,8 @@ def test_gradient_exchange_gloo_world2(tmp_path):
     for r in (r0, r1):
         assert r["bucket_numel"] == 5 * 3 + 3 and r["bucket_views"] and r["bucket_skipped_unused"]
         for b, a in zip(r["bucket"], r0["avg"]):
+            torch.testing.assert_close(b, a)
+        # the two-part layout puts the early group (here: the bias, 3 elements) first and exchanges to the same result
+        assert r["two_part_split"] == (3, 1, 1)
+        for b, a in zip(r["two_part"], r0["avg"]):
             torch.testing.assert_close(b, a)

@@ -912,10 +912,36 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
     barrier()
     t_timed1 = sampler.mark() if sampler else None
 
-    t = torch.tensor([dev_ms, t_e2e * 1e3], dtype=torch.float64, device=device)
+    # ---- the same step with the sampling chain inside the forward it belongs to (no pipelining across steps), so the line
+    # carries both numbers and the pipelined one can be read against it; headline workload only, outside the clock window
+    inline_ms = 0.0
+    if graphed and args.fps_ahead and wl.key == HEADLINE and world == 1 and not args.no_inline_sampling_arm:
+        try:
+            plain = GraphedStep(step, inputs, device_starts(), ahead=0, one_graph=getattr(run_step, "one_graph", False))
+            for _ in range(2):
+                plain(inputs, device_starts())
+            barrier()
+            pe = []
+            for _ in range(args.steps):
+                flush.zero_()
+                starts = device_starts()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                plain(inputs, starts)
+                b.record()
+                pe.append((a, b))
+            barrier()
+            inline_ms = sum(a.elapsed_time(b) for a, b in pe)
+            del plain
+        except Exception as e:  # noqa: BLE001 -- the comparison arm is optional; the headline number does not depend on it
+            print("bench.py: sampling-in-forward arm failed (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
+            torch.cuda.synchronize()
+            inline_ms = 0.0
+
+    t = torch.tensor([dev_ms, t_e2e * 1e3, inline_ms], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, inline_ms = float(t[0]), float(t[1]), float(t[2])
     clouds = world * B * args.steps
     h2d = sum(t.numel() * t.element_size() for t in host) + sum(8 * B for _ in wl.fps_sizes)
     d2h = res_host.numel() * res_host.element_size()
@@ -953,6 +979,11 @@ def run_workload(wl, args, mpc, device, rank, local, world, sampler):
             "last_result": float(res_host.float().reshape(-1)[0]),
         }
         rec["clocks_whole_workload"] = sampler.summary(t_begin, t_timed1) if sampler else None
+        if inline_ms > 0:
+            rec["method"]["sampling_in_forward_arm"] = {
+                "value": clouds / (inline_ms / 1e3), "unit": UNIT, "ms_per_step": inline_ms / args.steps,
+                "note": "same step, same graph replay and timing rules, with every FPS chain inside the forward that uses it "
+                        "(--fps-ahead 0); measured after the timed region, N=1 only"}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(wl, wl.cpu_steps, 1)
             rec["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -1028,6 +1059,8 @@ def main():
     ap.add_argument("--no-graph-allreduce", action="store_true", help="N > 1: keep the NCCL gradient all-reduce and the "
                     "optimiser step outside the step graph (default: both are captured in it, and the all-reduce of the "
                     "late layers' gradients runs on a communication stream beside the encoder's backward)")
+    ap.add_argument("--no-inline-sampling-arm", action="store_true", help="skip the extra N=1 measurement of the headline "
+                    "step with the FPS chain inside the forward (reported as method.sampling_in_forward_arm)")
     ap.add_argument("--fps-ahead", type=int, default=2, choices=[0, 1, 2], help="software pipeline depth of the FPS chain "
                     "(see GraphedStep): 0 = inside the forward it belongs to, 1 = one batch ahead, 2 = two batches ahead "
                     "in two segments")

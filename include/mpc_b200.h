@@ -371,12 +371,19 @@ int mpc_umbrella_features_f32(const float* xyz, const int64_t* idx, int64_t ldk,
  * kernels records a clock64() timeline per warp role (producer / splitter / MMA / epilogue: 256 slots each).
  * Pass NULL to switch it off (the default).  Process-global. */
 int mpc_debug_trace_buffer(void* device_buffer);
-/* Debug facility: launch-geometry knobs of the streaming BatchNorm kernels (0 restores the built-in default).
- * id 0: elementwise CTAs per SM, 1: column-reduction CTAs per SM, 2: float4 per thread the elementwise grid is sized
- * for, 3: non-zero forces the grid-wide FPS variant for every cloud above 8192 points (parity tests of that variant
- * at sizes the CPU oracle finishes), 4: feature-space kNN variant (1 = never the register-tiled kernel), 5: KB of shared-memory padding of
- * that kernel (occupancy experiments).
- * Process-global; used by scratch/bench_bn.py to pick the defaults. */
+/* Debug facility: kernel-variant and launch-geometry knobs (0 restores the built-in default).  Every value gives the
+ * same results except the two timing experiments of id 4 marked below.
+ * id 0: elementwise CTAs per SM of the streaming BatchNorm kernels, 1: their column-reduction CTAs per SM, 2: float4
+ *       per thread their elementwise grid is sized for (scratch/bench_bn.py picked the defaults);
+ * id 3: non-zero forces the grid-wide FPS variant for every cloud above 8192 points (parity tests of that variant at
+ *       sizes the CPU oracle finishes);
+ * id 4: feature-space kNN: 1 = never the register-tiled kernel; >= 100 = mpc_knn_tc_f32 timing experiments that SKIP
+ *       WORK AND RETURN WRONG RESULTS (101: no selection, 102: no MMAs; scratch/knn_tc_time.py only);
+ * id 5: KB of shared-memory padding of the register-tiled kNN kernel (occupancy experiments) / CTAs per SM cap of the
+ *       grouped transition gather;
+ * id 6: smallest N that takes the bucket-pruned FPS variant (default 8193; < 0: never);
+ * id 7: non-zero forces the ungrouped transition gather kernel.
+ * Process-global. */
 int mpc_debug_set_knob(int id, int64_t value);
 
 #ifdef __cplusplus

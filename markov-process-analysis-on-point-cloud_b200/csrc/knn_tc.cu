@@ -73,21 +73,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 
-// ascending list, strict <: candidates arrive in ascending index order, so equal keys keep the lower index first
+// ascending list, strict <: candidates arrive in ascending index order, so equal keys keep the lower index first.
+// The caller guarantees d < ld[LIST - 1] (the insertion threshold is at most the last entry).  Select form: with
+// c[p] = d < ld[p] (monotone over a sorted list) slot p takes its lower neighbour where c[p - 1], the new pair where
+// only c[p], and keeps its own otherwise -- 16 independent compares and 2 selects per slot and array, no dependent
+// swap chain (the selection warps run one per scheduler, so a chain's latency is not hidden by anything).
 __device__ __forceinline__ void list_insert(float (&ld)[LIST], int (&li)[LIST], float d, int n) {
-    ld[LIST - 1] = d;
-    li[LIST - 1] = n;
+    bool up = d < ld[LIST - 1];
 #pragma unroll
     for (int p = LIST - 1; p > 0; --p) {
-        if (ld[p] < ld[p - 1]) {
-            const float td = ld[p];
-            ld[p] = ld[p - 1];
-            ld[p - 1] = td;
-            const int ti = li[p];
-            li[p] = li[p - 1];
-            li[p - 1] = ti;
-        }
+        const bool below = d < ld[p - 1];
+        ld[p] = below ? ld[p - 1] : (up ? d : ld[p]);
+        li[p] = below ? li[p - 1] : (up ? n : li[p]);
+        up = below;
     }
+    ld[0] = up ? d : ld[0];
+    li[0] = up ? n : li[0];
 }
 
 #define KNN_TRACE(role, j, k)                                                                            \
@@ -297,18 +298,28 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
                 // knock it out, next minimum.  Most slabs that get here hold one candidate for one or two of the warp's
                 // 32 queries.
                 while (dmin < thr) {
-                    int pos = 31;
+                    // position of the minimum: four independent 8-column chains, lowest column wins
+                    int pa = 32, pb = 32, pc = 32, pd = 32;
 #pragma unroll
-                    for (int i = 30; i >= 0; --i) pos = __uint_as_float(v[i]) == dmin ? i : pos;
+                    for (int i = 7; i >= 0; --i) {
+                        pa = __uint_as_float(v[i]) == dmin ? i : pa;
+                        pb = __uint_as_float(v[8 + i]) == dmin ? 8 + i : pb;
+                        pc = __uint_as_float(v[16 + i]) == dmin ? 16 + i : pc;
+                        pd = __uint_as_float(v[24 + i]) == dmin ? 24 + i : pd;
+                    }
+                    const int pos = min(min(pa, pb), min(pc, pd));
                     list_insert(ld, li, dmin, n0 + c0 + pos);
                     thr = fminf(ld[LIST - 1], ld[K - 1] + 2.5f * eps);
-                    float nmin = __int_as_float(0x7f800000);
+                    float m[8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i == pos) v[i] = 0x7f800000u;  // +inf
-                        nmin = fminf(nmin, __uint_as_float(v[i]));
+                    for (int g = 0; g < 8; ++g) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (g * 4 + e == pos) v[g * 4 + e] = 0x7f800000u;  // +inf
+                        m[g] = fminf(fminf(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1])),
+                                     fminf(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])));
                     }
-                    dmin = nmin;
+                    dmin = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
                 }
             }
             tc_fence_before();

@@ -153,6 +153,13 @@ def test_reduction_scratch_is_left_zero(mpc):
         assert float(buf.abs().sum()) == 0.0, key
 
 
+def _sum_close(a, b, rtol, atol, msg=None):
+    """Comparison for gradients that are long fp32 sums (weight gradients, gradients summed over rows): two correct
+    evaluations differ by ~1e-6 of the tensor's largest element (accumulation order -- the split-K reduction of the
+    weight-gradient GEMM is ordered by arrival), so the absolute tolerance carries a term relative to that scale."""
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol + 1e-5 * float(b.abs().max()), msg=msg)
+
+
 @pytest.mark.parametrize("M,C,padded", [(1, 2, False), (1000, 50, False), (65536, 50, True), (333, 13, True), (64, 300, False)])
 def test_smooth_cross_entropy_matches_reference_chain(mpc, M, C, padded):
     """Fused label-smoothed CE vs the reference's op chain (R/models/repsurf/pointnet2_part_seg_msg.py:159-180) on
@@ -195,9 +202,9 @@ def test_deferred_weight_gradients_match(mpc):
                      + [xi.grad.clone()])
     mpc.ops.set_defer_wgrad(False)
     for a, b in zip(grads[0], grads[1]):
-        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4)
+        _sum_close(a, b, rtol=1e-3, atol=1e-4)
     for a, b in zip(grads[1], grads[2]):
-        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4)
+        _sum_close(a, b, rtol=1e-3, atol=1e-4)
 
 
 @pytest.mark.parametrize("Np", [256, 375, 1000])  # clouds that are / are not a whole number of 128-row GEMM tiles
@@ -221,10 +228,10 @@ def test_split_projection_equals_concatenated_projection(mpc, train, Np):
     torch.cuda.synchronize()
     torch.testing.assert_close(y1, y2, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(a1.grad, a2.grad, rtol=1e-3, atol=1e-5)
-    torch.testing.assert_close(g1.grad, g2.grad, rtol=1e-3, atol=1e-4)
+    _sum_close(g1.grad, g2.grad, rtol=1e-3, atol=1e-4)
     for (k, p), (_, q) in zip(lin.named_parameters(), ref.named_parameters()):
         if q.grad is not None:
-            torch.testing.assert_close(p.grad, q.grad, rtol=1e-3, atol=1e-4, msg=k)
+            _sum_close(p.grad, q.grad, rtol=1e-3, atol=1e-4, msg=k)
     if train:
         torch.testing.assert_close(lin.norm2.running_var, ref.norm2.running_var, rtol=1e-5, atol=1e-6)
 
@@ -254,7 +261,7 @@ def test_bn_backward_reads_strided_grad_rows(mpc):
             mpc.ops._grad_rows = old
 
     for a, b in zip(run(False), run(True)):
-        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4)
+        _sum_close(a, b, rtol=1e-3, atol=1e-4)
 
 
 @pytest.mark.parametrize("M,K,N,res", [(4096, 64, 64, True), (1000, 128, 256, False), (16384, 512, 1024, True),
